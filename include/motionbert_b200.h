@@ -1,0 +1,138 @@
+/* motionbert_b200.h -- C ABI of the B200-native DSTformer encoder (libmotionbert_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of Walter0807/MotionBERT: the forward pass of
+ *     lib/model/DSTformer.py:269-361   class DSTformer  (.forward / .get_representation)
+ * Everything below replaces, for that path, the chain of torch.nn calls the reference issues
+ * (nn.Linear / nn.LayerNorm / nn.GELU / softmax / matmul: DSTformer.py:79-85,138-200,239-249,329-358).
+ * The reference has no native/FFI layer of its own; the binding a maintainer adds is
+ * the ctypes stub shown in INTEGRATION.md (shipped as motionbert_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain C types only; every device buffer is allocated and owned by the CALLER (PyTorch's caching
+ *     allocator in the Python host); the library allocates no device memory and keeps no reference to
+ *     activations after a call returns.  Host-side immutable state (TMA tensor maps, offsets) lives in
+ *     the opaque handle.
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     no internal synchronisation, CUDA-graph capturable.
+ *   - return 0 on success, negative MbStatus otherwise; never throws, never exits.
+ *     mb_last_error() returns a thread-local message for the last failing call on this thread.
+ *   - thread-safe: distinct handles may be used concurrently from different host threads / devices
+ *     (nn.DataParallel drives one replica per GPU from its own Python thread).
+ *   - there is NO CPU fallback: on a device that is not sm_100 every compute entry point fails with
+ *     MB_ERR_ARCH.
+ */
+#ifndef MOTIONBERT_B200_H_
+#define MOTIONBERT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+typedef enum MbStatus {
+    MB_OK = 0,
+    MB_ERR_INVALID = -1,    /* bad argument / unsupported shape (F > maxlen, J mismatch, C % 256 != 0 ...) */
+    MB_ERR_NULL = -2,       /* required pointer is NULL                                                    */
+    MB_ERR_ALIGN = -3,      /* device pointer not 16-byte aligned                                          */
+    MB_ERR_ARCH = -4,       /* device is not compute capability 10.x                                        */
+    MB_ERR_CUDA = -5,       /* a CUDA runtime / driver call failed (message has cudaGetErrorString)         */
+    MB_ERR_WORKSPACE = -6   /* workspace too small                                                          */
+} MbStatus;
+
+/* Arithmetic mode of the GEMM-shaped work (operands are always bf16 on the tensor cores, fp32 accumulate). */
+typedef enum MbMath {
+    MB_MATH_BF16X3 = 0,     /* x = hi + lo split, 3 MMA passes: fp32 parity (~1e-5 rel)  -- default, "fp32" configs */
+    MB_MATH_BF16 = 1        /* single bf16 pass: for the reference's bf16/AMP-style training configs             */
+} MbMath;
+
+/* Mirrors the constructor arguments of DSTformer.__init__ (DSTformer.py:270-273) as the factory passes
+ * them (lib/utils/learning.py:83-85).  hidden = int(dim_feat * mlp_ratio) (DSTformer.py:232). */
+typedef struct MbDesc {
+    int32_t dim_in;       /* 3                                    */
+    int32_t dim_out;      /* 3                                    */
+    int32_t dim_feat;     /* C: 512 (base) / 256 (Lite)           */
+    int32_t dim_rep;      /* 512                                  */
+    int32_t depth;        /* 5                                    */
+    int32_t num_heads;    /* 8   (head_dim = C / heads in {32,64})*/
+    int32_t hidden;       /* 1024                                 */
+    int32_t num_joints;   /* 17                                   */
+    int32_t maxlen;       /* 243                                  */
+    float eps;            /* LayerNorm eps, 1e-6 from the factory */
+    float qk_scale;       /* 0 => head_dim ** -0.5 (DSTformer.py:94) */
+    int32_t math;         /* MbMath                               */
+} MbDesc;
+
+typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
+
+/* flags for mb_forward */
+#define MB_FLAG_REF_GEMM   0x1u   /* TEST ONLY: CUDA-core reference GEMM instead of tcgen05           */
+#define MB_FLAG_REF_ATTN_T 0x2u   /* TEST ONLY: CUDA-core reference temporal attention                */
+
+int mb_version(void);
+const char* mb_last_error(void);
+
+/* Create / destroy the host-side handle for one module replica on the CURRENT device. */
+int mb_create(const MbDesc* desc, MbEncoder** out);
+void mb_destroy(MbEncoder* enc);
+
+/* Parameter tree: the 4 + depth*2*24 + 6 + depth*2 tensors of DSTformer.state_dict() in registration
+ * order (DSTformer.py:276-311).  mb_param_info lets the host verify names and sizes. */
+int mb_param_count(const MbEncoder* enc);
+int mb_param_info(const MbEncoder* enc, int index, char* name, int name_cap, int64_t* numel);
+
+/* Packed weights: bf16 hi/lo planes of every nn.Linear weight with the preceding LayerNorm's affine
+ * folded in, plus the small fp32 vectors.  Re-run after every optimizer step / load_state_dict.
+ *   params : host array of mb_param_count() device pointers (fp32, contiguous) in state_dict order. */
+int mb_packed_bytes(const MbEncoder* enc, size_t* bytes);
+int mb_pack_weights(MbEncoder* enc, const float* const* params, void* packed, void* stream);
+
+/* Scratch for one forward call of shape (B, F, num_joints, dim_in). */
+int mb_workspace_bytes(const MbEncoder* enc, int B, int F, size_t* bytes);
+
+/* DSTformer.forward (DSTformer.py:329-358).
+ *   x   : (B, F, J, dim_in) fp32 contiguous, device
+ *   out : (B, F, J, dim_out) fp32 or NULL   -- forward(x)
+ *   rep : (B, F, J, dim_rep) fp32 or NULL   -- get_representation(x) (DSTformer.py:360-361)
+ *   drop_path_scale : NULL (eval / rate 0: the shipped configs) or device fp32 [depth*2*4][B*F] per-frame
+ *         DropPath factors mask/keep_prob (lib/model/drop.py:17-32), one vector per residual sublayer
+ *         in call order (st block: S-attn, S-mlp, T-attn, T-mlp; then ts block: T-attn, T-mlp, S-attn, S-mlp). */
+int mb_forward(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
+               const float* drop_path_scale, void* workspace, size_t workspace_bytes, int B, int F,
+               uint32_t flags, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): H2D of x, forward, D2H of out/rep on `stream`,
+ * synchronised before returning.  `workspace` must additionally hold the device copies:
+ * mb_workspace_bytes_host() bytes. */
+int mb_workspace_bytes_host(const MbEncoder* enc, int B, int F, int want_out, int want_rep, size_t* bytes);
+int mb_forward_host(MbEncoder* enc, const void* packed, const float* x_host, float* out_host, float* rep_host,
+                    void* workspace, size_t workspace_bytes, int B, int F, uint32_t flags, void* stream);
+
+/* Number of kernels one mb_forward call launches for this (B, F) (for bench.py's gpu_launches). */
+int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags);
+
+/* ------------------------------------------------------------------ kernel-level test hooks ----------
+ * Exercise one kernel in isolation so tests/ can localise a failure on the device.  Not used by the
+ * product path. */
+
+/* y[M,N] = epilogue(A[M,K] . W[N,K]^T): A, W fp32 on device; scratch >= mb_test_linear_scratch_bytes().
+ * mode: 0 LN-folded split (returns hi+lo as fp32), 1 LN+GELU split, 2 residual (+stats), 3 LN+tanh, 4 bias.
+ * gamma/beta (LN modes) and resid (mode 2) may be NULL otherwise.  stats_out (mode 2): [M][N/256][3]. */
+int mb_test_linear_scratch_bytes(int M, int N, int K, size_t* bytes);
+int mb_test_linear(int mode, int math, int use_ref, int M, int N, int K, const float* A, const float* W,
+                   const float* bias, const float* gamma, const float* beta, const float* resid, float eps,
+                   float* y, float* stats_out, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Attention over a fp32 qkv buffer [B*F*J, 3C] -> y fp32 [B*F*J, C].  temporal=1: forward_temporal
+ * (DSTformer.py:188-200), 0: forward_spatial (:178-186). */
+int mb_test_attention_scratch_bytes(int B, int F, int J, int C, size_t* bytes);
+int mb_test_attention(int temporal, int math, int use_ref, int B, int F, int J, int C, int H, const float* qkv,
+                      float* y, void* scratch, size_t scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOTIONBERT_B200_H_ */

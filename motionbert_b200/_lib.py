@@ -1,0 +1,84 @@
+"""ctypes binding of libmotionbert_b200.so (the C ABI in include/motionbert_b200.h).
+
+This is the stub a maintainer of the reference would add.  It fails loudly
+when the CUDA library is missing: there is no CPU or PyTorch fallback behind it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmotionbert_b200.so")
+
+MB_MATH_BF16X3 = 0
+MB_MATH_BF16 = 1
+MB_FLAG_REF_GEMM = 0x1
+MB_FLAG_REF_ATTN_T = 0x2
+
+# every symbol include/motionbert_b200.h declares
+EXPORTS = [
+    "mb_version", "mb_last_error", "mb_create", "mb_destroy", "mb_param_count", "mb_param_info",
+    "mb_packed_bytes", "mb_pack_weights", "mb_workspace_bytes", "mb_forward", "mb_workspace_bytes_host",
+    "mb_forward_host", "mb_forward_launch_count", "mb_test_linear_scratch_bytes", "mb_test_linear",
+    "mb_test_attention_scratch_bytes", "mb_test_attention",
+]
+
+
+class MbDesc(C.Structure):
+    _fields_ = [
+        ("dim_in", C.c_int32), ("dim_out", C.c_int32), ("dim_feat", C.c_int32), ("dim_rep", C.c_int32),
+        ("depth", C.c_int32), ("num_heads", C.c_int32), ("hidden", C.c_int32), ("num_joints", C.c_int32),
+        ("maxlen", C.c_int32), ("eps", C.c_float), ("qk_scale", C.c_float), ("math", C.c_int32),
+    ]
+
+
+class MbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; raises if it has not been built (python -m motionbert_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MbError(f"{LIB_PATH} is missing: build it with `python -m motionbert_b200.build` "
+                      "(there is no CPU / PyTorch fallback for the DSTformer hot path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u32, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
+    fp = C.c_void_p   # device / host float* passed as raw addresses
+    lib.mb_version.restype = i32
+    lib.mb_last_error.restype = C.c_char_p
+    lib.mb_create.argtypes = [C.POINTER(MbDesc), C.POINTER(vp)]
+    lib.mb_destroy.argtypes = [vp]
+    lib.mb_destroy.restype = None
+    lib.mb_param_count.argtypes = [vp]
+    lib.mb_param_info.argtypes = [vp, i32, C.c_char_p, i32, C.POINTER(C.c_int64)]
+    lib.mb_packed_bytes.argtypes = [vp, C.POINTER(sz)]
+    lib.mb_pack_weights.argtypes = [vp, C.POINTER(vp), vp, vp]
+    lib.mb_workspace_bytes.argtypes = [vp, i32, i32, C.POINTER(sz)]
+    lib.mb_forward.argtypes = [vp, vp, fp, fp, fp, fp, vp, sz, i32, i32, u32, vp]
+    lib.mb_workspace_bytes_host.argtypes = [vp, i32, i32, i32, i32, C.POINTER(sz)]
+    lib.mb_forward_host.argtypes = [vp, vp, fp, fp, fp, vp, sz, i32, i32, u32, vp]
+    lib.mb_forward_launch_count.argtypes = [vp, i32, u32]
+    lib.mb_test_linear_scratch_bytes.argtypes = [i32, i32, i32, C.POINTER(sz)]
+    lib.mb_test_linear.argtypes = [i32, i32, i32, i32, i32, i32, fp, fp, fp, fp, fp, fp, C.c_float, fp, fp, vp, sz, vp]
+    lib.mb_test_attention_scratch_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
+    lib.mb_test_attention.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, fp, fp, vp, sz, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("mb_last_error", "mb_destroy"):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc < 0:
+        msg = load().mb_last_error().decode("utf-8", "replace")
+        raise MbError(f"{what or 'libmotionbert_b200'} failed ({rc}): {msg}")
+    return rc

@@ -1,0 +1,920 @@
+// Host side of libmotionbert_b200.so: the C ABI declared in include/motionbert_b200.h.
+// Builds the launch plan of one DSTformer forward (DSTformer.py:329-358) out of the kernels in
+// gemm_tc.cuh / attn_t_tc.cuh / simt_kernels.cuh.  No device allocation, no synchronisation
+// (except mb_forward_host), everything on the caller's stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/motionbert_b200.h"
+#include "attn_t_tc.cuh"
+#include "gemm_tc.cuh"
+#include "simt_kernels.cuh"
+
+using namespace mb;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return fail(MB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+#define LAUNCH_CHECK(what)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess) return fail(MB_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e__)); \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------ driver entry
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// bf16 tensor map of rank `rank`; dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1.
+static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                     const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if (reinterpret_cast<uintptr_t>(base) & 15) return fail(MB_ERR_ALIGN, "tensor map base not 16-byte aligned");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_el[i - 1] * 2;   // bytes
+    }
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------ per-device init
+struct DevInfo {
+    int sms = 0;
+    int cc_major = 0;
+    bool attrs_set = false;
+};
+static std::mutex g_dev_mu;
+static DevInfo g_dev[64];
+
+template <typename K>
+static cudaError_t set_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+static int device_init(int* dev_out, DevInfo* info_out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(MB_ERR_INVALID, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DevInfo& d = g_dev[dev];
+    if (!d.attrs_set) {
+        CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (d.cc_major != 10)
+            return fail(MB_ERR_ARCH, "device %d is compute capability %d.x; this library is sm_100a only (no fallback)",
+                        dev, d.cc_major);
+#define SET_GEMM(P, E) CUDA_TRY(set_smem(gemm_tc_kernel<P, E>, GemmCfg<P>::SMEM_BYTES))
+        SET_GEMM(3, EPI_LN_SPLIT); SET_GEMM(3, EPI_LN_GELU_SPLIT); SET_GEMM(3, EPI_RESID);
+        SET_GEMM(3, EPI_LN_TANH_F32); SET_GEMM(3, EPI_BIAS_F32);
+        SET_GEMM(1, EPI_LN_SPLIT); SET_GEMM(1, EPI_LN_GELU_SPLIT); SET_GEMM(1, EPI_RESID);
+        SET_GEMM(1, EPI_LN_TANH_F32); SET_GEMM(1, EPI_BIAS_F32);
+#undef SET_GEMM
+        CUDA_TRY(set_smem(attn_t_tc_kernel<64, 3>, AttnCfg<64, 3>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_t_tc_kernel<32, 3>, AttnCfg<32, 3>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_t_tc_kernel<64, 1>, AttnCfg<64, 1>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_t_tc_kernel<32, 1>, AttnCfg<32, 1>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s_kernel<64>, 200 * 1024));
+        CUDA_TRY(set_smem(attn_s_kernel<32>, 200 * 1024));
+        CUDA_TRY(set_smem(attn_t_ref_kernel<64>, 200 * 1024));
+        CUDA_TRY(set_smem(attn_t_ref_kernel<32>, 200 * 1024));
+        d.attrs_set = true;
+    }
+    *dev_out = dev;
+    *info_out = d;
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------ handle
+enum LinOp { L_QKV_S = 0, L_PROJ_S, L_FC1_S, L_FC2_S, L_QKV_T, L_PROJ_T, L_FC1_T, L_FC2_T, L_PER_BLOCK };
+
+struct LinearPack {
+    int N = 0, K = 0;
+    bool ln = false;
+    int p_w = -1, p_b = -1, p_g = -1, p_beta = -1;   // indices into the parameter list
+    size_t off_hi = 0, off_lo = 0, off_c = 0, off_s = 0;   // byte offsets into the packed buffer
+    CUtensorMap tmap;                                   // valid for `packed_ptr`
+};
+
+struct ActBuf {
+    float* x;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    float* stats;
+    CUtensorMap tmap;   // A-operand map over (hi, lo)
+};
+
+struct Plan {
+    const void* ws = nullptr;
+    int B = 0, F = 0;
+    ActBuf act[4];
+    __nv_bfloat16* qkv = nullptr;   // planes [2][M][3C]
+    __nv_bfloat16* hid = nullptr;   // planes [2][M][hidden] (aliases qkv region)
+    __nv_bfloat16* ao = nullptr;    // planes [2][M][C]
+    float* rep_ws = nullptr;
+    CUtensorMap tm_hid, tm_ao, tm_q, tm_kv;
+};
+
+struct MbEncoder {
+    MbDesc d;
+    int device = 0;
+    DevInfo dev;
+    std::vector<std::string> names;
+    std::vector<int64_t> numels;
+    std::map<std::string, int> index;
+    std::vector<LinearPack> lin;   // 2*depth*8 + 1
+    size_t off_small[8] = {0};     // joints_w, joints_b, pos, temp, head_w, head_b, ts_w(base), ts_b(base)
+    size_t packed_bytes = 0;
+    const void* packed_ptr = nullptr;
+    std::mutex mu;
+    std::vector<Plan> plans;
+};
+
+static int passes_of(const MbDesc& d) { return d.math == MB_MATH_BF16 ? 1 : 3; }
+
+static void add_param(MbEncoder* e, const std::string& n, int64_t numel) {
+    e->index[n] = static_cast<int>(e->names.size());
+    e->names.push_back(n);
+    e->numels.push_back(numel);
+}
+
+static void build_param_list(MbEncoder* e) {
+    const MbDesc& d = e->d;
+    const int64_t C = d.dim_feat, hid = d.hidden, J = d.num_joints;
+    add_param(e, "temp_embed", static_cast<int64_t>(d.maxlen) * C);
+    add_param(e, "pos_embed", J * C);
+    add_param(e, "joints_embed.weight", C * d.dim_in);
+    add_param(e, "joints_embed.bias", C);
+    const char* streams[2] = {"blocks_st", "blocks_ts"};
+    for (int s = 0; s < 2; ++s)
+        for (int i = 0; i < d.depth; ++i) {
+            const std::string p = std::string(streams[s]) + "." + std::to_string(i) + ".";
+            for (const char* n : {"norm1_s", "norm1_t"}) {
+                add_param(e, p + n + ".weight", C);
+                add_param(e, p + n + ".bias", C);
+            }
+            for (const char* a : {"attn_s", "attn_t"}) {
+                add_param(e, p + a + ".proj.weight", C * C);
+                add_param(e, p + a + ".proj.bias", C);
+                add_param(e, p + a + ".qkv.weight", 3 * C * C);
+                add_param(e, p + a + ".qkv.bias", 3 * C);
+            }
+            for (const char* n : {"norm2_s", "norm2_t"}) {
+                add_param(e, p + n + ".weight", C);
+                add_param(e, p + n + ".bias", C);
+            }
+            for (const char* m : {"mlp_s", "mlp_t"}) {
+                add_param(e, p + m + ".fc1.weight", hid * C);
+                add_param(e, p + m + ".fc1.bias", hid);
+                add_param(e, p + m + ".fc2.weight", C * hid);
+                add_param(e, p + m + ".fc2.bias", C);
+            }
+        }
+    add_param(e, "norm.weight", C);
+    add_param(e, "norm.bias", C);
+    add_param(e, "pre_logits.fc.weight", static_cast<int64_t>(d.dim_rep) * C);
+    add_param(e, "pre_logits.fc.bias", d.dim_rep);
+    add_param(e, "head.weight", static_cast<int64_t>(d.dim_out) * d.dim_rep);
+    add_param(e, "head.bias", d.dim_out);
+    for (int i = 0; i < d.depth; ++i) {
+        add_param(e, "ts_attn." + std::to_string(i) + ".weight", 2 * 2 * C);
+        add_param(e, "ts_attn." + std::to_string(i) + ".bias", 2);
+    }
+}
+
+static void build_packed_layout(MbEncoder* e) {
+    const MbDesc& d = e->d;
+    const int C = d.dim_feat, hid = d.hidden;
+    e->lin.resize(2 * d.depth * L_PER_BLOCK + 1);
+    size_t off = 0;
+    auto place = [&](LinearPack& L, int N, int K, bool ln, const std::string& w, const std::string& b,
+                     const std::string& norm) {
+        L.N = N; L.K = K; L.ln = ln;
+        L.p_w = e->index.at(w);
+        L.p_b = e->index.at(b);
+        if (ln) {
+            L.p_g = e->index.at(norm + ".weight");
+            L.p_beta = e->index.at(norm + ".bias");
+        }
+        L.off_hi = off; off = align_up(off + static_cast<size_t>(N) * K * 2, 1024);
+        L.off_lo = off; off = align_up(off + static_cast<size_t>(N) * K * 2, 1024);
+        L.off_c = off;  off = align_up(off + static_cast<size_t>(N) * 4, 256);
+        L.off_s = off;  off = align_up(off + static_cast<size_t>(N) * 4, 256);
+    };
+    const char* streams[2] = {"blocks_st", "blocks_ts"};
+    for (int s = 0; s < 2; ++s)
+        for (int i = 0; i < d.depth; ++i) {
+            const std::string p = std::string(streams[s]) + "." + std::to_string(i) + ".";
+            LinearPack* L = &e->lin[(s * d.depth + i) * L_PER_BLOCK];
+            place(L[L_QKV_S], 3 * C, C, true, p + "attn_s.qkv.weight", p + "attn_s.qkv.bias", p + "norm1_s");
+            place(L[L_PROJ_S], C, C, false, p + "attn_s.proj.weight", p + "attn_s.proj.bias", "");
+            place(L[L_FC1_S], hid, C, true, p + "mlp_s.fc1.weight", p + "mlp_s.fc1.bias", p + "norm2_s");
+            place(L[L_FC2_S], C, hid, false, p + "mlp_s.fc2.weight", p + "mlp_s.fc2.bias", "");
+            place(L[L_QKV_T], 3 * C, C, true, p + "attn_t.qkv.weight", p + "attn_t.qkv.bias", p + "norm1_t");
+            place(L[L_PROJ_T], C, C, false, p + "attn_t.proj.weight", p + "attn_t.proj.bias", "");
+            place(L[L_FC1_T], hid, C, true, p + "mlp_t.fc1.weight", p + "mlp_t.fc1.bias", p + "norm2_t");
+            place(L[L_FC2_T], C, hid, false, p + "mlp_t.fc2.weight", p + "mlp_t.fc2.bias", "");
+        }
+    place(e->lin.back(), d.dim_rep, C, true, "pre_logits.fc.weight", "pre_logits.fc.bias", "norm");
+    const size_t small_sizes[8] = {static_cast<size_t>(C) * d.dim_in, static_cast<size_t>(C),
+                                   static_cast<size_t>(d.num_joints) * C, static_cast<size_t>(d.maxlen) * C,
+                                   static_cast<size_t>(d.dim_out) * d.dim_rep, static_cast<size_t>(d.dim_out),
+                                   static_cast<size_t>(d.depth) * 4 * C, static_cast<size_t>(d.depth) * 2};
+    for (int i = 0; i < 8; ++i) {
+        e->off_small[i] = off;
+        off = align_up(off + small_sizes[i] * 4, 256);
+    }
+    e->packed_bytes = off;
+}
+
+// ------------------------------------------------------------------------------------ ABI: basics
+extern "C" int mb_version(void) { return MB_ABI_VERSION; }
+extern "C" const char* mb_last_error(void) { return g_err; }
+
+static int check_desc(const MbDesc* d) {
+    if (!d) return fail(MB_ERR_NULL, "desc is NULL");
+    if (d->dim_feat <= 0 || d->dim_feat % 256 != 0 || d->dim_feat > 1024)
+        return fail(MB_ERR_INVALID, "dim_feat=%d unsupported (multiple of 256, <= 1024)", d->dim_feat);
+    if (d->hidden <= 0 || d->hidden % 256 != 0) return fail(MB_ERR_INVALID, "hidden=%d must be a multiple of 256", d->hidden);
+    if (d->dim_rep <= 0 || d->dim_rep % 256 != 0) return fail(MB_ERR_INVALID, "dim_rep=%d must be a multiple of 256", d->dim_rep);
+    if (d->num_heads <= 0 || d->dim_feat % d->num_heads != 0) return fail(MB_ERR_INVALID, "num_heads=%d does not divide dim_feat", d->num_heads);
+    const int hd = d->dim_feat / d->num_heads;
+    if (hd != 32 && hd != 64) return fail(MB_ERR_INVALID, "head_dim=%d unsupported (32 or 64)", hd);
+    if (d->num_joints < 1 || d->num_joints > 32) return fail(MB_ERR_INVALID, "num_joints=%d unsupported (1..32)", d->num_joints);
+    if (d->maxlen < 1 || d->maxlen > 256) return fail(MB_ERR_INVALID, "maxlen=%d unsupported (1..256)", d->maxlen);
+    if (d->dim_in < 1 || d->dim_in > 8) return fail(MB_ERR_INVALID, "dim_in=%d unsupported (1..8)", d->dim_in);
+    if (d->dim_out < 1 || d->depth < 1) return fail(MB_ERR_INVALID, "dim_out/depth must be positive");
+    if (d->math != MB_MATH_BF16X3 && d->math != MB_MATH_BF16) return fail(MB_ERR_INVALID, "unknown math mode %d", d->math);
+    if (!(d->eps > 0.f)) return fail(MB_ERR_INVALID, "eps must be positive");
+    return MB_OK;
+}
+
+extern "C" int mb_create(const MbDesc* desc, MbEncoder** out) {
+    if (!out) return fail(MB_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    int rc = check_desc(desc);
+    if (rc) return rc;
+    int dev;
+    DevInfo info;
+    rc = device_init(&dev, &info);
+    if (rc) return rc;
+    MbEncoder* e = new MbEncoder();
+    e->d = *desc;
+    e->device = dev;
+    e->dev = info;
+    build_param_list(e);
+    build_packed_layout(e);
+    *out = e;
+    return MB_OK;
+}
+
+extern "C" void mb_destroy(MbEncoder* enc) { delete enc; }
+
+extern "C" int mb_param_count(const MbEncoder* enc) {
+    if (!enc) return fail(MB_ERR_NULL, "enc is NULL");
+    return static_cast<int>(enc->names.size());
+}
+
+extern "C" int mb_param_info(const MbEncoder* enc, int index, char* name, int name_cap, int64_t* numel) {
+    if (!enc) return fail(MB_ERR_NULL, "enc is NULL");
+    if (index < 0 || index >= static_cast<int>(enc->names.size())) return fail(MB_ERR_INVALID, "param index %d out of range", index);
+    if (name && name_cap > 0) {
+        strncpy(name, enc->names[index].c_str(), name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (numel) *numel = enc->numels[index];
+    return MB_OK;
+}
+
+extern "C" int mb_packed_bytes(const MbEncoder* enc, size_t* bytes) {
+    if (!enc || !bytes) return fail(MB_ERR_NULL, "NULL argument");
+    *bytes = enc->packed_bytes;
+    return MB_OK;
+}
+
+extern "C" int mb_pack_weights(MbEncoder* enc, const float* const* params, void* packed, void* stream_) {
+    if (!enc || !params || !packed) return fail(MB_ERR_NULL, "NULL argument");
+    if (reinterpret_cast<uintptr_t>(packed) & 1023) return fail(MB_ERR_ALIGN, "packed buffer must be 1024-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const int np = static_cast<int>(enc->names.size());
+    for (int i = 0; i < np; ++i) {
+        if (!params[i]) return fail(MB_ERR_NULL, "params[%d] (%s) is NULL", i, enc->names[i].c_str());
+        if (reinterpret_cast<uintptr_t>(params[i]) & 3) return fail(MB_ERR_ALIGN, "params[%d] misaligned", i);
+    }
+    uint8_t* base = static_cast<uint8_t*>(packed);
+    std::lock_guard<std::mutex> lk(enc->mu);
+    const int passes = passes_of(enc->d);
+    for (LinearPack& L : enc->lin) {
+        const int warps_per_block = 8;
+        const int grid = (L.N + warps_per_block - 1) / warps_per_block;
+        pack_linear_kernel<<<grid, 256, 0, st>>>(
+            params[L.p_w], params[L.p_b], L.ln ? params[L.p_g] : nullptr, L.ln ? params[L.p_beta] : nullptr, L.N, L.K,
+            reinterpret_cast<__nv_bfloat16*>(base + L.off_hi), reinterpret_cast<__nv_bfloat16*>(base + L.off_lo),
+            reinterpret_cast<float*>(base + L.off_c), L.ln ? reinterpret_cast<float*>(base + L.off_s) : nullptr);
+        LAUNCH_CHECK("pack_linear_kernel");
+        // hi and lo planes are 1024-aligned but not necessarily adjacent: describe them as 2 planes with the
+        // actual plane stride
+        const uint64_t dims[3] = {static_cast<uint64_t>(L.K), static_cast<uint64_t>(L.N), 2};
+        const uint64_t str[2] = {static_cast<uint64_t>(L.K), static_cast<uint64_t>((L.off_lo - L.off_hi) / 2)};
+        const int BK = passes == 3 ? 32 : 64;
+        const uint32_t box[3] = {static_cast<uint32_t>(BK), static_cast<uint32_t>(GEMM_BN), static_cast<uint32_t>(passes == 3 ? 2 : 1)};
+        int rc = make_tmap(&L.tmap, base + L.off_hi, 3, dims, str, box, BK * 2);
+        if (rc) return rc;
+    }
+    const MbDesc& d = enc->d;
+    auto copy = [&](size_t off, const float* src, size_t n) {
+        return cudaMemcpyAsync(base + off, src, n * 4, cudaMemcpyDeviceToDevice, st);
+    };
+    const int C = d.dim_feat;
+    CUDA_TRY(copy(enc->off_small[0], params[enc->index.at("joints_embed.weight")], static_cast<size_t>(C) * d.dim_in));
+    CUDA_TRY(copy(enc->off_small[1], params[enc->index.at("joints_embed.bias")], C));
+    CUDA_TRY(copy(enc->off_small[2], params[enc->index.at("pos_embed")], static_cast<size_t>(d.num_joints) * C));
+    CUDA_TRY(copy(enc->off_small[3], params[enc->index.at("temp_embed")], static_cast<size_t>(d.maxlen) * C));
+    CUDA_TRY(copy(enc->off_small[4], params[enc->index.at("head.weight")], static_cast<size_t>(d.dim_out) * d.dim_rep));
+    CUDA_TRY(copy(enc->off_small[5], params[enc->index.at("head.bias")], d.dim_out));
+    for (int i = 0; i < d.depth; ++i) {
+        CUDA_TRY(copy(enc->off_small[6] + static_cast<size_t>(i) * 4 * C * 4,
+                      params[enc->index.at("ts_attn." + std::to_string(i) + ".weight")], static_cast<size_t>(4) * C));
+        CUDA_TRY(copy(enc->off_small[7] + static_cast<size_t>(i) * 2 * 4,
+                      params[enc->index.at("ts_attn." + std::to_string(i) + ".bias")], 2));
+    }
+    enc->packed_ptr = packed;
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------ workspace
+struct WsLayout {
+    size_t act_x[4], act_hi[4], act_lo[4], act_st[4];
+    size_t qkv, ao, rep, total;
+    size_t qkv_plane_bytes;
+};
+
+static WsLayout ws_layout(const MbDesc& d, int B, int F) {
+    WsLayout w;
+    const size_t M = static_cast<size_t>(B) * F * d.num_joints;
+    const size_t C = d.dim_feat;
+    const size_t ng = C / STATS_GROUP;
+    size_t off = 0;
+    for (int i = 0; i < 4; ++i) {
+        w.act_x[i] = off;  off = align_up(off + M * C * 4, 1024);
+        w.act_hi[i] = off; off = align_up(off + M * C * 2, 1024);
+        w.act_lo[i] = off; off = align_up(off + M * C * 2, 1024);
+        w.act_st[i] = off; off = align_up(off + M * ng * 3 * 4, 1024);
+    }
+    const size_t wide = static_cast<size_t>(3 * d.dim_feat > d.hidden ? 3 * d.dim_feat : d.hidden);
+    w.qkv_plane_bytes = align_up(M * wide * 2, 1024);
+    w.qkv = off; off += 2 * w.qkv_plane_bytes;
+    w.ao = off;  off = align_up(off + 2 * align_up(M * C * 2, 1024), 1024);
+    w.rep = off; off = align_up(off + M * d.dim_rep * 4, 1024);
+    w.total = off;
+    return w;
+}
+
+extern "C" int mb_workspace_bytes(const MbEncoder* enc, int B, int F, size_t* bytes) {
+    if (!enc || !bytes) return fail(MB_ERR_NULL, "NULL argument");
+    if (B < 1 || F < 1 || F > enc->d.maxlen) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d (maxlen %d)", B, F, enc->d.maxlen);
+    *bytes = ws_layout(enc->d, B, F).total;
+    return MB_OK;
+}
+
+static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
+    const MbDesc& d = e->d;
+    const WsLayout w = ws_layout(d, B, F);
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    const uint64_t M = static_cast<uint64_t>(B) * F * d.num_joints;
+    const uint64_t C = d.dim_feat;
+    const int passes = passes_of(d);
+    P->ws = ws; P->B = B; P->F = F;
+    int rc;
+    for (int i = 0; i < 4; ++i) {
+        ActBuf& a = P->act[i];
+        a.x = reinterpret_cast<float*>(base + w.act_x[i]);
+        a.hi = reinterpret_cast<__nv_bfloat16*>(base + w.act_hi[i]);
+        a.lo = reinterpret_cast<__nv_bfloat16*>(base + w.act_lo[i]);
+        a.stats = reinterpret_cast<float*>(base + w.act_st[i]);
+        const uint64_t dims[3] = {C, M, 2};
+        const uint64_t str[2] = {C, (w.act_lo[i] - w.act_hi[i]) / 2};
+        const int BK = passes == 3 ? 32 : 64;
+        const uint32_t box[3] = {static_cast<uint32_t>(BK), GEMM_BM, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
+        if ((rc = make_tmap(&a.tmap, a.hi, 3, dims, str, box, BK * 2))) return rc;
+    }
+    P->qkv = reinterpret_cast<__nv_bfloat16*>(base + w.qkv);
+    P->hid = P->qkv;
+    P->ao = reinterpret_cast<__nv_bfloat16*>(base + w.ao);
+    P->rep_ws = reinterpret_cast<float*>(base + w.rep);
+    const uint64_t qkv_plane_el = w.qkv_plane_bytes / 2;
+    {
+        const int BK = passes == 3 ? 32 : 64;
+        const uint32_t box[3] = {static_cast<uint32_t>(BK), GEMM_BM, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
+        const uint64_t dims_h[3] = {static_cast<uint64_t>(d.hidden), M, 2};
+        const uint64_t str_h[2] = {static_cast<uint64_t>(d.hidden), qkv_plane_el};
+        if ((rc = make_tmap(&P->tm_hid, P->hid, 3, dims_h, str_h, box, BK * 2))) return rc;
+        const uint64_t ao_plane_el = align_up(M * C * 2, 1024) / 2;
+        const uint64_t dims_a[3] = {C, M, 2};
+        const uint64_t str_a[2] = {C, ao_plane_el};
+        if ((rc = make_tmap(&P->tm_ao, P->ao, 3, dims_a, str_a, box, BK * 2))) return rc;
+    }
+    {
+        const int hd = d.dim_feat / d.num_heads;
+        const uint64_t C3 = 3 * C;
+        const uint64_t dims[5] = {C3, static_cast<uint64_t>(d.num_joints), static_cast<uint64_t>(F),
+                                  static_cast<uint64_t>(B), 2};
+        const uint64_t str[4] = {C3, C3 * d.num_joints, C3 * d.num_joints * F, qkv_plane_el};
+        const uint32_t planes = passes == 3 ? 2 : 1;
+        const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
+        const uint32_t box_q[5] = {static_cast<uint32_t>(hd), 1, ATT_BM, 1, planes};
+        const uint32_t box_kv[5] = {static_cast<uint32_t>(hd), 1, NK, 1, planes};
+        if ((rc = make_tmap(&P->tm_q, P->qkv, 5, dims, str, box_q, hd * 2))) return rc;
+        if ((rc = make_tmap(&P->tm_kv, P->qkv, 5, dims, str, box_kv, hd * 2))) return rc;
+    }
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------ launches
+template <int EPI>
+static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tmA, const __nv_bfloat16* a_hi,
+                       const __nv_bfloat16* a_lo, const LinearPack& L, const uint8_t* packed, GemmParams p,
+                       cudaStream_t st) {
+    p.N = L.N;
+    p.K = L.K;
+    p.vec0 = reinterpret_cast<const float*>(packed + L.off_c);
+    p.vec1 = reinterpret_cast<const float*>(packed + L.off_s);
+    const int passes = passes_of(e->d);
+    if (passes == 1) p.out_lo = nullptr;
+    if (flags & MB_FLAG_REF_GEMM) {
+        const long warps = static_cast<long>(p.M) * (p.N / STATS_GROUP);
+        const int grid = static_cast<int>((warps + 7) / 8);
+        gemm_ref_kernel<EPI><<<grid, 256, 0, st>>>(
+            a_hi, passes == 3 ? a_lo : nullptr, reinterpret_cast<const __nv_bfloat16*>(packed + L.off_hi),
+            passes == 3 ? reinterpret_cast<const __nv_bfloat16*>(packed + L.off_lo) : nullptr, p);
+        LAUNCH_CHECK("gemm_ref_kernel");
+        return MB_OK;
+    }
+    const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / GEMM_BN);
+    const int grid = tiles < e->dev.sms ? tiles : e->dev.sms;
+    if (passes == 3)
+        gemm_tc_kernel<3, EPI><<<grid, GEMM_THREADS, GemmCfg<3>::SMEM_BYTES, st>>>(tmA, L.tmap, p);
+    else
+        gemm_tc_kernel<1, EPI><<<grid, GEMM_THREADS, GemmCfg<1>::SMEM_BYTES, st>>>(tmA, L.tmap, p);
+    LAUNCH_CHECK("gemm_tc_kernel");
+    return MB_OK;
+}
+
+static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const Plan& P, int B, int F,
+                       size_t qkv_plane_el, size_t ao_plane_el, cudaStream_t st) {
+    const MbDesc& d = e->d;
+    const int C = d.dim_feat, H = d.num_heads, J = d.num_joints, hd = C / H;
+    const int passes = passes_of(d);
+    const float scale = d.qk_scale > 0.f ? d.qk_scale : 1.0f / sqrtf(static_cast<float>(hd));   // DSTformer.py:94
+    const __nv_bfloat16* q_hi = P.qkv;
+    const __nv_bfloat16* q_lo = passes == 3 ? P.qkv + qkv_plane_el : nullptr;
+    __nv_bfloat16* o_hi = P.ao;
+    __nv_bfloat16* o_lo = passes == 3 ? P.ao + ao_plane_el : nullptr;
+    if (!temporal) {
+        const size_t smem = static_cast<size_t>(J) * 3 * C * 4;
+        if (hd == 64) attn_s_kernel<64><<<B * F, 256, smem, st>>>(q_hi, q_lo, B * F, J, C, H, scale, o_hi, o_lo);
+        else attn_s_kernel<32><<<B * F, 256, smem, st>>>(q_hi, q_lo, B * F, J, C, H, scale, o_hi, o_lo);
+        LAUNCH_CHECK("attn_s_kernel");
+        return MB_OK;
+    }
+    if (flags & MB_FLAG_REF_ATTN_T) {
+        const size_t smem = static_cast<size_t>(F) * hd * 2 * 4;
+        if (hd == 64) attn_t_ref_kernel<64><<<B * J * H, 128, smem, st>>>(q_hi, q_lo, B, F, J, C, H, scale, o_hi, o_lo);
+        else attn_t_ref_kernel<32><<<B * J * H, 128, smem, st>>>(q_hi, q_lo, B, F, J, C, H, scale, o_hi, o_lo);
+        LAUNCH_CHECK("attn_t_ref_kernel");
+        return MB_OK;
+    }
+    AttnTParams ap;
+    ap.B = B; ap.F = F; ap.J = J; ap.C = C; ap.H = H;
+    ap.NK = (F + 15) / 16 * 16;
+    ap.scale_log2e = scale * 1.4426950408889634f;
+    ap.out_hi = o_hi;
+    ap.out_lo = o_lo;
+    const int prob = B * J * H;
+    const int grid = prob < e->dev.sms ? prob : e->dev.sms;
+    if (hd == 64 && passes == 3) attn_t_tc_kernel<64, 3><<<grid, ATT_THREADS, AttnCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    else if (hd == 32 && passes == 3) attn_t_tc_kernel<32, 3><<<grid, ATT_THREADS, AttnCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    else if (hd == 64) attn_t_tc_kernel<64, 1><<<grid, ATT_THREADS, AttnCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    else attn_t_tc_kernel<32, 1><<<grid, ATT_THREADS, AttnCfg<32, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    LAUNCH_CHECK("attn_t_tc_kernel");
+    return MB_OK;
+}
+
+extern "C" int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags) {
+    if (!enc) return fail(MB_ERR_NULL, "enc is NULL");
+    (void)flags;
+    // embed + depth * (2 blocks * 4 sublayers * {attn: 3 kernels, mlp: 2 kernels}/2 ... ) + fuse + tail
+    // per block: 2 attention sublayers (qkv gemm, attention, proj gemm) + 2 mlp sublayers (fc1, fc2) = 10
+    return 1 + enc->d.depth * (2 * 10 + 1) + 1 + (want_out ? 1 : 0);
+}
+
+extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
+                          const float* drop_path_scale, void* workspace, size_t workspace_bytes, int B, int F,
+                          uint32_t flags, void* stream_) {
+    if (!enc || !packed || !x || !workspace) return fail(MB_ERR_NULL, "NULL argument");
+    if (!out && !rep) return fail(MB_ERR_NULL, "both out and rep are NULL");
+    const MbDesc& d = enc->d;
+    if (B < 1 || F < 1) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d", B, F);
+    if (F > d.maxlen) return fail(MB_ERR_INVALID, "F=%d exceeds maxlen=%d (temp_embed, DSTformer.py:336)", F, d.maxlen);
+    const size_t M_ = static_cast<size_t>(B) * F * d.num_joints;
+    if (M_ > 0x7fffffffULL / 4) return fail(MB_ERR_INVALID, "B*F*J=%zu too large", M_);
+    if ((reinterpret_cast<uintptr_t>(x) & 3) || (out && (reinterpret_cast<uintptr_t>(out) & 3)) ||
+        (rep && (reinterpret_cast<uintptr_t>(rep) & 15)) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
+        return fail(MB_ERR_ALIGN, "misaligned buffer (rep: 16 B, workspace: 1024 B)");
+    const WsLayout wl = ws_layout(d, B, F);
+    if (workspace_bytes < wl.total) return fail(MB_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, wl.total);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != enc->device) return fail(MB_ERR_INVALID, "handle was created on device %d, current device is %d", enc->device, dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+
+    Plan P;
+    {
+        std::lock_guard<std::mutex> lk(enc->mu);
+        if (packed != enc->packed_ptr) return fail(MB_ERR_INVALID, "packed buffer differs from the one given to mb_pack_weights");
+        bool found = false;
+        for (const Plan& q : enc->plans)
+            if (q.ws == workspace && q.B == B && q.F == F) { P = q; found = true; break; }
+        if (!found) {
+            int rc = build_plan(enc, &P, workspace, B, F);
+            if (rc) return rc;
+            if (enc->plans.size() >= 16) enc->plans.erase(enc->plans.begin());
+            enc->plans.push_back(P);
+        }
+    }
+
+    const uint8_t* pk = static_cast<const uint8_t*>(packed);
+    const int M = static_cast<int>(M_);
+    const int C = d.dim_feat, J = d.num_joints;
+    const int ng = C / STATS_GROUP;
+    const size_t qkv_plane_el = wl.qkv_plane_bytes / 2;
+    const size_t ao_plane_el = align_up(M_ * C * 2, 1024) / 2;
+    const int rows_grid = (M + 7) / 8;
+    const int passes = passes_of(d);
+    int rc;
+
+    // embed (DSTformer.py:330-337) -> act[0]
+    embed_kernel<<<rows_grid, 256, 0, st>>>(
+        x, d.dim_in, reinterpret_cast<const float*>(pk + enc->off_small[0]),
+        reinterpret_cast<const float*>(pk + enc->off_small[1]), reinterpret_cast<const float*>(pk + enc->off_small[2]),
+        reinterpret_cast<const float*>(pk + enc->off_small[3]), M, F, J, C, P.act[0].x, P.act[0].hi,
+        passes == 3 ? P.act[0].lo : nullptr, P.act[0].stats);
+    LAUNCH_CHECK("embed_kernel");
+
+    GemmParams base;
+    memset(&base, 0, sizeof(base));
+    base.M = M;
+    base.nh_in = ng;
+    base.ln_dim = static_cast<float>(C);
+    base.eps = d.eps;
+    base.J = J;
+
+    int sub = 0;   // residual sublayer counter for drop_path_scale
+    auto dp = [&](int idx) -> const float* {
+        return drop_path_scale ? drop_path_scale + static_cast<size_t>(idx) * B * F : nullptr;
+    };
+
+    // one residual attention sublayer: dst = src + proj(attn(qkv(LN(src))))      (DSTformer.py:241,243,246,248)
+    auto attn_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst) -> int {
+        GemmParams p = base;
+        p.stats_in = src.stats;
+        p.out_hi = P.qkv;
+        p.out_lo = P.qkv + qkv_plane_el;
+        int r = launch_gemm<EPI_LN_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_QKV_T : L_QKV_S], pk, p, st);
+        if (r) return r;
+        r = launch_attn(enc, flags, temporal, P, B, F, qkv_plane_el, ao_plane_el, st);
+        if (r) return r;
+        GemmParams q = base;
+        q.resid = src.x;
+        q.row_scale = dp(sub++);
+        q.out_f32 = dst.x;
+        q.out_hi = dst.hi;
+        q.out_lo = dst.lo;
+        q.stats_out = dst.stats;
+        return launch_gemm<EPI_RESID>(enc, flags, P.tm_ao, P.ao, P.ao + ao_plane_el, L[temporal ? L_PROJ_T : L_PROJ_S], pk, q, st);
+    };
+    // one residual MLP sublayer: dst = src + fc2(gelu(fc1(LN(src))))             (DSTformer.py:242,244,247,249)
+    auto mlp_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst) -> int {
+        GemmParams p = base;
+        p.stats_in = src.stats;
+        p.out_hi = P.hid;
+        p.out_lo = P.hid + qkv_plane_el;
+        int r = launch_gemm<EPI_LN_GELU_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_FC1_T : L_FC1_S], pk, p, st);
+        if (r) return r;
+        GemmParams q = base;
+        q.resid = src.x;
+        q.row_scale = dp(sub++);
+        q.out_f32 = dst.x;
+        q.out_hi = dst.hi;
+        q.out_lo = dst.lo;
+        q.stats_out = dst.stats;
+        return launch_gemm<EPI_RESID>(enc, flags, P.tm_hid, P.hid, P.hid + qkv_plane_el, L[temporal ? L_FC2_T : L_FC2_S], pk, q, st);
+    };
+
+    const ActBuf& X0 = P.act[0];
+    const ActBuf& S1 = P.act[1];
+    const ActBuf& S2 = P.act[2];
+    const ActBuf& T1 = P.act[3];
+    for (int i = 0; i < d.depth; ++i) {
+        const LinearPack* Lst = &enc->lin[(0 * d.depth + i) * L_PER_BLOCK];
+        const LinearPack* Lts = &enc->lin[(1 * d.depth + i) * L_PER_BLOCK];
+        sub = i * 8;
+        // blocks_st[i] : 'stage_st'  S-attn, S-mlp, T-attn, T-mlp   (DSTformer.py:240-244)  X0 -> S1 -> S2 -> S1 -> S2
+        if ((rc = attn_sublayer(Lst, false, X0, S1))) return rc;
+        if ((rc = mlp_sublayer(Lst, false, S1, S2))) return rc;
+        if ((rc = attn_sublayer(Lst, true, S2, S1))) return rc;
+        if ((rc = mlp_sublayer(Lst, true, S1, S2))) return rc;
+        // blocks_ts[i] : 'stage_ts'  T-attn, T-mlp, S-attn, S-mlp   (DSTformer.py:245-249)  X0 -> T1 -> S1 -> T1 -> S1
+        if ((rc = attn_sublayer(Lts, true, X0, T1))) return rc;
+        if ((rc = mlp_sublayer(Lts, true, T1, S1))) return rc;
+        if ((rc = attn_sublayer(Lts, false, S1, T1))) return rc;
+        if ((rc = mlp_sublayer(Lts, false, T1, S1))) return rc;
+        // fusion (DSTformer.py:343-349): (x_st = S2, x_ts = S1) -> X0
+        fuse_kernel<<<rows_grid, 256, 0, st>>>(
+            S2.x, S1.x, reinterpret_cast<const float*>(pk + enc->off_small[6]) + static_cast<size_t>(i) * 4 * C,
+            reinterpret_cast<const float*>(pk + enc->off_small[7]) + static_cast<size_t>(i) * 2, M, C, X0.x, X0.hi,
+            passes == 3 ? X0.lo : nullptr, X0.stats);
+        LAUNCH_CHECK("fuse_kernel");
+    }
+    // tail (DSTformer.py:352-357): rep = tanh(Linear(LN(x))), out = Linear(rep)
+    float* rep_buf = rep ? rep : P.rep_ws;
+    {
+        GemmParams p = base;
+        p.stats_in = X0.stats;
+        p.out_f32 = rep_buf;
+        if ((rc = launch_gemm<EPI_LN_TANH_F32>(enc, flags, X0.tmap, X0.hi, X0.lo, enc->lin.back(), pk, p, st))) return rc;
+    }
+    if (out) {
+        head_kernel<<<rows_grid, 256, 0, st>>>(rep_buf, reinterpret_cast<const float*>(pk + enc->off_small[4]),
+                                               reinterpret_cast<const float*>(pk + enc->off_small[5]), M, d.dim_rep,
+                                               d.dim_out, out);
+        LAUNCH_CHECK("head_kernel");
+    }
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------ host-buffer entry
+extern "C" int mb_workspace_bytes_host(const MbEncoder* enc, int B, int F, int want_out, int want_rep, size_t* bytes) {
+    size_t ws = 0;
+    int rc = mb_workspace_bytes(enc, B, F, &ws);
+    if (rc) return rc;
+    const size_t M = static_cast<size_t>(B) * F * enc->d.num_joints;
+    ws = align_up(ws, 1024);
+    ws += align_up(M * enc->d.dim_in * 4, 1024);
+    if (want_out) ws += align_up(M * enc->d.dim_out * 4, 1024);
+    if (want_rep) ws += align_up(M * enc->d.dim_rep * 4, 1024);
+    *bytes = ws;
+    return MB_OK;
+}
+
+extern "C" int mb_forward_host(MbEncoder* enc, const void* packed, const float* x_host, float* out_host,
+                               float* rep_host, void* workspace, size_t workspace_bytes, int B, int F, uint32_t flags,
+                               void* stream_) {
+    if (!enc || !x_host || !workspace) return fail(MB_ERR_NULL, "NULL argument");
+    size_t need = 0, core = 0;
+    int rc = mb_workspace_bytes_host(enc, B, F, out_host != nullptr, rep_host != nullptr, &need);
+    if (rc) return rc;
+    if (workspace_bytes < need) return fail(MB_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+    mb_workspace_bytes(enc, B, F, &core);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const size_t M = static_cast<size_t>(B) * F * enc->d.num_joints;
+    uint8_t* p = static_cast<uint8_t*>(workspace) + align_up(core, 1024);
+    float* x_dev = reinterpret_cast<float*>(p); p += align_up(M * enc->d.dim_in * 4, 1024);
+    float* out_dev = nullptr;
+    float* rep_dev = nullptr;
+    if (out_host) { out_dev = reinterpret_cast<float*>(p); p += align_up(M * enc->d.dim_out * 4, 1024); }
+    if (rep_host) { rep_dev = reinterpret_cast<float*>(p); p += align_up(M * enc->d.dim_rep * 4, 1024); }
+    CUDA_TRY(cudaMemcpyAsync(x_dev, x_host, M * enc->d.dim_in * 4, cudaMemcpyHostToDevice, st));
+    rc = mb_forward(enc, packed, x_dev, out_dev, rep_dev, nullptr, workspace, core, B, F, flags, st);
+    if (rc) return rc;
+    if (out_host) CUDA_TRY(cudaMemcpyAsync(out_host, out_dev, M * enc->d.dim_out * 4, cudaMemcpyDeviceToHost, st));
+    if (rep_host) CUDA_TRY(cudaMemcpyAsync(rep_host, rep_dev, M * enc->d.dim_rep * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------ test hooks
+__global__ void merge_planes_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* y, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __bfloat162float(hi[i]) + (lo ? __bfloat162float(lo[i]) : 0.f);
+}
+__global__ void split_flat_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        __nv_bfloat16 h, l;
+        split_bf16(x[i], h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+struct LinScratch {
+    size_t a_hi, a_lo, a_st, w_hi, w_lo, vc, vs, o_hi, o_lo, total;
+};
+static LinScratch lin_scratch(int M, int N, int K) {
+    LinScratch s;
+    size_t off = 0;
+    s.a_hi = off; off = align_up(off + static_cast<size_t>(M) * K * 2, 1024);
+    s.a_lo = off; off = align_up(off + static_cast<size_t>(M) * K * 2, 1024);
+    s.a_st = off; off = align_up(off + static_cast<size_t>(M) * (K / STATS_GROUP + 1) * 12, 1024);
+    s.w_hi = off; off = align_up(off + static_cast<size_t>(N) * K * 2, 1024);
+    s.w_lo = off; off = align_up(off + static_cast<size_t>(N) * K * 2, 1024);
+    s.vc = off;   off = align_up(off + static_cast<size_t>(N) * 4, 1024);
+    s.vs = off;   off = align_up(off + static_cast<size_t>(N) * 4, 1024);
+    s.o_hi = off; off = align_up(off + static_cast<size_t>(M) * N * 2, 1024);
+    s.o_lo = off; off = align_up(off + static_cast<size_t>(M) * N * 2, 1024);
+    s.total = off;
+    return s;
+}
+
+extern "C" int mb_test_linear_scratch_bytes(int M, int N, int K, size_t* bytes) {
+    if (!bytes) return fail(MB_ERR_NULL, "NULL argument");
+    *bytes = lin_scratch(M, N, K).total;
+    return MB_OK;
+}
+
+extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int K, const float* A, const float* W,
+                              const float* bias, const float* gamma, const float* beta, const float* resid, float eps,
+                              float* y, float* stats_out, void* scratch, size_t scratch_bytes, void* stream_) {
+    if (!A || !W || !bias || !y || !scratch) return fail(MB_ERR_NULL, "NULL argument");
+    if (M < 1 || N % 256 || K % 256 || K > 1024 || N < 256) return fail(MB_ERR_INVALID, "bad shape M=%d N=%d K=%d", M, N, K);
+    if (mode < 0 || mode > 4) return fail(MB_ERR_INVALID, "bad mode");
+    const bool ln = (mode == EPI_LN_SPLIT || mode == EPI_LN_GELU_SPLIT || mode == EPI_LN_TANH_F32);
+    if (ln && (!gamma || !beta)) return fail(MB_ERR_NULL, "LN modes need gamma/beta");
+    if (mode == EPI_RESID && !resid) return fail(MB_ERR_NULL, "residual mode needs resid");
+    const LinScratch s = lin_scratch(M, N, K);
+    if (scratch_bytes < s.total) return fail(MB_ERR_WORKSPACE, "scratch too small");
+    int dev;
+    DevInfo info;
+    int rc = device_init(&dev, &info);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    auto* a_hi = reinterpret_cast<__nv_bfloat16*>(b + s.a_hi);
+    auto* a_lo = reinterpret_cast<__nv_bfloat16*>(b + s.a_lo);
+    auto* a_st = reinterpret_cast<float*>(b + s.a_st);
+    auto* w_hi = reinterpret_cast<__nv_bfloat16*>(b + s.w_hi);
+    auto* w_lo = reinterpret_cast<__nv_bfloat16*>(b + s.w_lo);
+    auto* vc = reinterpret_cast<float*>(b + s.vc);
+    auto* vs = reinterpret_cast<float*>(b + s.vs);
+    auto* o_hi = reinterpret_cast<__nv_bfloat16*>(b + s.o_hi);
+    auto* o_lo = reinterpret_cast<__nv_bfloat16*>(b + s.o_lo);
+    const int passes = math == MB_MATH_BF16 ? 1 : 3;
+    split_rows_kernel<<<(M + 7) / 8, 256, 0, st>>>(A, M, K, a_hi, a_lo, a_st);
+    LAUNCH_CHECK("split_rows_kernel");
+    pack_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, bias, ln ? gamma : nullptr, ln ? beta : nullptr, N, K, w_hi, w_lo, vc, vs);
+    LAUNCH_CHECK("pack_linear_kernel");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K;
+    p.vec0 = vc; p.vec1 = vs;
+    p.stats_in = a_st; p.nh_in = K / STATS_GROUP; p.ln_dim = static_cast<float>(K); p.eps = eps;
+    p.resid = resid; p.J = 1;
+    p.out_f32 = y; p.out_hi = o_hi; p.out_lo = passes == 3 ? o_lo : nullptr;
+    p.stats_out = stats_out;
+    CUtensorMap tmA, tmB;
+    // the scratch planes are adjacent only up to alignment padding: use the true plane strides
+    {
+        const int BK = passes == 3 ? 32 : 64;
+        const uint32_t pl = passes == 3 ? 2 : 1;
+        const uint64_t dA[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), 2};
+        const uint64_t sA[2] = {static_cast<uint64_t>(K), (s.a_lo - s.a_hi) / 2};
+        const uint32_t bA[3] = {static_cast<uint32_t>(BK), GEMM_BM, pl};
+        if ((rc = make_tmap(&tmA, a_hi, 3, dA, sA, bA, BK * 2))) return rc;
+        const uint64_t dB[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), 2};
+        const uint64_t sB[2] = {static_cast<uint64_t>(K), (s.w_lo - s.w_hi) / 2};
+        const uint32_t bB[3] = {static_cast<uint32_t>(BK), GEMM_BN, pl};
+        if ((rc = make_tmap(&tmB, w_hi, 3, dB, sB, bB, BK * 2))) return rc;
+    }
+    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
+    const int grid = tiles < info.sms ? tiles : info.sms;
+#define RUN(E)                                                                                                       \
+    do {                                                                                                             \
+        if (use_ref) {                                                                                               \
+            const long warps = static_cast<long>(M) * (N / STATS_GROUP);                                             \
+            gemm_ref_kernel<E><<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(a_hi, passes == 3 ? a_lo : nullptr, w_hi, \
+                                                                                   passes == 3 ? w_lo : nullptr, p);  \
+        } else if (passes == 3) {                                                                                    \
+            gemm_tc_kernel<3, E><<<grid, GEMM_THREADS, GemmCfg<3>::SMEM_BYTES, st>>>(tmA, tmB, p);                   \
+        } else {                                                                                                     \
+            gemm_tc_kernel<1, E><<<grid, GEMM_THREADS, GemmCfg<1>::SMEM_BYTES, st>>>(tmA, tmB, p);                   \
+        }                                                                                                            \
+    } while (0)
+    switch (mode) {
+        case EPI_LN_SPLIT: RUN(EPI_LN_SPLIT); break;
+        case EPI_LN_GELU_SPLIT: RUN(EPI_LN_GELU_SPLIT); break;
+        case EPI_RESID: RUN(EPI_RESID); break;
+        case EPI_LN_TANH_F32: RUN(EPI_LN_TANH_F32); break;
+        default: RUN(EPI_BIAS_F32); break;
+    }
+#undef RUN
+    LAUNCH_CHECK("test gemm");
+    if (mode == EPI_LN_SPLIT || mode == EPI_LN_GELU_SPLIT) {
+        const size_t n = static_cast<size_t>(M) * N;
+        merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(o_hi, passes == 3 ? o_lo : nullptr, y, n);
+        LAUNCH_CHECK("merge_planes_kernel");
+    }
+    return MB_OK;
+}
+
+extern "C" int mb_test_attention_scratch_bytes(int B, int F, int J, int C, size_t* bytes) {
+    if (!bytes) return fail(MB_ERR_NULL, "NULL argument");
+    const size_t M = static_cast<size_t>(B) * F * J;
+    *bytes = 2 * align_up(M * 3 * C * 2, 1024) + 2 * align_up(M * C * 2, 1024);
+    return MB_OK;
+}
+
+extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int F, int J, int C, int H,
+                                 const float* qkv, float* y, void* scratch, size_t scratch_bytes, void* stream_) {
+    if (!qkv || !y || !scratch) return fail(MB_ERR_NULL, "NULL argument");
+    size_t need;
+    mb_test_attention_scratch_bytes(B, F, J, C, &need);
+    if (scratch_bytes < need) return fail(MB_ERR_WORKSPACE, "scratch too small");
+    if (H < 1 || C % H || (C / H != 32 && C / H != 64) || F < 1 || F > 256 || J < 1 || J > 32)
+        return fail(MB_ERR_INVALID, "bad attention shape");
+    MbDesc d;
+    memset(&d, 0, sizeof(d));
+    d.dim_in = 3; d.dim_out = 3; d.dim_feat = C; d.dim_rep = 256; d.depth = 1; d.num_heads = H; d.hidden = 256;
+    d.num_joints = J; d.maxlen = 256; d.eps = 1e-6f; d.math = math;
+    MbEncoder e;
+    e.d = d;
+    int rc = device_init(&e.device, &e.dev);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const size_t M = static_cast<size_t>(B) * F * J;
+    const size_t qkv_plane = align_up(M * 3 * C * 2, 1024);
+    const size_t ao_plane = align_up(M * C * 2, 1024);
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    Plan P;
+    P.qkv = reinterpret_cast<__nv_bfloat16*>(b);
+    P.ao = reinterpret_cast<__nv_bfloat16*>(b + 2 * qkv_plane);
+    const int passes = math == MB_MATH_BF16 ? 1 : 3;
+    {
+        const size_t n = M * 3 * C;
+        split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(qkv, P.qkv, P.qkv + qkv_plane / 2, n);
+        LAUNCH_CHECK("split_flat_kernel");
+    }
+    if (temporal && !use_ref) {
+        const int hd = C / H;
+        const uint64_t C3 = 3ull * C;
+        const uint64_t dims[5] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 2};
+        const uint64_t str[4] = {C3, C3 * J, C3 * J * F, qkv_plane / 2};
+        const uint32_t planes = passes == 3 ? 2 : 1;
+        const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
+        const uint32_t box_q[5] = {static_cast<uint32_t>(hd), 1, ATT_BM, 1, planes};
+        const uint32_t box_kv[5] = {static_cast<uint32_t>(hd), 1, NK, 1, planes};
+        if ((rc = make_tmap(&P.tm_q, P.qkv, 5, dims, str, box_q, hd * 2))) return rc;
+        if ((rc = make_tmap(&P.tm_kv, P.qkv, 5, dims, str, box_kv, hd * 2))) return rc;
+    }
+    rc = launch_attn(&e, use_ref ? MB_FLAG_REF_ATTN_T : 0u, temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st);
+    if (rc) return rc;
+    const size_t n = M * C;
+    merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(P.ao, passes == 3 ? P.ao + ao_plane / 2 : nullptr, y, n);
+    LAUNCH_CHECK("merge_planes_kernel");
+    return MB_OK;
+}

@@ -1,0 +1,74 @@
+"""The C-ABI library loads and exports every symbol include/motionbert_b200.h declares; host-side logic that
+needs no GPU.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from motionbert_b200 import _lib, build as _build_mod  # noqa: F401
+from motionbert_b200 import build
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "motionbert_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb_[a-z_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_header_and_binding_agree():
+    assert _declared() == sorted(_lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in _declared():
+        assert hasattr(lib, name), name
+
+
+def test_version_and_desc_layout(lib):
+    assert lib.mb_version() == 1
+    assert ctypes.sizeof(_lib.MbDesc) == 12 * 4
+
+
+def test_create_fails_loudly_without_a_b200(lib):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    d = _lib.MbDesc(3, 3, 512, 512, 5, 8, 1024, 17, 243, 1e-6, 0.0, 0)
+    h = ctypes.c_void_p()
+    rc = lib.mb_create(ctypes.byref(d), ctypes.byref(h))
+    assert rc < 0 and not h.value
+    assert len(lib.mb_last_error()) > 0
+    with pytest.raises(_lib.MbError):
+        _lib.check(rc, "mb_create")
+
+
+def test_bad_descriptor_is_rejected(lib):
+    for bad in ((3, 3, 500, 512, 5, 8, 1024, 17, 243, 1e-6, 0.0, 0),      # C % 256
+                (3, 3, 512, 512, 5, 7, 1024, 17, 243, 1e-6, 0.0, 0),      # heads !| C
+                (3, 3, 512, 512, 5, 8, 1024, 17, 300, 1e-6, 0.0, 0),      # maxlen > 256
+                (3, 3, 512, 512, 5, 8, 1024, 17, 243, 1e-6, 0.0, 9)):     # math mode
+        d = _lib.MbDesc(*bad)
+        h = ctypes.c_void_p()
+        assert lib.mb_create(ctypes.byref(d), ctypes.byref(h)) == -1
+        assert b"" != lib.mb_last_error()
+    assert lib.mb_create(None, ctypes.byref(ctypes.c_void_p())) == -2
+
+
+def test_sass_contains_blackwell_instructions():
+    """The shipped kernels are tcgen05 / TMA code, not legacy mma.sync (B200_PROFILING.md mnemonics)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass and "STTM" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
