@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- sequences/sec of the DSTformer forward (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU path (oracle port), rank 0 only
+
+A "step" is one forward of the hot path over one batch of synthetic 2D skeleton clips.  At N=1 the workload is
+BASELINE config 2: DSTformer-base forward, B=256, T=243, 17 joints, fp32-parity arithmetic (BF16x3).  Multi-GPU:
+the batch shards across ranks as independent sequences (weak scaling: B=256 per GPU), no data-path collective;
+NCCL is only used for the barrier and the max-over-ranks time.
+
+JSON keys follow the driver contract; `roofline` is the tcgen05 GEMM class (the dominant kernels), measured with
+CUDA events around every launch in a separate profiled pass of the same steps.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}   # B200_PROFILING.md
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback (B200_PROFILING.md)"
+    return d
+
+
+MODELS = {"base": dict(dim_feat=512, mlp_ratio=2), "lite": dict(dim_feat=256, mlp_ratio=4)}
+
+
+def flops_per_sequence(dim_feat, hidden, T, J=17, depth=5, dim_rep=512, dim_in=3, dim_out=3):
+    """Algorithmic FLOPs of one forward (equals torch FlopCounterMode on the reference)."""
+    C = dim_feat
+    tok = depth * (4 * 8 * C * C + 4 * 4 * C * hidden + 2 * 4 * J * C + 2 * 4 * T * C + 8 * C) \
+        + 2 * dim_in * C + 2 * C * dim_rep + 2 * dim_rep * dim_out
+    return float(tok) * T * J
+
+
+def gemm_flops_per_sequence(dim_feat, hidden, T, J=17, depth=5, dim_rep=512):
+    """FLOPs of the work the tcgen05 GEMM kernel does (qkv/proj/fc1/fc2 of 20 sublayers + pre_logits)."""
+    C = dim_feat
+    tok = depth * (4 * 8 * C * C + 4 * 4 * C * hidden) + 2 * C * dim_rep
+    return float(tok) * T * J
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.index)], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            try:
+                sm.append(float(row[0])); mx.append(float(row[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), row[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(model, device, math):
+    from functools import partial
+
+    import torch.nn as nn
+
+    from motionbert_b200 import DSTformer
+    cfg = MODELS[model]
+    torch.manual_seed(0)                      # reference init (random-init weights of that architecture)
+    m = DSTformer(dim_in=3, dim_out=3, dim_feat=cfg["dim_feat"], dim_rep=512, depth=5, num_heads=8,
+                  mlp_ratio=cfg["mlp_ratio"], norm_layer=partial(nn.LayerNorm, eps=1e-6), maxlen=243, num_joints=17)
+    # move the S/T fusion and LayerNorm affine off their trivial init so no sub-path is constant
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for i in range(5):
+            m.ts_attn[i].weight.normal_(0, 0.05, generator=g)
+        for mod in m.modules():
+            if isinstance(mod, nn.LayerNorm):
+                mod.weight.add_(0.1 * torch.randn(mod.weight.shape, generator=g))
+                mod.bias.add_(0.05 * torch.randn(mod.bias.shape, generator=g))
+    m = m.to(device).eval()
+    m.set_math_mode(math)
+    return m
+
+
+def synthetic_clips(B, T, seed):
+    """x,y ~ U(-1,1), confidence ~ U(0,1), pinned host memory."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, T, 17, 3, generator=g)
+    x[..., :2] = x[..., :2] * 2 - 1
+    return x.pin_memory() if torch.cuda.is_available() else x
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_rate(model, T, budget_s=20.0, batch=2, max_iters=12):
+    """The reference's own CPU forward, restated op-for-op with torch CPU ops (oracle/dstformer_torch_cpu.py; the
+    reference itself is PyTorch-only Python and cannot travel to the GPU box).  All host threads."""
+    from oracle import dstformer_oracle as O
+    from oracle import dstformer_torch_cpu as OT
+    cfg = O.BASE if model == "base" else O.LITE
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {k: torch.from_numpy(v) for k, v in O.make_params(cfg, 0).items()}
+    x = torch.from_numpy(O.make_input(batch, T, cfg.num_joints, 1))
+    OT.forward(P, x, cfg.depth, cfg.num_heads, cfg.eps)           # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_iters and (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter()
+        OT.forward(P, x, cfg.depth, cfg.num_heads, cfg.eps)
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return {"value": batch / med, "unit": "sequences/sec", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} forwards of B={batch} x T={T} x 17 ({model}), median {med * 1e3:.0f} ms, "
+                      f"torch {torch.__version__} CPU fp32, {cores} threads"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    cb = cpu_reference_rate(args.model, args.frames, budget_s=min(120.0, 8.0 * steps), batch=2, max_iters=steps + args.warmup)
+    line = {
+        "impl": "reference", "metric": f"sequences/sec DSTformer-{args.model} fwd (Bx{args.frames}x17)",
+        "value": cb["value"], "unit": "sequences/sec", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 2.0 / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DSTformer-{args.model} forward, T={args.frames}, 17 joints, fp32; bounded CPU sample B=2 per step"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "sequences/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="base", choices=["base", "lite"])
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step")
+    ap.add_argument("--frames", type=int, default=243)
+    ap.add_argument("--math", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the DSTformer hot path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+
+    from motionbert_b200 import _lib
+    model = build_model(args.model, device, args.math)
+    cfg = MODELS[args.model]
+    hidden = int(cfg["dim_feat"] * cfg["mlp_ratio"])
+    B, T = args.batch, args.frames
+
+    x_host = synthetic_clips(B, T, seed=1 + rank)          # each rank owns its own shard of sequences
+    out_host = torch.empty(B, T, 17, 3).pin_memory()
+    x_dev = x_host.to(device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (also builds the handle, packs weights, allocates the workspace)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = model(x_dev)
+    barrier()
+
+    # ---- device-resident throughput: K forwards, inputs already in HBM, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.no_grad():
+        ev0.record()
+        for _ in range(args.steps):
+            out = model(x_dev)
+        ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    clocks = sampler.summary()
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: pinned host clip -> H2D -> forward -> D2H of the 3D pose, every step
+    barrier()
+    with torch.no_grad():
+        for _ in range(2):
+            out_host.copy_(model(x_host.to(device, non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize(device)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            xd = x_host.to(device, non_blocking=True)
+            out_host.copy_(model(xd), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize(device)
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * B / (e2e_ms * 1e-3)
+
+    # ---- per-kernel-class device time (CUDA events around every launch; separate profiled pass)
+    lib = _lib.load()
+    st = model._state_for(device)
+    _lib.check(lib.mb_profile_enable(st.handle, 1))
+    with torch.no_grad():
+        for _ in range(args.steps):
+            model(x_dev)
+    ms_cls = (ctypes.c_float * 9)()
+    n_cls = (ctypes.c_int * 9)()
+    _lib.check(lib.mb_profile_read(st.handle, ms_cls, n_cls))
+    _lib.check(lib.mb_profile_enable(st.handle, 0))
+    names = ["gemm_qkv", "gemm_fc1", "gemm_resid", "gemm_tail", "attn_t", "attn_s", "embed", "fuse", "head"]
+    cls_ms = {n: float(ms_cls[i]) / args.steps for i, n in enumerate(names)}
+    cls_n = {n: int(n_cls[i]) // args.steps for i, n in enumerate(names)}
+    gemm_ms = sum(cls_ms[n] for n in names[:4])
+    gemm_launches = sum(cls_n[n] for n in names[:4])
+    prof_total = sum(cls_ms.values())
+
+    peaks = load_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    gemm_flop = gemm_flops_per_sequence(cfg["dim_feat"], hidden, T) * B
+    achieved_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    total_flop = flops_per_sequence(cfg["dim_feat"], hidden, T) * B
+    passes = 3 if args.math == "bf16x3" else 1
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all 4 epilogue variants)",
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+        "traffic": None,
+        "peak_source": peaks["_source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+        "mma_passes": passes,
+        "note": f"achieved = algorithmic GEMM FLOPs per launch ({gemm_flop / max(gemm_launches, 1) / 1e9:.1f} GFLOP avg over "
+                f"{gemm_launches} launches/step) / mean launch time; {passes} bf16 MMA pass(es) per algorithmic FLOP, so the "
+                f"tensor pipe does {passes}x this work (ceiling of frac = {1.0 / passes:.3f})",
+        "tensor_pipe_tflops_executed": achieved_tf * passes,
+        "whole_step_tflops": total_flop / (ms_per_step * 1e-3) / 1e12,
+        "whole_step_frac": total_flop / (ms_per_step * 1e-3) / 1e12 / peak_tf,
+        "class_ms_per_step": cls_ms, "class_launches_per_step": cls_n,
+        "class_share": {n: (cls_ms[n] / prof_total if prof_total else 0.0) for n in names},
+    }
+
+    launches = _lib.check(lib.mb_forward_launch_count(st.handle, 1, 0)) * args.steps
+
+    line = {
+        "metric": f"sequences/sec DSTformer-{args.model} fwd (Bx{T}x17)",
+        "value": value, "unit": "sequences/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (fp32-parity split-bf16 tensor-core arithmetic, fp32 accumulate/residual)" if passes == 3 else "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2: DSTformer-{args.model} (depth=5, dim={cfg['dim_feat']}, 8 heads) forward, "
+                               f"B={B} per GPU, T={T}, 17 joints, fp32 I/O", "global_batch": world * B, "seq_len": T,
+                   "parallelism": f"dp{world} (independent sequences per rank, no data-path collective)",
+                   "l2": "per-step working set ~26 GB of activations >> 126 MB L2; every kernel streams > 2 GB, no flush needed",
+                   "weights": "torch.manual_seed(0) reference init, ts_attn/LayerNorm affine perturbed"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "sequences/sec", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                "api": "motionbert_b200.DSTformer.forward(x) on a pinned host clip, result copied back to pinned host"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_rate(args.model, T, budget_s=20.0)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,15 @@ int mb_forward_host(MbEncoder* enc, const void* packed, const float* x_host, flo
 /* Number of kernels one mb_forward call launches for this (B, F) (for bench.py's gpu_launches). */
 int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags);
 
+/* Per-kernel-class device timing for bench.py's roofline: while enabled, mb_forward brackets every launch
+ * with CUDA events on the caller's stream.  mb_profile_read synchronises, returns the accumulated
+ * milliseconds and launch counts per class since the last read and resets them.
+ * classes: 0 gemm LN->qkv, 1 gemm LN->fc1+GELU, 2 gemm proj/fc2+residual, 3 gemm tail (rep), 4 temporal attention,
+ *          5 spatial attention, 6 embed, 7 fusion, 8 head.   Not thread-safe; measurement only. */
+#define MB_PROFILE_CLASSES 9
+int mb_profile_enable(MbEncoder* enc, int on);
+int mb_profile_read(MbEncoder* enc, float* ms_by_class, int* launches_by_class);
+
 /* ------------------------------------------------------------------ kernel-level test hooks ----------
  * Exercise one kernel in isolation so tests/ can localise a failure on the device.  Not used by the
  * product path. */

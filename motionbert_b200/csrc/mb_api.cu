@@ -173,7 +173,32 @@ struct MbEncoder {
     const void* packed_ptr = nullptr;
     std::mutex mu;
     std::vector<Plan> plans;
+    // profiling (bench only)
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<int> event_class;   // class of the launch that FOLLOWS event i (-1: end marker)
+    size_t events_used = 0;
+    ~MbEncoder() {
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
 };
+
+enum ProfClass { PC_GEMM_QKV = 0, PC_GEMM_FC1, PC_GEMM_RESID, PC_GEMM_TAIL, PC_ATTN_T, PC_ATTN_S, PC_EMBED, PC_FUSE, PC_HEAD };
+
+// record an event before a launch of class `cls` (or cls = -1 as the closing marker)
+static void prof_mark(const MbEncoder* ce, cudaStream_t st, int cls) {
+    MbEncoder* e = const_cast<MbEncoder*>(ce);
+    if (!e->profiling) return;
+    if (e->events_used == e->events.size()) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        e->events.push_back(ev);
+        e->event_class.push_back(-1);
+    }
+    e->event_class[e->events_used] = cls;
+    cudaEventRecord(e->events[e->events_used], st);
+    ++e->events_used;
+}
 
 static int passes_of(const MbDesc& d) { return d.math == MB_MATH_BF16 ? 1 : 3; }
 
@@ -486,6 +511,8 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
     p.vec1 = reinterpret_cast<const float*>(packed + L.off_s);
     const int passes = passes_of(e->d);
     if (passes == 1) p.out_lo = nullptr;
+    prof_mark(e, st, EPI == EPI_LN_SPLIT ? PC_GEMM_QKV : EPI == EPI_LN_GELU_SPLIT ? PC_GEMM_FC1
+                     : EPI == EPI_RESID ? PC_GEMM_RESID : PC_GEMM_TAIL);
     if (flags & MB_FLAG_REF_GEMM) {
         const long warps = static_cast<long>(p.M) * (p.N / STATS_GROUP);
         const int grid = static_cast<int>((warps + 7) / 8);
@@ -515,6 +542,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     const __nv_bfloat16* q_lo = passes == 3 ? P.qkv + qkv_plane_el : nullptr;
     __nv_bfloat16* o_hi = P.ao;
     __nv_bfloat16* o_lo = passes == 3 ? P.ao + ao_plane_el : nullptr;
+    prof_mark(e, st, temporal ? PC_ATTN_T : PC_ATTN_S);
     if (!temporal) {
         const size_t smem = static_cast<size_t>(J) * 3 * C * 4;
         if (hd == 64) attn_s_kernel<64><<<B * F, 256, smem, st>>>(q_hi, q_lo, B * F, J, C, H, scale, o_hi, o_lo);
@@ -599,6 +627,7 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
     int rc;
 
     // embed (DSTformer.py:330-337) -> act[0]
+    prof_mark(enc, st, PC_EMBED);
     embed_kernel<<<rows_grid, 256, 0, st>>>(
         x, d.dim_in, reinterpret_cast<const float*>(pk + enc->off_small[0]),
         reinterpret_cast<const float*>(pk + enc->off_small[1]), reinterpret_cast<const float*>(pk + enc->off_small[2]),
@@ -675,6 +704,7 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         if ((rc = attn_sublayer(Lts, false, S1, T1))) return rc;
         if ((rc = mlp_sublayer(Lts, false, T1, S1))) return rc;
         // fusion (DSTformer.py:343-349): (x_st = S2, x_ts = S1) -> X0
+        prof_mark(enc, st, PC_FUSE);
         fuse_kernel<<<rows_grid, 256, 0, st>>>(
             S2.x, S1.x, reinterpret_cast<const float*>(pk + enc->off_small[6]) + static_cast<size_t>(i) * 4 * C,
             reinterpret_cast<const float*>(pk + enc->off_small[7]) + static_cast<size_t>(i) * 2, M, C, X0.x, X0.hi,
@@ -690,11 +720,37 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         if ((rc = launch_gemm<EPI_LN_TANH_F32>(enc, flags, X0.tmap, X0.hi, X0.lo, enc->lin.back(), pk, p, st))) return rc;
     }
     if (out) {
+        prof_mark(enc, st, PC_HEAD);
         head_kernel<<<rows_grid, 256, 0, st>>>(rep_buf, reinterpret_cast<const float*>(pk + enc->off_small[4]),
                                                reinterpret_cast<const float*>(pk + enc->off_small[5]), M, d.dim_rep,
                                                d.dim_out, out);
         LAUNCH_CHECK("head_kernel");
     }
+    prof_mark(enc, st, -1);
+    return MB_OK;
+}
+
+extern "C" int mb_profile_enable(MbEncoder* enc, int on) {
+    if (!enc) return fail(MB_ERR_NULL, "enc is NULL");
+    enc->profiling = on != 0;
+    enc->events_used = 0;
+    return MB_OK;
+}
+
+extern "C" int mb_profile_read(MbEncoder* enc, float* ms_by_class, int* launches_by_class) {
+    if (!enc || !ms_by_class || !launches_by_class) return fail(MB_ERR_NULL, "NULL argument");
+    for (int i = 0; i < MB_PROFILE_CLASSES; ++i) { ms_by_class[i] = 0.f; launches_by_class[i] = 0; }
+    if (enc->events_used == 0) return MB_OK;
+    CUDA_TRY(cudaEventSynchronize(enc->events[enc->events_used - 1]));
+    for (size_t i = 0; i + 1 < enc->events_used; ++i) {
+        const int cls = enc->event_class[i];
+        if (cls < 0 || cls >= MB_PROFILE_CLASSES) continue;
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, enc->events[i], enc->events[i + 1]));
+        ms_by_class[cls] += ms;
+        launches_by_class[cls] += 1;
+    }
+    enc->events_used = 0;
     return MB_OK;
 }
 

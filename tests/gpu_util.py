@@ -1,0 +1,46 @@
+"""Helpers for the -m gpu tests: call the C-ABI test hooks with torch-allocated device buffers."""
+import ctypes
+
+import torch
+
+from motionbert_b200 import _lib
+
+
+def _scratch(nbytes, device):
+    t = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    return t, (t.data_ptr() + 1023) // 1024 * 1024
+
+
+def test_linear(mode, A, W, bias, gamma=None, beta=None, resid=None, eps=1e-6, math=0, use_ref=0):
+    """Returns (y fp32 [M,N], stats [M, N/256, 3] or None)."""
+    lib = _lib.load()
+    dev = A.device
+    M, K = A.shape
+    N = W.shape[0]
+    nb = ctypes.c_size_t()
+    _lib.check(lib.mb_test_linear_scratch_bytes(M, N, K, ctypes.byref(nb)))
+    keep, sp = _scratch(nb.value, dev)
+    y = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
+    stats = torch.zeros(M, N // 256, 3, dtype=torch.float32, device=dev) if mode == 2 else None
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mb_test_linear(mode, math, use_ref, M, N, K, ptr(A), ptr(W), ptr(bias), ptr(gamma), ptr(beta),
+                                      ptr(resid), eps, ptr(y), ptr(stats), sp, nb.value, st), "mb_test_linear")
+        torch.cuda.synchronize(dev)
+    return y, stats
+
+
+def test_attention(temporal, qkv, B, F, J, C, H, math=0, use_ref=0):
+    lib = _lib.load()
+    dev = qkv.device
+    nb = ctypes.c_size_t()
+    _lib.check(lib.mb_test_attention_scratch_bytes(B, F, J, C, ctypes.byref(nb)))
+    keep, sp = _scratch(nb.value, dev)
+    y = torch.full((B * F * J, C), float("nan"), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mb_test_attention(int(temporal), math, use_ref, B, F, J, C, H, qkv.data_ptr(), y.data_ptr(),
+                                         sp, nb.value, st), "mb_test_attention")
+        torch.cuda.synchronize(dev)
+    return y

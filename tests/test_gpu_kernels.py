@@ -1,0 +1,125 @@
+"""Kernel-level parity through the C-ABI test hooks: each CUDA kernel against a plain torch fp64 restatement
+of the same op (tolerances written per test).  Localises failures before the whole-model tests run."""
+import math
+
+import pytest
+import torch
+
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = a.double(); b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30)), float((a - b).abs().max())
+
+
+def _mk(M, N, K, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = (torch.randn(M, K, generator=g) * 1.5 + 0.3).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = (torch.randn(N, generator=g) * 0.1).to(dev)
+    gamma = (1 + 0.2 * torch.randn(K, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(K, generator=g)).to(dev)
+    resid = torch.randn(M, N, generator=g).to(dev)
+    return A, W, b, gamma, beta, resid
+
+
+def _expected(mode, A, W, b, gamma, beta, resid, eps):
+    A, W, b = A.double(), W.double(), b.double()
+    if mode in (0, 1, 3):
+        x = torch.nn.functional.layer_norm(A, (A.shape[1],), gamma.double(), beta.double(), eps)
+        y = x @ W.T + b
+        if mode == 1:
+            y = torch.nn.functional.gelu(y)
+        if mode == 3:
+            y = torch.tanh(y)
+        return y
+    y = A @ W.T + b
+    if mode == 2:
+        y = resid.double() + y
+    return y
+
+
+SHAPES = [(128, 256, 256), (300, 512, 512), (1000, 1536, 512), (77, 512, 1024), (4131, 1024, 512), (459, 768, 256)]
+
+
+@pytest.mark.parametrize("use_ref", [1, 0], ids=["simt_ref", "tcgen05"])
+@pytest.mark.parametrize("mode", [4, 0, 1, 2, 3], ids=["bias", "ln_split", "ln_gelu", "resid", "ln_tanh"])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_linear_bf16x3(cuda_device, M, N, K, mode, use_ref):
+    A, W, b, gamma, beta, resid = _mk(M, N, K, cuda_device, seed=M + N + K + mode)
+    y, stats = G.test_linear(mode, A, W, b, gamma, beta, resid, 1e-6, math=0, use_ref=use_ref)
+    exp = _expected(mode, A, W, b, gamma, beta, resid, 1e-6)
+    assert torch.isfinite(y).all(), "non-finite / unwritten output"
+    rel, mx = _rel(y, exp)
+    # BF16x3: 16-bit operand mantissas, fp32 accumulate; split-plane outputs (modes 0,1) carry 2^-17 rounding
+    assert rel < 3e-5, f"rel {rel:.3e} max {mx:.3e}"
+    if mode == 2:
+        # LN partial statistics of the output rows: (shift, sum(x-shift), sum((x-shift)^2)) per 256 columns
+        e = exp.float().reshape(M, N // 256, 256)
+        mean_g = stats[..., 0] + stats[..., 1] / 256
+        var_g = stats[..., 2] / 256 - (stats[..., 1] / 256) ** 2
+        assert float((mean_g - e.mean(-1)).abs().max()) < 1e-4
+        assert float((var_g - e.var(-1, unbiased=False)).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 512), (77, 512, 1024)])
+@pytest.mark.parametrize("mode", [4, 0, 2])
+def test_linear_bf16_single_pass(cuda_device, M, N, K, mode):
+    A, W, b, gamma, beta, resid = _mk(M, N, K, cuda_device, seed=7)
+    y, _ = G.test_linear(mode, A, W, b, gamma, beta, resid, 1e-6, math=1, use_ref=0)
+    exp = _expected(mode, A, W, b, gamma, beta, resid, 1e-6)
+    assert torch.isfinite(y).all()
+    rel, mx = _rel(y, exp)
+    assert rel < 8e-3, f"rel {rel:.3e} max {mx:.3e}"     # plain bf16 operands: 2^-9 per element
+
+
+def _attn_expected(qkv, B, F, J, C, H, temporal):
+    d = C // H
+    q, k, v = qkv.double().reshape(B * F, J, 3, H, d).permute(2, 0, 3, 1, 4)
+    if temporal:
+        q, k, v = [t.reshape(B, F, H, J, d).permute(0, 2, 3, 1, 4) for t in (q, k, v)]
+        att = ((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(-1)
+        return (att @ v).permute(0, 3, 2, 1, 4).reshape(B * F * J, C)
+    att = ((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(-1)
+    return (att @ v).transpose(1, 2).reshape(B * F * J, C)
+
+
+ATT_SHAPES = [(2, 27, 17, 512, 8), (1, 243, 17, 512, 8), (3, 16, 17, 256, 8), (2, 130, 17, 512, 8), (1, 1, 17, 256, 8),
+              (2, 243, 17, 256, 8), (5, 30, 17, 512, 8)]
+
+
+@pytest.mark.parametrize("use_ref", [1, 0], ids=["simt_ref", "tcgen05"])
+@pytest.mark.parametrize("B,F,J,C,H", ATT_SHAPES)
+def test_temporal_attention(cuda_device, B, F, J, C, H, use_ref):
+    g = torch.Generator().manual_seed(B * 1000 + F)
+    qkv = (torch.randn(B * F * J, 3 * C, generator=g) * 1.2).to(cuda_device)
+    y = G.test_attention(1, qkv, B, F, J, C, H, math=0, use_ref=use_ref)
+    exp = _attn_expected(qkv, B, F, J, C, H, True)
+    assert torch.isfinite(y).all(), "non-finite / unwritten output"
+    rel, mx = _rel(y, exp)
+    assert rel < 3e-5, f"rel {rel:.3e} max {mx:.3e}"
+
+
+@pytest.mark.parametrize("B,F,J,C,H", ATT_SHAPES[:4])
+def test_spatial_attention(cuda_device, B, F, J, C, H):
+    g = torch.Generator().manual_seed(B * 77 + F)
+    qkv = (torch.randn(B * F * J, 3 * C, generator=g) * 1.2).to(cuda_device)
+    y = G.test_attention(0, qkv, B, F, J, C, H, math=0, use_ref=0)
+    exp = _attn_expected(qkv, B, F, J, C, H, False)
+    assert torch.isfinite(y).all()
+    rel, mx = _rel(y, exp)
+    assert rel < 2e-5, f"rel {rel:.3e} max {mx:.3e}"
+
+
+@pytest.mark.parametrize("B,F,J,C,H", [(2, 27, 17, 512, 8), (1, 243, 17, 256, 8)])
+def test_temporal_attention_bf16_single_pass(cuda_device, B, F, J, C, H):
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(B * F * J, 3 * C, generator=g).to(cuda_device)
+    y = G.test_attention(1, qkv, B, F, J, C, H, math=1, use_ref=0)
+    exp = _attn_expected(qkv, B, F, J, C, H, True)
+    assert torch.isfinite(y).all()
+    rel, mx = _rel(y, exp)
+    assert rel < 1.5e-2, f"rel {rel:.3e} max {mx:.3e}"
