@@ -129,7 +129,7 @@ int mb_profile_read(MbEncoder* enc, float* ms_by_class, int* launches_by_class);
 
 /* y[M,N] = epilogue(A[M,K] . W[N,K]^T): A, W fp32 on device; scratch >= mb_test_linear_scratch_bytes().
  * mode: 0 LN-folded split (returns hi+lo as fp32), 1 LN+GELU split, 2 residual (+stats), 3 LN+tanh, 4 bias.
- * gamma/beta (LN modes) and resid (mode 2) may be NULL otherwise.  stats_out (mode 2): [M][N/256][3]. */
+ * gamma/beta (LN modes) and resid (mode 2) may be NULL otherwise.  stats_out (mode 2): [M][N/128][3]. */
 int mb_test_linear_scratch_bytes(int M, int N, int K, size_t* bytes);
 int mb_test_linear(int mode, int math, int use_ref, int M, int N, int K, const float* A, const float* W,
                    const float* bias, const float* gamma, const float* beta, const float* resid, float eps,

@@ -8,8 +8,9 @@
 // Tiles: 128 x 256 x BK (BK = 32 / SWIZZLE_64B for 3 passes, 64 / SWIZZLE_128B for 1 pass), 4-stage
 // TMA->smem ring (48 KB / stage), two 256-column fp32 accumulators in TMEM (all 512 columns) so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
-// Warp roles (192 threads): w0 = TMA producer, w1 = MMA issuer (+TMEM alloc), w2..w5 = epilogue
-// (TMEM lane quadrant = warp_idx % 4; thread = one output row, 32-column chunks via tcgen05.ld).
+// Warp roles (320 threads): w0 = TMA producer, w1 = MMA issuer (+TMEM alloc), w2..w9 = epilogue
+// (TMEM lane quadrant = warp_idx % 4, column half = (warp_idx-2)/4; thread = one output row x 128 columns,
+// 32-column chunks via tcgen05.ld; residual loads are register double-buffered one chunk ahead).
 //
 // The epilogue is where the reference's elementwise ops are folded (DSTformer.py line refs):
 //   EPI_LN_SPLIT      y = rstd*(acc - mean*s[n]) + c[n]            LayerNorm folded algebraically   (:241,243 qkv)
@@ -28,15 +29,16 @@ enum : int { EPI_LN_SPLIT = 0, EPI_LN_GELU_SPLIT = 1, EPI_RESID = 2, EPI_LN_TANH
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 192;
-constexpr int STATS_GROUP = 256;   // LayerNorm partial statistics are kept per 256-column group
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_THREADS = 256;
+constexpr int STATS_GROUP = 128;   // LayerNorm partial statistics are kept per 128-column group
 
 struct GemmParams {
     int M, N, K;
     const float* vec0;        // bias[n] (RESID/BIAS) or c[n] (LN modes)
     const float* vec1;        // s[n] = sum_k W'[n,k] (LN modes)
-    const float* stats_in;    // LN modes: [M][nh_in][3] = (shift, sum(x-shift), sum((x-shift)^2)) per 256-col group
-    int nh_in;                // groups per row of the LN input (= C/256)
+    const float* stats_in;    // LN modes: [M][nh_in][3] = (shift, sum(x-shift), sum((x-shift)^2)) per 128-col group
+    int nh_in;                // groups per row of the LN input (= C/128)
     float ln_dim;             // C (number of normalised features)
     float eps;
     const float* resid;       // RESID: fp32 [M,N]
@@ -45,7 +47,7 @@ struct GemmParams {
     float* out_f32;           // RESID / *_F32
     __nv_bfloat16* out_hi;    // split outputs [M,N]
     __nv_bfloat16* out_lo;    // may be null when PASSES == 1
-    float* stats_out;         // RESID: [M][N/256][3]
+    float* stats_out;         // RESID: [M][N/128][3]
 };
 
 template <int PASSES>
@@ -117,7 +119,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,   // 3D (K, M, plane), b
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 128);
+            mbar_init(&tempty_bar[i], GEMM_EPI_THREADS);
         }
         fence_barrier_init();
     }
@@ -188,8 +190,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,   // 3D (K, M, plane), b
             if (acc == 0) acc_phase ^= 1;
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 2..9)
         const int quad = warp & 3;                      // TMEM lanes [32*quad, 32*quad+32)
+        const int half = (warp - 2) >> 2;               // columns [128*half, 128*half+128) of the tile
+        constexpr int NCH = GEMM_BN / 2 / 32;           // 4 chunks of 32 columns per thread
+        const int ngrp_out = p.N / STATS_GROUP;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -197,35 +202,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,   // 3D (K, M, plane), b
             const int row = m_idx * GEMM_BM + quad * 32 + lane;
             const bool row_ok = row < p.M;
             const size_t row_off = static_cast<size_t>(row) * p.N;
+            const int colbase = n_idx * GEMM_BN + half * (GEMM_BN / 2);
 
             float mean = 0.f, rstd = 1.f, rscale = 1.f;
             if (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32) {
                 if (row_ok) ln_row_stats(p.stats_in + static_cast<size_t>(row) * p.nh_in * 3, p.nh_in, p.ln_dim,
                                          p.eps, mean, rstd);
             }
+            // residual prefetch (one chunk ahead, issued before the accumulator is even ready)
+            float4 xr[2][8];
             if (EPI == EPI_RESID) {
                 if (row_ok && p.row_scale) rscale = p.row_scale[row / p.J];
+                const float4* x4 = reinterpret_cast<const float4*>(p.resid + row_off + colbase);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xr[0][i] = row_ok ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             float st_shift = 0.f, st_sum = 0.f, st_sq = 0.f;
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(quad * 32) << 16);
-#pragma unroll 1
-            for (int ch = 0; ch < GEMM_BN / 32; ++ch) {
+            const uint32_t t_row = tmem_base + acc * GEMM_BN + half * (GEMM_BN / 2) +
+                                   (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int col0 = colbase + ch * 32;
+                if (EPI == EPI_RESID) {
+                    if (ch + 1 < NCH) {
+                        const float4* x4 = reinterpret_cast<const float4*>(p.resid + row_off + col0 + 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            xr[(ch + 1) & 1][i] = row_ok ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 uint32_t r[32];
                 tmem_ld32(t_row + ch * 32, r);
                 tmem_ld_wait();
-                const int col0 = n_idx * GEMM_BN + ch * 32;
                 float v[32];
                 if (EPI == EPI_RESID) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
-                    const float4* x4 = reinterpret_cast<const float4*>(p.resid + row_off + col0);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 b = __ldg(b4 + i);
-                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok) x = x4[i];
+                        const float4 x = xr[ch & 1][i];
                         v[4 * i + 0] = x.x + rscale * (__uint_as_float(r[4 * i + 0]) + b.x);
                         v[4 * i + 1] = x.y + rscale * (__uint_as_float(r[4 * i + 1]) + b.y);
                         v[4 * i + 2] = x.z + rscale * (__uint_as_float(r[4 * i + 2]) + b.z);
@@ -299,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,   // 3D (K, M, plane), b
             mbar_arrive(&tempty_bar[acc]);
             if (EPI == EPI_RESID) {
                 if (row_ok && p.stats_out) {
-                    float* so = p.stats_out + (static_cast<size_t>(row) * num_n + n_idx) * 3;
+                    float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;
                     so[0] = st_shift;
                     so[1] = st_sum;
                     so[2] = st_sq;

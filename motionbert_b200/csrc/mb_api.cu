@@ -20,6 +20,17 @@
 
 using namespace mb;
 
+// launch a warp-per-token-row kernel templated on NV = C/128 (locals C, rows_grid, st must be in scope)
+#define ROWK(K, ...)                                              \
+    do {                                                          \
+        switch (C / 128) {                                        \
+            case 2: K<2><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+            case 4: K<4><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+            case 6: K<6><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+            default: K<8><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+        }                                                         \
+    } while (0)
+
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, ...) {
@@ -628,7 +639,7 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
 
     // embed (DSTformer.py:330-337) -> act[0]
     prof_mark(enc, st, PC_EMBED);
-    embed_kernel<<<rows_grid, 256, 0, st>>>(
+    ROWK(embed_kernel,
         x, d.dim_in, reinterpret_cast<const float*>(pk + enc->off_small[0]),
         reinterpret_cast<const float*>(pk + enc->off_small[1]), reinterpret_cast<const float*>(pk + enc->off_small[2]),
         reinterpret_cast<const float*>(pk + enc->off_small[3]), M, F, J, C, P.act[0].x, P.act[0].hi,
@@ -705,7 +716,7 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         if ((rc = mlp_sublayer(Lts, false, T1, S1))) return rc;
         // fusion (DSTformer.py:343-349): (x_st = S2, x_ts = S1) -> X0
         prof_mark(enc, st, PC_FUSE);
-        fuse_kernel<<<rows_grid, 256, 0, st>>>(
+        ROWK(fuse_kernel,
             S2.x, S1.x, reinterpret_cast<const float*>(pk + enc->off_small[6]) + static_cast<size_t>(i) * 4 * C,
             reinterpret_cast<const float*>(pk + enc->off_small[7]) + static_cast<size_t>(i) * 2, M, C, X0.x, X0.hi,
             passes == 3 ? X0.lo : nullptr, X0.stats);
@@ -861,7 +872,11 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
     auto* o_hi = reinterpret_cast<__nv_bfloat16*>(b + s.o_hi);
     auto* o_lo = reinterpret_cast<__nv_bfloat16*>(b + s.o_lo);
     const int passes = math == MB_MATH_BF16 ? 1 : 3;
-    split_rows_kernel<<<(M + 7) / 8, 256, 0, st>>>(A, M, K, a_hi, a_lo, a_st);
+    {
+        const int C = K;
+        const int rows_grid = (M + 7) / 8;
+        ROWK(split_rows_kernel, A, M, K, a_hi, a_lo, a_st);
+    }
     LAUNCH_CHECK("split_rows_kernel");
     pack_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, bias, ln ? gamma : nullptr, ln ? beta : nullptr, N, K, w_hi, w_lo, vc, vs);
     LAUNCH_CHECK("pack_linear_kernel");

@@ -182,13 +182,24 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {   // a -> low half
     return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }
-// split two floats, return packed hi pair and packed lo pair
+// split two floats, return packed hi pair and packed lo pair (x0 -> low half).  cvt.rn.bf16x2.f32 converts
+// both lanes in one instruction; the residual is exact in fp32.
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(x0, h0, l0);
-    split_bf16(x1, h1, l1);
-    hi = pack_bf16(h0, h1);
-    lo = pack_bf16(l0, l1);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float f0 = __uint_as_float(hi << 16);
+    const float f1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, MUFU.EX2 (rel err 2^-22)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 }  // namespace mb

@@ -20,7 +20,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // One warp owns one token row of C channels held as float4 per lane per 128-channel slab
-// (channels 128*i + 4*lane .. +3).  Writes fp32 x, bf16 hi/lo planes and the per-256-group
+// (channels 128*i + 4*lane .. +3).  Writes fp32 x, bf16 hi/lo planes and the per-128-group
 // LayerNorm partials consumed by the next GEMM's LN-folded epilogue.
 template <int MAXV>
 __device__ __forceinline__ void emit_row(const float4 (&v)[MAXV], int nv, size_t row, int C, float* __restrict__ x,
@@ -41,35 +41,32 @@ __device__ __forceinline__ void emit_row(const float4 (&v)[MAXV], int nv, size_t
         }
     }
     if (stats) {
-        const int ng = C / STATS_GROUP;
-        for (int g = 0; g < ng; ++g) {
-            const float shift = __shfl_sync(0xffffffffu, v[2 * g].x, 0);
-            float s1 = 0.f, s2 = 0.f;
+        // one 128-channel slab (= one float4 per lane) is exactly one statistics group
 #pragma unroll
-            for (int i = 0; i < MAXV; ++i) {
-                if (i == 2 * g || i == 2 * g + 1) {
-                    const float d0 = v[i].x - shift, d1 = v[i].y - shift, d2 = v[i].z - shift, d3 = v[i].w - shift;
-                    s1 += (d0 + d1) + (d2 + d3);
-                    s2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        for (int i = 0; i < MAXV; ++i) {
+            if (i < nv) {
+                const float shift = __shfl_sync(0xffffffffu, v[i].x, 0);
+                const float d0 = v[i].x - shift, d1 = v[i].y - shift, d2 = v[i].z - shift, d3 = v[i].w - shift;
+                float s1 = (d0 + d1) + (d2 + d3);
+                float s2 = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) {
+                    float* so = stats + (row * nv + i) * 3;
+                    so[0] = shift;
+                    so[1] = s1;
+                    so[2] = s2;
                 }
-            }
-            s1 = warp_sum(s1);
-            s2 = warp_sum(s2);
-            if (lane == 0) {
-                float* so = stats + (row * ng + g) * 3;
-                so[0] = shift;
-                so[1] = s1;
-                so[2] = s2;
             }
         }
     }
 }
 
-constexpr int ROW_MAXV = 8;   // up to C = 1024 channels per token row
 
 // ---------------------------------------------------------------------------------------------
 // embed (DSTformer.py:330-337): joints_embed Linear(3->C) + pos_embed[j] + temp_embed[f]
 // ---------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ xin, int dim_in,
                                                      const float* __restrict__ W,      // [C, dim_in]
                                                      const float* __restrict__ bias,   // [C]
@@ -85,10 +82,10 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ xi
     const int f = (row / J) % F;
     float in[8];
     for (int k = 0; k < dim_in && k < 8; ++k) in[k] = xin[static_cast<size_t>(row) * dim_in + k];
-    float4 v[ROW_MAXV];
-    const int nv = C / 128;
+    float4 v[NV];
+    constexpr int nv = NV;
 #pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         if (i < nv) {
             const int c = 128 * i + 4 * lane;
             float o[4];
@@ -104,13 +101,14 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ xi
                                (o[3] + pe.w) + te.w);
         }
     }
-    emit_row<ROW_MAXV>(v, nv, row, C, x, hi, lo, stats);
+    emit_row<NV>(v, nv, row, C, x, hi, lo, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
 // S/T stream fusion (DSTformer.py:343-349): alpha = softmax(Linear(2C->2)(cat[x_st, x_ts])) per token
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ xst, const float* __restrict__ xts,
+template <int NV>
+__global__ void __launch_bounds__(256, 4) fuse_kernel(const float* __restrict__ xst, const float* __restrict__ xts,
                                                     const float* __restrict__ Wa,   // [2, 2C]
                                                     const float* __restrict__ ba,   // [2]
                                                     int M, int C, float* __restrict__ x,
@@ -119,12 +117,12 @@ __global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ xst
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = lane_id();
-    const int nv = C / 128;
+    constexpr int nv = NV;
     const size_t base = static_cast<size_t>(row) * C;
-    float4 a[ROW_MAXV], b[ROW_MAXV];
+    float4 a[NV], b[NV];
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         if (i < nv) {
             const int c = 128 * i + 4 * lane;
             a[i] = *reinterpret_cast<const float4*>(xst + base + c);
@@ -145,14 +143,14 @@ __global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ xst
     const float e0 = expf(d0 - mx), e1 = expf(d1 - mx);
     const float inv = 1.0f / (e0 + e1);
     const float al0 = e0 * inv, al1 = e1 * inv;
-    float4 v[ROW_MAXV];
+    float4 v[NV];
 #pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         if (i < nv)
             v[i] = make_float4(a[i].x * al0 + b[i].x * al1, a[i].y * al0 + b[i].y * al1, a[i].z * al0 + b[i].z * al1,
                                a[i].w * al0 + b[i].w * al1);
     }
-    emit_row<ROW_MAXV>(v, nv, row, C, x, hi, lo, stats);
+    emit_row<NV>(v, nv, row, C, x, hi, lo, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,18 +209,19 @@ __global__ void __launch_bounds__(256) pack_linear_kernel(const float* __restric
 }
 
 // fp32 [M,K] -> hi/lo planes + LN partial stats (used by the test hooks to feed the GEMM)
+template <int NV>
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ xin, int M, int C,
                                                           __nv_bfloat16* __restrict__ hi,
                                                           __nv_bfloat16* __restrict__ lo, float* __restrict__ stats) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = lane_id();
-    const int nv = C / 128;
-    float4 v[ROW_MAXV];
+    constexpr int nv = NV;
+    float4 v[NV];
 #pragma unroll
-    for (int i = 0; i < ROW_MAXV; ++i)
-        if (i < nv) v[i] = *reinterpret_cast<const float4*>(xin + static_cast<size_t>(row) * C + 128 * i + 4 * lane);
-    emit_row<ROW_MAXV>(v, nv, row, C, nullptr, hi, lo, stats);
+    for (int i = 0; i < NV; ++i)
+        v[i] = *reinterpret_cast<const float4*>(xin + static_cast<size_t>(row) * C + 128 * i + 4 * lane);
+    emit_row<NV>(v, nv, row, C, nullptr, hi, lo, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -392,7 +391,7 @@ __global__ void __launch_bounds__(128) attn_t_ref_kernel(const __nv_bfloat16* __
 
 // ---------------------------------------------------------------------------------------------
 // Bring-up / test reference GEMM on CUDA cores with the same fused epilogues as gemm_tc_kernel.
-// One warp per (row, 256-column group); lanes stride the group's columns.
+// One warp per (row, 128-column group); lanes stride the group's columns.
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(256) gemm_ref_kernel(const __nv_bfloat16* __restrict__ a_hi,

@@ -20,7 +20,7 @@ run k_attn1    300 $PT tests/test_gpu_kernels.py -k "temporal_attention_bf16"
 run f_simt     900 $PT tests/test_gpu_forward.py -k "simt" -s
 run f_main     900 $PT tests/test_gpu_forward.py -k "not simt" -s
 run smoke      600 python __graft_entry__.py smoke
-run bench_s    600 python bench.py --steps 3 --warmup 3 --batch 32 --no-cpu-baseline
+[ -n "$SKIP_BENCH_S" ] || run bench_s    600 python bench.py --steps 3 --warmup 3 --batch 32 --no-cpu-baseline
 run bench      900 python bench.py --steps 5 --warmup 3
 for f in k_ref k_gemm k_gemm1 k_attn k_attn1 f_simt f_main smoke bench_s bench; do
   echo "----- $f"; tail -n ${TAILN:-12} gpurun_out/$f.log

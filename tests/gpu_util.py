@@ -12,7 +12,7 @@ def _scratch(nbytes, device):
 
 
 def test_linear(mode, A, W, bias, gamma=None, beta=None, resid=None, eps=1e-6, math=0, use_ref=0):
-    """Returns (y fp32 [M,N], stats [M, N/256, 3] or None)."""
+    """Returns (y fp32 [M,N], stats [M, N/128, 3] or None)."""
     lib = _lib.load()
     dev = A.device
     M, K = A.shape
@@ -21,7 +21,7 @@ def test_linear(mode, A, W, bias, gamma=None, beta=None, resid=None, eps=1e-6, m
     _lib.check(lib.mb_test_linear_scratch_bytes(M, N, K, ctypes.byref(nb)))
     keep, sp = _scratch(nb.value, dev)
     y = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
-    stats = torch.zeros(M, N // 256, 3, dtype=torch.float32, device=dev) if mode == 2 else None
+    stats = torch.zeros(M, N // 128, 3, dtype=torch.float32, device=dev) if mode == 2 else None
     ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
     with torch.cuda.device(dev):
         st = torch.cuda.current_stream(dev).cuda_stream
