@@ -71,6 +71,7 @@ typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 /* flags for mb_forward */
 #define MB_FLAG_REF_GEMM   0x1u   /* TEST ONLY: CUDA-core reference GEMM instead of tcgen05           */
 #define MB_FLAG_REF_ATTN_T 0x2u   /* TEST ONLY: CUDA-core reference temporal attention                */
+#define MB_FLAG_GEMM_1CTA  0x4u   /* TEST ONLY: first-generation 1-CTA tcgen05 GEMM (LSU epilogue)    */
 
 int mb_version(void);
 const char* mb_last_error(void);
@@ -131,7 +132,7 @@ int mb_profile_read(MbEncoder* enc, float* ms_by_class, int* launches_by_class);
  * mode: 0 LN-folded split (returns hi+lo as fp32), 1 LN+GELU split, 2 residual (+stats), 3 LN+tanh, 4 bias.
  * gamma/beta (LN modes) and resid (mode 2) may be NULL otherwise.  stats_out (mode 2): [M][N/128][3]. */
 int mb_test_linear_scratch_bytes(int M, int N, int K, size_t* bytes);
-int mb_test_linear(int mode, int math, int use_ref, int M, int N, int K, const float* A, const float* W,
+int mb_test_linear(int mode, int math, int use_ref /* 0: 2-CTA tcgen05 (product), 1: CUDA-core reference, 2: 1-CTA tcgen05 */, int M, int N, int K, const float* A, const float* W,
                    const float* bias, const float* gamma, const float* beta, const float* resid, float eps,
                    float* y, float* stats_out, void* scratch, size_t scratch_bytes, void* stream);
 

@@ -1,0 +1,344 @@
+// 2-CTA (cta_group::2) tcgen05 GEMM with a TMA-fed / TMA-drained epilogue  --  the production GEMM.
+//
+//   D[M,N] = A[M,K] * W[N,K]^T, operands as bf16 hi/lo planes (see gemm_tc.cuh for the arithmetic modes and
+//   the fused epilogues; this kernel shares GemmParams / EPI_* with it).
+//
+// Why a second kernel: ncu on the 1-CTA version (profiles/r01_*) showed (a) L1TEX saturated (65-70 %) by the
+// epilogue's row-strided 16-byte global accesses, which also starves the TMA->smem operand feed, and (b) 48 KB
+// of operands per 768 MMA-cycles per SM.  Here:
+//   * a CTA PAIR (cluster 2x1, same TPC) computes a 256 x 256 tile with UMMA M=256: each CTA stages only its own
+//     128 A rows and HALF of the B tile (32 KB / stage instead of 48 KB), the leader CTA's single thread issues the
+//     MMAs for both SMs, completion is multicast to both CTAs' barriers (tcgen05.commit ... multicast::cluster);
+//   * the epilogue never touches global memory with LSU instructions for tile data: the residual tile arrives by
+//     TMA into swizzled smem (one 32x32 fp32 box per warp, prefetched one chunk ahead), results are written to
+//     swizzled smem staging and leave through TMA stores (cp.async.bulk.tensor ... bulk_group), fully coalesced,
+//     rows beyond M clipped by the tensor map.
+// Warp roles per CTA (320 threads): w0 TMA producer, w1 MMA issuer (leader CTA only) + TMEM alloc,
+// w2..w9 epilogue (lane quadrant = warp%4, column half = (warp-2)/4, 4 chunks of 32 columns each).
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace mb {
+
+constexpr int G2_STAGES = 4;
+constexpr int G2_THREADS = 320;
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_EPI_THREADS_PAIR = 2 * G2_EPI_WARPS * 32;   // arrivals on the leader's tmem-empty barrier
+constexpr int G2_STAGING_PER_WARP = 12288;                   // buf0 4 KB | buf1 4 KB | split 4 KB
+
+template <int PASSES>
+struct Gemm2Cfg {
+    static constexpr int BK = (PASSES == 3) ? 32 : 64;
+    static constexpr int SWZ = BK * 2;
+    static constexpr uint32_t LAYOUT = (SWZ == 128) ? 2u : 4u;
+    static constexpr int PLANES = (PASSES == 3) ? 2 : 1;
+    static constexpr int A_PLANE = 128 * SWZ;                  // this CTA's 128 rows of A
+    static constexpr int B_PLANE = 128 * SWZ;                  // this CTA's half (128 of 256 rows) of the W tile
+    static constexpr int A_BYTES = PLANES * A_PLANE;
+    static constexpr int B_BYTES = PLANES * B_PLANE;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB
+    static constexpr int OFF_STAGING = G2_STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_STAGING + G2_EPI_WARPS * G2_STAGING_PER_WARP;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+};
+
+template <int PASSES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane), box (BK, 128, PLANES)
+             const __grid_constant__ CUtensorMap tmB,   // bf16 3D (K, N, plane), box (BK, 128, PLANES)
+             const __grid_constant__ CUtensorMap tmR,   // fp32 2D (N, M) residual,    box (32, 32)         [RESID]
+             const __grid_constant__ CUtensorMap tmX,   // fp32 2D (N, M) output,      box (32, 32)         [RESID/F32]
+             const __grid_constant__ CUtensorMap tmS,   // bf16 3D (N, M, plane) out,  box (32, 32, PLANES) [RESID/SPLIT]
+             const GemmParams p) {
+    using Cfg = Gemm2Cfg<PASSES>;
+    constexpr bool kResid = (EPI == EPI_RESID);
+    constexpr bool kF32Out = (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32);
+    constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT);
+    constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* full_bar = bars;                             // [STAGES] leader's is the one in use
+    uint64_t* empty_bar = bars + G2_STAGES;                // [STAGES] per CTA, multicast-committed by the leader
+    uint64_t* tfull_bar = bars + 2 * G2_STAGES;            // [2]      per CTA, multicast-committed by the leader
+    uint64_t* tempty_bar = bars + 2 * G2_STAGES + 2;       // [2]      leader's: 512 epilogue threads of the pair
+    uint64_t* rbar = bars + 2 * G2_STAGES + 4;             // [8 warps][2] residual-tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + 2 * G2_EPI_WARPS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+
+    const int num_mp = (p.M + 255) / 256;
+    const int num_n = p.N / 256;
+    const int num_tiles = num_mp * num_n;
+    const int num_kb = p.K / Cfg::BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (kResid) tma_prefetch_desc(&tmR);
+        if (kF32Out) tma_prefetch_desc(&tmX);
+        if (kSplitOut) tma_prefetch_desc(&tmS);
+        for (int i = 0; i < G2_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], G2_EPI_THREADS_PAIR);
+        }
+        for (int i = 0; i < 2 * G2_EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                const int m_pair = tile / num_n, n_idx = tile % num_n;
+                const int a_row = m_pair * 256 + static_cast<int>(rank) * 128;
+                const int b_row = n_idx * 256 + static_cast<int>(rank) * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sB = sA + Cfg::A_BYTES;
+                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    tma_load_3d_2cta(sA, &tmA, full_leader, kb * Cfg::BK, a_row, 0);
+                    tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::BK, b_row, 0);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t IDESC = umma_idesc_bf16(256, 256, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint32_t sB = sA + Cfg::A_BYTES;
+                        const uint64_t a_hi = umma_smem_desc(sA, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        const uint64_t b_hi = umma_smem_desc(sB, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        const uint64_t a_lo = umma_smem_desc(sA + Cfg::A_PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        const uint64_t b_lo = umma_smem_desc(sB + Cfg::B_PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+#pragma unroll
+                        for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
+                            const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
+                            if (PASSES == 3) {
+                                umma_ss_2cta(d_tmem, a_lo + koff, b_hi + koff, IDESC, (kb | ks) != 0);
+                                umma_ss_2cta(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1);
+                                umma_ss_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1);
+                            } else {
+                                umma_ss_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, (kb | ks) != 0);
+                            }
+                        }
+                        tc_commit_2cta(&empty_bar[stage], 3);
+                        if (kb == num_kb - 1) tc_commit_2cta(&tfull_bar[acc], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int half = ew >> 2;
+        constexpr int NCH = 4;
+        uint8_t* stg = smem + Cfg::OFF_STAGING + ew * G2_STAGING_PER_WARP;
+        uint8_t* buf[2] = {stg, stg + 4096};
+        uint8_t* bufS = stg + 8192;
+        uint64_t* my_rbar = rbar + 2 * ew;
+        const int ngrp_out = p.N / STATS_GROUP;
+        const uint32_t sw128 = static_cast<uint32_t>(lane & 7);          // SWIZZLE_128B: chunk16 ^= row % 8
+        const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3);    // SWIZZLE_64B : chunk16 ^= (row / 2) % 4
+
+        auto chunk_coords = [&](int tile, int ch, int& col0, int& rowb) {
+            const int m_pair = tile / num_n, n_idx = tile % num_n;
+            col0 = n_idx * 256 + half * 128 + ch * 32;
+            rowb = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32;
+        };
+        uint32_t ci = 0;   // chunks processed by this warp (buffer parity / rbar phase)
+        if (kResid && lane == 0 && pair < num_tiles) {
+            int c0, r0;
+            chunk_coords(pair, 0, c0, r0);
+            mbar_arrive_expect_tx(&my_rbar[0], 4096);
+            tma_load_2d(buf[0], &tmR, &my_rbar[0], c0, r0);
+        }
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += npairs) {
+            const int m_pair = tile / num_n, n_idx = tile % num_n;
+            const int row = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32 + lane;
+            const bool row_ok = row < p.M;
+
+            float mean = 0.f, rstd = 1.f, rscale = 1.f;
+            if (kLn) {
+                if (row_ok) ln_row_stats(p.stats_in + static_cast<size_t>(row) * p.nh_in * 3, p.nh_in, p.ln_dim,
+                                         p.eps, mean, rstd);
+            }
+            if (kResid) {
+                if (row_ok && p.row_scale) rscale = p.row_scale[row / p.J];
+            }
+            float st_shift = 0.f, st_sum = 0.f, st_sq = 0.f;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * 256 + half * 128 + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch, ++ci) {
+                const int b = ci & 1;
+                int col0, rowb;
+                chunk_coords(tile, ch, col0, rowb);
+                if (kResid) {
+                    mbar_wait(&my_rbar[b], (ci >> 1) & 1);            // residual chunk landed in buf[b]
+                    if (lane == 0) {
+                        tma_store_wait_read<0>();                      // group ci-1 no longer reads buf[b^1] / bufS
+                        int nt = tile, nc = ch + 1;
+                        if (nc == NCH) { nc = 0; nt = tile + npairs; }
+                        if (nt < num_tiles) {
+                            int c1, r1;
+                            chunk_coords(nt, nc, c1, r1);
+                            mbar_arrive_expect_tx(&my_rbar[b ^ 1], 4096);
+                            tma_load_2d(buf[b ^ 1], &tmR, &my_rbar[b ^ 1], c1, r1);
+                        }
+                    }
+                } else {
+                    if (lane == 0) tma_store_wait_read<1>();           // group ci-2 no longer reads buf[b]
+                }
+                uint32_t r[32];
+                tmem_ld32(t_row + ch * 32, r);
+                tmem_ld_wait();
+                float v[32];
+                if (kResid) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bb = __ldg(b4 + i);
+                        const float4 x = *reinterpret_cast<const float4*>(buf[b] + lane * 128 + ((i ^ sw128) << 4));
+                        v[4 * i + 0] = x.x + rscale * (__uint_as_float(r[4 * i + 0]) + bb.x);
+                        v[4 * i + 1] = x.y + rscale * (__uint_as_float(r[4 * i + 1]) + bb.y);
+                        v[4 * i + 2] = x.z + rscale * (__uint_as_float(r[4 * i + 2]) + bb.z);
+                        v[4 * i + 3] = x.w + rscale * (__uint_as_float(r[4 * i + 3]) + bb.w);
+                    }
+                    if (ch == 0) st_shift = v[0];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float d = v[i] - st_shift;
+                        st_sum += d;
+                        st_sq = fmaf(d, d, st_sq);
+                    }
+                } else if (EPI == EPI_BIAS_F32) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bb = __ldg(b4 + i);
+                        v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
+                        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+                        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+                        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                    }
+                } else {
+                    const float4* c4 = reinterpret_cast<const float4*>(p.vec0 + col0);
+                    const float4* s4 = reinterpret_cast<const float4*>(p.vec1 + col0);
+                    const float ms = -mean * rstd;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 c = __ldg(c4 + i);
+                        const float4 s = __ldg(s4 + i);
+                        v[4 * i + 0] = fmaf(rstd, __uint_as_float(r[4 * i + 0]), fmaf(ms, s.x, c.x));
+                        v[4 * i + 1] = fmaf(rstd, __uint_as_float(r[4 * i + 1]), fmaf(ms, s.y, c.y));
+                        v[4 * i + 2] = fmaf(rstd, __uint_as_float(r[4 * i + 2]), fmaf(ms, s.z, c.z));
+                        v[4 * i + 3] = fmaf(rstd, __uint_as_float(r[4 * i + 3]), fmaf(ms, s.w, c.w));
+                    }
+                    if (EPI == EPI_LN_GELU_SPLIT) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                    }
+                    if (EPI == EPI_LN_TANH_F32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+                    }
+                }
+                // all lanes have consumed buf[b] (residual) and lane 0 has seen the older store groups retire
+                __syncwarp();
+                uint8_t* xs = buf[b];                                   // fp32 staging (aliases the residual tile)
+                uint8_t* ss = kResid ? bufS : buf[b];                   // split staging
+                if (kF32Out) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(xs + lane * 128 + ((i ^ sw128) << 4)) =
+                            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                if (kSplitOut) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        *reinterpret_cast<uint4*>(ss + lane * 64 + ((i ^ sw64) << 4)) =
+                            make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                        if (PASSES == 3)
+                            *reinterpret_cast<uint4*>(ss + 2048 + lane * 64 + ((i ^ sw64) << 4)) =
+                                make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (kF32Out) tma_store_2d(&tmX, xs, col0, rowb);
+                    if (kSplitOut) tma_store_3d(&tmS, ss, col0, rowb, 0);
+                    tma_store_commit();
+                }
+            }
+            // every TMEM read of this accumulator is complete -> release it to the leader's MMA warp
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+            if (kResid) {
+                if (row_ok && p.stats_out) {
+                    float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;
+                    so[0] = st_shift;
+                    so[1] = st_sum;
+                    so[2] = st_sq;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta<512>(tmem_base);
+    }
+}
+
+}  // namespace mb

@@ -16,6 +16,7 @@
 #include "../../include/motionbert_b200.h"
 #include "attn_t_tc.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "simt_kernels.cuh"
 
 using namespace mb;
@@ -70,9 +71,10 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// bf16 tensor map of rank `rank`; dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1.
+// tensor map of rank `rank` (bf16, or fp32 when elem_bytes == 4); dims/strides innermost first; strides in
+// ELEMENTS for dims 1..rank-1.
 static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                     const uint32_t* box, int swizzle_bytes) {
+                     const uint32_t* box, int swizzle_bytes, int elem_bytes = 2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     if (reinterpret_cast<uintptr_t>(base) & 15) return fail(MB_ERR_ALIGN, "tensor map base not 16-byte aligned");
@@ -82,16 +84,32 @@ static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_
         gdim[i] = dims[i];
         bdim[i] = box[i];
         estr[i] = 1;
-        if (i > 0) gstr[i - 1] = strides_el[i - 1] * 2;   // bytes
+        if (i > 0) gstr[i - 1] = strides_el[i - 1] * static_cast<uint64_t>(elem_bytes);   // bytes
     }
     CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                   : CU_TENSOR_MAP_SWIZZLE_32B;
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+    CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return MB_OK;
+}
+
+// fp32 [rows, cols] row-major matrix, 32x32 boxes, SWIZZLE_128B (epilogue residual loads / fp32 stores)
+static int make_f32_tile_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols) {
+    const uint64_t dims[2] = {cols, rows};
+    const uint64_t str[1] = {cols};
+    const uint32_t box[2] = {32, 32};
+    return make_tmap(out, base, 2, dims, str, box, 128, 4);
+}
+// bf16 hi/lo planes [2][rows, cols] (plane stride in elements), 32x32xplanes boxes, SWIZZLE_64B (epilogue split stores)
+static int make_split_store_tmap(CUtensorMap* out, const void* hi, uint64_t rows, uint64_t cols, uint64_t plane_el,
+                                 int passes) {
+    const uint64_t dims[3] = {cols, rows, 2};
+    const uint64_t str[2] = {cols, plane_el};
+    const uint32_t box[3] = {32, 32, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
+    return make_tmap(out, hi, 3, dims, str, box, 64, 2);
 }
 
 // ------------------------------------------------------------------------------------ per-device init
@@ -126,6 +144,12 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         SET_GEMM(1, EPI_LN_SPLIT); SET_GEMM(1, EPI_LN_GELU_SPLIT); SET_GEMM(1, EPI_RESID);
         SET_GEMM(1, EPI_LN_TANH_F32); SET_GEMM(1, EPI_BIAS_F32);
 #undef SET_GEMM
+#define SET_GEMM2(P, E) CUDA_TRY(set_smem(gemm2_kernel<P, E>, Gemm2Cfg<P>::SMEM_BYTES))
+        SET_GEMM2(3, EPI_LN_SPLIT); SET_GEMM2(3, EPI_LN_GELU_SPLIT); SET_GEMM2(3, EPI_RESID);
+        SET_GEMM2(3, EPI_LN_TANH_F32); SET_GEMM2(3, EPI_BIAS_F32);
+        SET_GEMM2(1, EPI_LN_SPLIT); SET_GEMM2(1, EPI_LN_GELU_SPLIT); SET_GEMM2(1, EPI_RESID);
+        SET_GEMM2(1, EPI_LN_TANH_F32); SET_GEMM2(1, EPI_BIAS_F32);
+#undef SET_GEMM2
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 3>, AttnCfg<64, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<32, 3>, AttnCfg<32, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 1>, AttnCfg<64, 1>::SMEM_BYTES));
@@ -149,7 +173,8 @@ struct LinearPack {
     bool ln = false;
     int p_w = -1, p_b = -1, p_g = -1, p_beta = -1;   // indices into the parameter list
     size_t off_hi = 0, off_lo = 0, off_c = 0, off_s = 0;   // byte offsets into the packed buffer
-    CUtensorMap tmap;                                   // valid for `packed_ptr`
+    CUtensorMap tmap;                                   // 1-CTA kernel: box rows 256; valid for `packed_ptr`
+    CUtensorMap tmap2;                                  // 2-CTA kernel: box rows 128 (half of the W tile per CTA)
 };
 
 struct ActBuf {
@@ -158,6 +183,8 @@ struct ActBuf {
     __nv_bfloat16* lo;
     float* stats;
     CUtensorMap tmap;   // A-operand map over (hi, lo)
+    CUtensorMap tm_x;   // fp32 32x32 tile map over x (residual in / output)
+    CUtensorMap tm_st;  // split-store map over (hi, lo)
 };
 
 struct Plan {
@@ -169,6 +196,7 @@ struct Plan {
     __nv_bfloat16* ao = nullptr;    // planes [2][M][C]
     float* rep_ws = nullptr;
     CUtensorMap tm_hid, tm_ao, tm_q, tm_kv;
+    CUtensorMap tm_qkv_st, tm_hid_st;   // split-store maps of the qkv / hidden buffers
 };
 
 struct MbEncoder {
@@ -401,6 +429,8 @@ extern "C" int mb_pack_weights(MbEncoder* enc, const float* const* params, void*
         const uint32_t box[3] = {static_cast<uint32_t>(BK), static_cast<uint32_t>(GEMM_BN), static_cast<uint32_t>(passes == 3 ? 2 : 1)};
         int rc = make_tmap(&L.tmap, base + L.off_hi, 3, dims, str, box, BK * 2);
         if (rc) return rc;
+        const uint32_t box2[3] = {static_cast<uint32_t>(BK), 128u, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
+        if ((rc = make_tmap(&L.tmap2, base + L.off_hi, 3, dims, str, box2, BK * 2))) return rc;
     }
     const MbDesc& d = enc->d;
     auto copy = [&](size_t off, const float* src, size_t n) {
@@ -478,6 +508,8 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
         const int BK = passes == 3 ? 32 : 64;
         const uint32_t box[3] = {static_cast<uint32_t>(BK), GEMM_BM, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
         if ((rc = make_tmap(&a.tmap, a.hi, 3, dims, str, box, BK * 2))) return rc;
+        if ((rc = make_f32_tile_tmap(&a.tm_x, a.x, M, C))) return rc;
+        if ((rc = make_split_store_tmap(&a.tm_st, a.hi, M, C, (w.act_lo[i] - w.act_hi[i]) / 2, passes))) return rc;
     }
     P->qkv = reinterpret_cast<__nv_bfloat16*>(base + w.qkv);
     P->hid = P->qkv;
@@ -494,6 +526,8 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
         const uint64_t dims_a[3] = {C, M, 2};
         const uint64_t str_a[2] = {C, ao_plane_el};
         if ((rc = make_tmap(&P->tm_ao, P->ao, 3, dims_a, str_a, box, BK * 2))) return rc;
+        if ((rc = make_split_store_tmap(&P->tm_qkv_st, P->qkv, M, 3 * C, qkv_plane_el, passes))) return rc;
+        if ((rc = make_split_store_tmap(&P->tm_hid_st, P->hid, M, d.hidden, qkv_plane_el, passes))) return rc;
     }
     {
         const int hd = d.dim_feat / d.num_heads;
@@ -512,10 +546,17 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
 }
 
 // ------------------------------------------------------------------------------------ launches
+// Epilogue tensor maps of the 2-CTA kernel (unused ones may be null).
+struct EpiMaps {
+    const CUtensorMap* resid = nullptr;   // fp32 residual tile source       (EPI_RESID)
+    const CUtensorMap* out_x = nullptr;   // fp32 output                     (EPI_RESID / *_F32)
+    const CUtensorMap* out_s = nullptr;   // bf16 hi/lo split output         (EPI_RESID / *_SPLIT)
+};
+
 template <int EPI>
 static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tmA, const __nv_bfloat16* a_hi,
                        const __nv_bfloat16* a_lo, const LinearPack& L, const uint8_t* packed, GemmParams p,
-                       cudaStream_t st) {
+                       const EpiMaps& em, cudaStream_t st) {
     p.N = L.N;
     p.K = L.K;
     p.vec0 = reinterpret_cast<const float*>(packed + L.off_c);
@@ -533,13 +574,32 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
         LAUNCH_CHECK("gemm_ref_kernel");
         return MB_OK;
     }
-    const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / GEMM_BN);
-    const int grid = tiles < e->dev.sms ? tiles : e->dev.sms;
+    if (flags & MB_FLAG_GEMM_1CTA) {
+        const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / GEMM_BN);
+        const int grid = tiles < e->dev.sms ? tiles : e->dev.sms;
+        if (passes == 3)
+            gemm_tc_kernel<3, EPI><<<grid, GEMM_THREADS, GemmCfg<3>::SMEM_BYTES, st>>>(tmA, L.tmap, p);
+        else
+            gemm_tc_kernel<1, EPI><<<grid, GEMM_THREADS, GemmCfg<1>::SMEM_BYTES, st>>>(tmA, L.tmap, p);
+        LAUNCH_CHECK("gemm_tc_kernel");
+        return MB_OK;
+    }
+    // production path: CTA pairs (cluster 2x1), one pair per 256x256 tile, persistent
+    const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+    const int max_pairs = e->dev.sms / 2;
+    const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+    const CUtensorMap& tmR = em.resid ? *em.resid : tmA;
+    const CUtensorMap& tmX = em.out_x ? *em.out_x : tmA;
+    const CUtensorMap& tmS = em.out_s ? *em.out_s : tmA;
+    if ((EPI == EPI_RESID && (!em.resid || !em.out_x || !em.out_s)) ||
+        ((EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) && !em.out_s) ||
+        ((EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32) && !em.out_x))
+        return fail(MB_ERR_INVALID, "internal: missing epilogue tensor map");
     if (passes == 3)
-        gemm_tc_kernel<3, EPI><<<grid, GEMM_THREADS, GemmCfg<3>::SMEM_BYTES, st>>>(tmA, L.tmap, p);
+        gemm2_kernel<3, EPI><<<grid, G2_THREADS, Gemm2Cfg<3>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else
-        gemm_tc_kernel<1, EPI><<<grid, GEMM_THREADS, GemmCfg<1>::SMEM_BYTES, st>>>(tmA, L.tmap, p);
-    LAUNCH_CHECK("gemm_tc_kernel");
+        gemm2_kernel<1, EPI><<<grid, G2_THREADS, Gemm2Cfg<1>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
+    LAUNCH_CHECK("gemm2_kernel");
     return MB_OK;
 }
 
@@ -665,7 +725,9 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         p.stats_in = src.stats;
         p.out_hi = P.qkv;
         p.out_lo = P.qkv + qkv_plane_el;
-        int r = launch_gemm<EPI_LN_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_QKV_T : L_QKV_S], pk, p, st);
+        EpiMaps em;
+        em.out_s = &P.tm_qkv_st;
+        int r = launch_gemm<EPI_LN_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_QKV_T : L_QKV_S], pk, p, em, st);
         if (r) return r;
         r = launch_attn(enc, flags, temporal, P, B, F, qkv_plane_el, ao_plane_el, st);
         if (r) return r;
@@ -676,7 +738,11 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         q.out_hi = dst.hi;
         q.out_lo = dst.lo;
         q.stats_out = dst.stats;
-        return launch_gemm<EPI_RESID>(enc, flags, P.tm_ao, P.ao, P.ao + ao_plane_el, L[temporal ? L_PROJ_T : L_PROJ_S], pk, q, st);
+        EpiMaps em2;
+        em2.resid = &src.tm_x;
+        em2.out_x = &dst.tm_x;
+        em2.out_s = &dst.tm_st;
+        return launch_gemm<EPI_RESID>(enc, flags, P.tm_ao, P.ao, P.ao + ao_plane_el, L[temporal ? L_PROJ_T : L_PROJ_S], pk, q, em2, st);
     };
     // one residual MLP sublayer: dst = src + fc2(gelu(fc1(LN(src))))             (DSTformer.py:242,244,247,249)
     auto mlp_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst) -> int {
@@ -684,7 +750,9 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         p.stats_in = src.stats;
         p.out_hi = P.hid;
         p.out_lo = P.hid + qkv_plane_el;
-        int r = launch_gemm<EPI_LN_GELU_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_FC1_T : L_FC1_S], pk, p, st);
+        EpiMaps em;
+        em.out_s = &P.tm_hid_st;
+        int r = launch_gemm<EPI_LN_GELU_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_FC1_T : L_FC1_S], pk, p, em, st);
         if (r) return r;
         GemmParams q = base;
         q.resid = src.x;
@@ -693,7 +761,11 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         q.out_hi = dst.hi;
         q.out_lo = dst.lo;
         q.stats_out = dst.stats;
-        return launch_gemm<EPI_RESID>(enc, flags, P.tm_hid, P.hid, P.hid + qkv_plane_el, L[temporal ? L_FC2_T : L_FC2_S], pk, q, st);
+        EpiMaps em2;
+        em2.resid = &src.tm_x;
+        em2.out_x = &dst.tm_x;
+        em2.out_s = &dst.tm_st;
+        return launch_gemm<EPI_RESID>(enc, flags, P.tm_hid, P.hid, P.hid + qkv_plane_el, L[temporal ? L_FC2_T : L_FC2_S], pk, q, em2, st);
     };
 
     const ActBuf& X0 = P.act[0];
@@ -728,7 +800,11 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         GemmParams p = base;
         p.stats_in = X0.stats;
         p.out_f32 = rep_buf;
-        if ((rc = launch_gemm<EPI_LN_TANH_F32>(enc, flags, X0.tmap, X0.hi, X0.lo, enc->lin.back(), pk, p, st))) return rc;
+        CUtensorMap tm_rep;
+        if ((rc = make_f32_tile_tmap(&tm_rep, rep_buf, M_, d.dim_rep))) return rc;
+        EpiMaps em;
+        em.out_x = &tm_rep;
+        if ((rc = launch_gemm<EPI_LN_TANH_F32>(enc, flags, X0.tmap, X0.hi, X0.lo, enc->lin.back(), pk, p, em, st))) return rc;
     }
     if (out) {
         prof_mark(enc, st, PC_HEAD);
@@ -902,11 +978,30 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
         const uint32_t bB[3] = {static_cast<uint32_t>(BK), GEMM_BN, pl};
         if ((rc = make_tmap(&tmB, w_hi, 3, dB, sB, bB, BK * 2))) return rc;
     }
+    CUtensorMap tmB2, tmR, tmX, tmS;
+    {
+        const int BK = passes == 3 ? 32 : 64;
+        const uint32_t pl = passes == 3 ? 2 : 1;
+        const uint64_t dB[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), 2};
+        const uint64_t sB[2] = {static_cast<uint64_t>(K), (s.w_lo - s.w_hi) / 2};
+        const uint32_t bB[3] = {static_cast<uint32_t>(BK), 128u, pl};
+        if ((rc = make_tmap(&tmB2, w_hi, 3, dB, sB, bB, BK * 2))) return rc;
+        if ((rc = make_f32_tile_tmap(&tmR, resid ? resid : y, M, N))) return rc;
+        if ((rc = make_f32_tile_tmap(&tmX, y, M, N))) return rc;
+        if ((rc = make_split_store_tmap(&tmS, o_hi, M, N, (s.o_lo - s.o_hi) / 2, passes))) return rc;
+    }
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
     const int grid = tiles < info.sms ? tiles : info.sms;
+    const int tiles2 = ((M + 255) / 256) * (N / 256);
+    const int grid2 = 2 * (tiles2 < info.sms / 2 ? tiles2 : info.sms / 2);
 #define RUN(E)                                                                                                       \
     do {                                                                                                             \
-        if (use_ref) {                                                                                               \
+        if (use_ref == 0) {                                                                                          \
+            if (passes == 3)                                                                                         \
+                gemm2_kernel<3, E><<<grid2, G2_THREADS, Gemm2Cfg<3>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
+            else                                                                                                     \
+                gemm2_kernel<1, E><<<grid2, G2_THREADS, Gemm2Cfg<1>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
+        } else if (use_ref == 1) {                                                                                   \
             const long warps = static_cast<long>(M) * (N / STATS_GROUP);                                             \
             gemm_ref_kernel<E><<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(a_hi, passes == 3 ? a_lo : nullptr, w_hi, \
                                                                                    passes == 3 ? w_lo : nullptr, p);  \

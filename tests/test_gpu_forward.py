@@ -61,6 +61,14 @@ def test_forward_matches_reference_golden(cuda_device, name):
     _check_against_golden(out, rep, g, cfg, name)
 
 
+def test_forward_first_generation_1cta_gemm_still_matches(cuda_device):
+    cfg, P, x, g = load_case("base_b2_f27")
+    m = build_module(cfg, P, cuda_device)
+    m._kernel_flags = _lib.MB_FLAG_GEMM_1CTA
+    out, rep = _run(m, x, cuda_device)
+    _check_against_golden(out, rep, g, cfg, "base_b2_f27/1cta")
+
+
 def test_forward_matches_cpu_oracle_on_fresh_inputs(cuda_device):
     cfg = O.LITE
     P = O.make_params(cfg, 99)

@@ -42,10 +42,11 @@ def _expected(mode, A, W, b, gamma, beta, resid, eps):
     return y
 
 
-SHAPES = [(128, 256, 256), (300, 512, 512), (1000, 1536, 512), (77, 512, 1024), (4131, 1024, 512), (459, 768, 256)]
+SHAPES = [(128, 256, 256), (300, 512, 512), (1000, 1536, 512), (77, 512, 1024), (4131, 1024, 512), (459, 768, 256),
+          (40000, 512, 512)]
 
 
-@pytest.mark.parametrize("use_ref", [1, 0], ids=["simt_ref", "tcgen05"])
+@pytest.mark.parametrize("use_ref", [1, 2, 0], ids=["simt_ref", "tc1cta", "tc2cta"])
 @pytest.mark.parametrize("mode", [4, 0, 1, 2, 3], ids=["bias", "ln_split", "ln_gelu", "resid", "ln_tanh"])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_linear_bf16x3(cuda_device, M, N, K, mode, use_ref):
