@@ -16,6 +16,7 @@ MB_MATH_BF16 = 1
 MB_FLAG_REF_GEMM = 0x1
 MB_FLAG_REF_ATTN_T = 0x2
 MB_FLAG_GEMM_1CTA = 0x4
+MB_FLAG_REF_ATTN_S = 0x8
 
 # every symbol include/motionbert_b200.h declares
 EXPORTS = [

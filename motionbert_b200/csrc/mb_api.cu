@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/motionbert_b200.h"
+#include "attn_s_tc.cuh"
 #include "attn_t_tc.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
@@ -154,6 +155,10 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(attn_t_tc_kernel<32, 3>, AttnCfg<32, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 1>, AttnCfg<64, 1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<32, 1>, AttnCfg<32, 1>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s_tc_kernel<64, 3>, AttnSCfg<64, 3>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s_tc_kernel<32, 3>, AttnSCfg<32, 3>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s_tc_kernel<64, 1>, AttnSCfg<64, 1>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s_tc_kernel<32, 1>, AttnSCfg<32, 1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_s_kernel<64>, 200 * 1024));
         CUDA_TRY(set_smem(attn_s_kernel<32>, 200 * 1024));
         CUDA_TRY(set_smem(attn_t_ref_kernel<64>, 200 * 1024));
@@ -197,6 +202,7 @@ struct Plan {
     float* rep_ws = nullptr;
     CUtensorMap tm_hid, tm_ao, tm_q, tm_kv;
     CUtensorMap tm_qkv_st, tm_hid_st;   // split-store maps of the qkv / hidden buffers
+    CUtensorMap tm_qkv_sp;              // 4-D (col, joint, frame, plane) view of qkv for spatial attention
 };
 
 struct MbEncoder {
@@ -541,6 +547,10 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
         const uint32_t box_kv[5] = {static_cast<uint32_t>(hd), 1, NK, 1, planes};
         if ((rc = make_tmap(&P->tm_q, P->qkv, 5, dims, str, box_q, hd * 2))) return rc;
         if ((rc = make_tmap(&P->tm_kv, P->qkv, 5, dims, str, box_kv, hd * 2))) return rc;
+        const uint64_t dims4[4] = {C3, static_cast<uint64_t>(d.num_joints), static_cast<uint64_t>(B) * F, 2};
+        const uint64_t str4[3] = {C3, C3 * d.num_joints, qkv_plane_el};
+        const uint32_t box4[4] = {static_cast<uint32_t>(hd), ATS_SLAB, ATS_FRAMES, planes};
+        if ((rc = make_tmap(&P->tm_qkv_sp, P->qkv, 4, dims4, str4, box4, hd * 2))) return rc;
     }
     return MB_OK;
 }
@@ -614,11 +624,26 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     __nv_bfloat16* o_hi = P.ao;
     __nv_bfloat16* o_lo = passes == 3 ? P.ao + ao_plane_el : nullptr;
     prof_mark(e, st, temporal ? PC_ATTN_T : PC_ATTN_S);
-    if (!temporal) {
+    if (!temporal && (flags & MB_FLAG_REF_ATTN_S)) {
         const size_t smem = static_cast<size_t>(J) * 3 * C * 4;
         if (hd == 64) attn_s_kernel<64><<<B * F, 256, smem, st>>>(q_hi, q_lo, B * F, J, C, H, scale, o_hi, o_lo);
         else attn_s_kernel<32><<<B * F, 256, smem, st>>>(q_hi, q_lo, B * F, J, C, H, scale, o_hi, o_lo);
         LAUNCH_CHECK("attn_s_kernel");
+        return MB_OK;
+    }
+    if (!temporal) {
+        AttnSParams sp;
+        sp.BF = B * F; sp.J = J; sp.C = C; sp.H = H;
+        sp.scale_log2e = scale * 1.4426950408889634f;
+        sp.out_hi = o_hi;
+        sp.out_lo = o_lo;
+        const int prob = ((B * F + ATS_FRAMES - 1) / ATS_FRAMES) * H;
+        const int grid = prob < e->dev.sms ? prob : e->dev.sms;
+        if (hd == 64 && passes == 3) attn_s_tc_kernel<64, 3><<<grid, ATT_THREADS, AttnSCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        else if (hd == 32 && passes == 3) attn_s_tc_kernel<32, 3><<<grid, ATT_THREADS, AttnSCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        else if (hd == 64) attn_s_tc_kernel<64, 1><<<grid, ATT_THREADS, AttnSCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        else attn_s_tc_kernel<32, 1><<<grid, ATT_THREADS, AttnSCfg<32, 1>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        LAUNCH_CHECK("attn_s_tc_kernel");
         return MB_OK;
     }
     if (flags & MB_FLAG_REF_ATTN_T) {
@@ -1065,6 +1090,14 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(qkv, P.qkv, P.qkv + qkv_plane / 2, n);
         LAUNCH_CHECK("split_flat_kernel");
     }
+    if (!temporal && !use_ref) {
+        const int hd = C / H;
+        const uint64_t C3 = 3ull * C;
+        const uint64_t dims4[4] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(B) * F, 2};
+        const uint64_t str4[3] = {C3, C3 * J, qkv_plane / 2};
+        const uint32_t box4[4] = {static_cast<uint32_t>(hd), ATS_SLAB, ATS_FRAMES, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
+        if ((rc = make_tmap(&P.tm_qkv_sp, P.qkv, 4, dims4, str4, box4, hd * 2))) return rc;
+    }
     if (temporal && !use_ref) {
         const int hd = C / H;
         const uint64_t C3 = 3ull * C;
@@ -1077,7 +1110,8 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         if ((rc = make_tmap(&P.tm_q, P.qkv, 5, dims, str, box_q, hd * 2))) return rc;
         if ((rc = make_tmap(&P.tm_kv, P.qkv, 5, dims, str, box_kv, hd * 2))) return rc;
     }
-    rc = launch_attn(&e, use_ref ? MB_FLAG_REF_ATTN_T : 0u, temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st);
+    rc = launch_attn(&e, use_ref ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : 0u, temporal != 0, P, B, F, qkv_plane / 2,
+                     ao_plane / 2, st);
     if (rc) return rc;
     const size_t n = M * C;
     merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(P.ao, passes == 3 ? P.ao + ao_plane / 2 : nullptr, y, n);

@@ -12,17 +12,18 @@ run() {  # name, timeout, cmd...
   echo "=== $name exit $?" | tee -a gpurun_out/$name.log
 }
 PT="python -m pytest -q -p no:cacheprovider --timeout 300 -m gpu"
-run k_ref      600 $PT tests/test_gpu_kernels.py -k "simt_ref or spatial" -x
+run k_ref      600 $PT tests/test_gpu_kernels.py -k "simt_ref" -x
 run k_gemm     600 $PT tests/test_gpu_kernels.py -k "tc2cta and linear_bf16x3"
 run k_gemm_old 600 $PT tests/test_gpu_kernels.py -k "tc1cta and linear_bf16x3"
 run k_gemm1    300 $PT tests/test_gpu_kernels.py -k "single_pass and linear"
 run k_attn     600 $PT tests/test_gpu_kernels.py -k "tcgen05 and temporal_attention"
+run k_attns    600 $PT tests/test_gpu_kernels.py -k "tcgen05 and spatial_attention"
 run k_attn1    300 $PT tests/test_gpu_kernels.py -k "temporal_attention_bf16"
 run f_simt     900 $PT tests/test_gpu_forward.py -k "simt" -s
 run f_main     900 $PT tests/test_gpu_forward.py -k "not simt" -s
 run smoke      600 python __graft_entry__.py smoke
 [ -n "$SKIP_BENCH_S" ] || run bench_s    600 python bench.py --steps 3 --warmup 3 --batch 32 --no-cpu-baseline
 run bench      900 python bench.py --steps 5 --warmup 3
-for f in k_ref k_gemm k_gemm_old k_gemm1 k_attn k_attn1 f_simt f_main smoke bench_s bench; do
+for f in k_ref k_gemm k_gemm_old k_gemm1 k_attn k_attns k_attn1 f_simt f_main smoke bench_s bench; do
   echo "----- $f"; tail -n ${TAILN:-12} gpurun_out/$f.log
 done

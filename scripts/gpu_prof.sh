@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 NCU="ncu --clock-control none --profile-from-start off"
 timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/${TAG}_launches.csv \
    python scripts/prof_forward.py --batch $B > gpurun_out/${TAG}_launches.log 2>&1
-timeout 900 $NCU --set full --import-source on -k regex:gemm_tc -c 4 -o gpurun_out/${TAG}_gemm -f \
+timeout 900 $NCU --set full --import-source on -k regex:gemm2_kernel -c 4 -o gpurun_out/${TAG}_gemm -f \
    python scripts/prof_forward.py --batch $B > gpurun_out/${TAG}_gemm.log 2>&1
 timeout 900 $NCU --set full --import-source on -k regex:attn_ -c 2 -o gpurun_out/${TAG}_attn -f \
    python scripts/prof_forward.py --batch $B > gpurun_out/${TAG}_attn.log 2>&1

@@ -47,7 +47,7 @@ def test_forward_matches_reference_golden_simt_reference_kernels(cuda_device, na
     if x.shape[0] * x.shape[1] > 64:
         pytest.skip("CUDA-core reference GEMM is only run on the small cases")
     m = build_module(cfg, P, cuda_device)
-    m._kernel_flags = _lib.MB_FLAG_REF_GEMM | _lib.MB_FLAG_REF_ATTN_T
+    m._kernel_flags = _lib.MB_FLAG_REF_GEMM | _lib.MB_FLAG_REF_ATTN_T | _lib.MB_FLAG_REF_ATTN_S
     out, rep = _run(m, x, cuda_device)
     _check_against_golden(out, rep, g, cfg, name + "/simt")
 

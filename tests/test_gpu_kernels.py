@@ -104,15 +104,16 @@ def test_temporal_attention(cuda_device, B, F, J, C, H, use_ref):
     assert rel < 3e-5, f"rel {rel:.3e} max {mx:.3e}"
 
 
-@pytest.mark.parametrize("B,F,J,C,H", ATT_SHAPES[:4])
-def test_spatial_attention(cuda_device, B, F, J, C, H):
+@pytest.mark.parametrize("use_ref", [1, 0], ids=["simt_ref", "tcgen05"])
+@pytest.mark.parametrize("B,F,J,C,H", ATT_SHAPES)
+def test_spatial_attention(cuda_device, B, F, J, C, H, use_ref):
     g = torch.Generator().manual_seed(B * 77 + F)
     qkv = (torch.randn(B * F * J, 3 * C, generator=g) * 1.2).to(cuda_device)
-    y = G.test_attention(0, qkv, B, F, J, C, H, math=0, use_ref=0)
+    y = G.test_attention(0, qkv, B, F, J, C, H, math=0, use_ref=use_ref)
     exp = _attn_expected(qkv, B, F, J, C, H, False)
     assert torch.isfinite(y).all()
     rel, mx = _rel(y, exp)
-    assert rel < 2e-5, f"rel {rel:.3e} max {mx:.3e}"
+    assert rel < 3e-5, f"rel {rel:.3e} max {mx:.3e}"
 
 
 @pytest.mark.parametrize("B,F,J,C,H", [(2, 27, 17, 512, 8), (1, 243, 17, 256, 8)])
