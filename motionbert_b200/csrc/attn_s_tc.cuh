@@ -32,14 +32,18 @@ struct AttnSCfg {
     static constexpr int PLANES = (PASSES == 3) ? 2 : 1;
     static constexpr int PLANE = 128 * SWZ;
     static constexpr int TILE_BYTES = PLANES * PLANE;          // 32 KB (d=64, 3 passes)
-    static constexpr int OFF_K = 0;
-    static constexpr int OFF_V = TILE_BYTES;
-    static constexpr int OFF_Q = 2 * TILE_BYTES;               // two Q buffers
-    static constexpr int OFF_BAR = 4 * TILE_BYTES;
+    static constexpr int SET_BYTES = 3 * TILE_BYTES;           // Q | K | V of one problem
+    static constexpr int OFF_BAR = 2 * SET_BYTES;              // two problems in flight
     static constexpr int OFF_RED = OFF_BAR + 256;
-    static constexpr int SMEM_BYTES = OFF_RED + 128 * 4 + 1024;
+    static constexpr int SMEM_BYTES = OFF_RED + 3 * 128 * 4 + 1024;
+    static constexpr int TMEM_SET = 192;                       // S/P 128 columns + O 64 columns per problem
 };
 
+// Software-pipelined over problems i = 0, 1, ... of this CTA (two operand sets in smem, two S/P/O sets in TMEM):
+//   TMA      : loads set i+1 while set i is in use
+//   MMA      : S(i+1) = Q K^T is issued BEFORE waiting for the probabilities of problem i, so it runs under
+//              softmax(i); O(i) = P V runs under softmax(i+1)
+//   softmax  : softmax(i+1) precedes the output epilogue of problem i
 template <int HD, int PASSES>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF, plane), box (HD, 32, 4, PLANES)
@@ -48,80 +52,68 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-    uint64_t* k_full = bars + 0;
-    uint64_t* k_empty = bars + 1;
-    uint64_t* v_full = bars + 2;
-    uint64_t* v_empty = bars + 3;
-    uint64_t* q_full = bars + 4;    // [2]
-    uint64_t* q_empty = bars + 6;   // [2]
-    uint64_t* s_full = bars + 8;
-    uint64_t* p_full = bars + 9;
-    uint64_t* o_full = bars + 10;
-    uint64_t* o_empty = bars + 11;
+    uint64_t* in_full = bars + 0;    // [2] Q,K,V of a problem landed
+    uint64_t* in_empty = bars + 2;   // [2] P V of that problem retired
+    uint64_t* s_full = bars + 4;     // [2]
+    uint64_t* p_full = bars + 6;     // [2]
+    uint64_t* o_full = bars + 8;     // [2]
+    uint64_t* o_empty = bars + 10;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_groups = (p.BF + ATS_FRAMES - 1) / ATS_FRAMES;
     const int num_prob = num_groups * p.H;
+    const int n_mine = (num_prob > static_cast<int>(blockIdx.x))
+                           ? (num_prob - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
-        mbar_init(k_full, 1);  mbar_init(k_empty, 1);
-        mbar_init(v_full, 1);  mbar_init(v_empty, 1);
-        mbar_init(&q_full[0], 1);  mbar_init(&q_full[1], 1);
-        mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
-        mbar_init(s_full, 1);
-        mbar_init(p_full, ATT_SM_THREADS);
-        mbar_init(o_full, 1);
-        mbar_init(o_empty, ATT_SM_THREADS);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&in_full[i], 1);
+            mbar_init(&in_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], ATT_SM_THREADS);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_empty[i], ATT_SM_THREADS);
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;            // columns [0, 128): S, then P in place
-    const uint32_t tmem_O = tmem_base + 128;      // columns [128, 128 + HD)
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++it) {
+            for (int i = 0; i < n_mine; ++i) {
+                const int prob = blockIdx.x + i * gridDim.x;
                 const int h = prob % p.H, g = prob / p.H;
                 const int f0 = g * ATS_FRAMES;
-                const uint32_t ph = it & 1;
-                const int qs = it & 1;
-                const uint32_t q_ph = (it >> 1) & 1;
-                mbar_wait(k_empty, ph ^ 1);
-                mbar_arrive_expect_tx(k_full, Cfg::TILE_BYTES);
-                tma_load_4d(smem + Cfg::OFF_K, &tmQKV, k_full, p.C + h * HD, 0, f0, 0);
-                mbar_wait(&q_empty[qs], q_ph ^ 1);
-                mbar_arrive_expect_tx(&q_full[qs], Cfg::TILE_BYTES);
-                tma_load_4d(smem + Cfg::OFF_Q + qs * Cfg::TILE_BYTES, &tmQKV, &q_full[qs], h * HD, 0, f0, 0);
-                mbar_wait(v_empty, ph ^ 1);
-                mbar_arrive_expect_tx(v_full, Cfg::TILE_BYTES);
-                tma_load_4d(smem + Cfg::OFF_V, &tmQKV, v_full, 2 * p.C + h * HD, 0, f0, 0);
+                const int s = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                uint8_t* set = smem + s * Cfg::SET_BYTES;
+                mbar_wait(&in_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&in_full[s], Cfg::SET_BYTES);
+                tma_load_4d(set, &tmQKV, &in_full[s], h * HD, 0, f0, 0);                               // Q
+                tma_load_4d(set + Cfg::TILE_BYTES, &tmQKV, &in_full[s], p.C + h * HD, 0, f0, 0);       // K
+                tma_load_4d(set + 2 * Cfg::TILE_BYTES, &tmQKV, &in_full[s], 2 * p.C + h * HD, 0, f0, 0);   // V
             }
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
-        const uint32_t sK = smem_u32(smem + Cfg::OFF_K);
-        const uint32_t sV = smem_u32(smem + Cfg::OFF_V);
-        uint32_t it = 0;
-        for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++it) {
-            const uint32_t ph = it & 1;
-            const int qs = it & 1;
-            const uint32_t q_ph = (it >> 1) & 1;
-            mbar_wait(k_full, ph);
-            mbar_wait(&q_full[qs], q_ph);
+        auto issue_S = [&](int i) {
+            const int s = i & 1;
+            mbar_wait(&in_full[s], (i >> 1) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t sQ = smem_u32(smem + Cfg::OFF_Q + qs * Cfg::TILE_BYTES);
+                const uint32_t sQ = smem_u32(smem + s * Cfg::SET_BYTES);
+                const uint32_t sK = sQ + Cfg::TILE_BYTES;
+                const uint32_t tS = tmem_base + s * Cfg::TMEM_SET;
                 const uint64_t q_hi = umma_smem_desc(sQ, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                 const uint64_t q_lo = umma_smem_desc(sQ + Cfg::PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                 const uint64_t k_hi = umma_smem_desc(sK, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
@@ -130,40 +122,46 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
                 for (int ks = 0; ks < HD / 16; ++ks) {
                     const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
                     if (PASSES == 3) {
-                        umma_ss(tmem_S, q_lo + koff, k_hi + koff, idesc_s, ks != 0);
-                        umma_ss(tmem_S, q_hi + koff, k_lo + koff, idesc_s, 1);
-                        umma_ss(tmem_S, q_hi + koff, k_hi + koff, idesc_s, 1);
+                        umma_ss(tS, q_lo + koff, k_hi + koff, idesc_s, ks != 0);
+                        umma_ss(tS, q_hi + koff, k_lo + koff, idesc_s, 1);
+                        umma_ss(tS, q_hi + koff, k_hi + koff, idesc_s, 1);
                     } else {
-                        umma_ss(tmem_S, q_hi + koff, k_hi + koff, idesc_s, ks != 0);
+                        umma_ss(tS, q_hi + koff, k_hi + koff, idesc_s, ks != 0);
                     }
                 }
-                tc_commit(s_full);
-                tc_commit(&q_empty[qs]);
-                tc_commit(k_empty);
+                tc_commit(&s_full[s]);
             }
             __syncwarp();
-            mbar_wait(p_full, ph);
-            mbar_wait(v_full, ph);
-            mbar_wait(o_empty, ph ^ 1);
+        };
+        if (n_mine > 0) issue_S(0);
+        for (int i = 0; i < n_mine; ++i) {
+            if (i + 1 < n_mine) issue_S(i + 1);
+            const int s = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            mbar_wait(&p_full[s], ph);
+            mbar_wait(&o_empty[s], ph ^ 1);
             tc_fence_after();
             if (lane == 0) {
+                const uint32_t sV = smem_u32(smem + s * Cfg::SET_BYTES + 2 * Cfg::TILE_BYTES);
+                const uint32_t tS = tmem_base + s * Cfg::TMEM_SET;
+                const uint32_t tO = tS + 128;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {                 // 128 keys = 8 K-steps of 16
-                    const uint32_t a_hi = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);
+                    const uint32_t a_hi = tS + 32 * (ks >> 1) + 8 * (ks & 1);
                     const uint32_t a_lo = a_hi + 16;
                     const uint32_t voff = static_cast<uint32_t>(ks) * 16 * Cfg::SWZ;
                     const uint64_t v_hi = umma_smem_desc(sV + voff, 8 * Cfg::SWZ, 8 * Cfg::SWZ, Cfg::LAYOUT);
                     const uint64_t v_lo = umma_smem_desc(sV + Cfg::PLANE + voff, 8 * Cfg::SWZ, 8 * Cfg::SWZ, Cfg::LAYOUT);
                     if (PASSES == 3) {
-                        umma_ts(tmem_O, a_lo, v_hi, idesc_o, ks != 0);
-                        umma_ts(tmem_O, a_hi, v_lo, idesc_o, 1);
-                        umma_ts(tmem_O, a_hi, v_hi, idesc_o, 1);
+                        umma_ts(tO, a_lo, v_hi, idesc_o, ks != 0);
+                        umma_ts(tO, a_hi, v_lo, idesc_o, 1);
+                        umma_ts(tO, a_hi, v_hi, idesc_o, 1);
                     } else {
-                        umma_ts(tmem_O, a_hi, v_hi, idesc_o, ks != 0);
+                        umma_ts(tO, a_hi, v_hi, idesc_o, ks != 0);
                     }
                 }
-                tc_commit(o_full);
-                tc_commit(v_empty);
+                tc_commit(&o_full[s]);
+                tc_commit(&in_empty[s]);
             }
             __syncwarp();
         }
@@ -173,85 +171,94 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
         const int half = (warp - 2) >> 2;
         const int r_in_tile = quad * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        float* red_sum = reinterpret_cast<float*>(smem + Cfg::OFF_RED);   // [128]
+        float* red_sum = reinterpret_cast<float*>(smem + Cfg::OFF_RED);   // [3][128], slot = problem index % 3
         const float sl2 = p.scale_log2e;
-        uint32_t it = 0;
-        for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++it) {
-            const int h = prob % p.H, g = prob / p.H;
-            const uint32_t ph = it & 1;
-            mbar_wait(s_full, ph);
+
+        auto softmax = [&](int i) {
+            const int s = i & 1;
+            const uint32_t tS = tmem_base + s * Cfg::TMEM_SET;
+            mbar_wait(&s_full[s], (i >> 1) & 1);
             tc_fence_after();
             if (half == 0) {
                 // my frame's 32-column diagonal block: columns [32*quad, 32*quad + 32), first J valid
                 uint32_t r[32];
-                tmem_ld32(tmem_S + lane_off + quad * 32, r);
+                tmem_ld32(tS + lane_off + quad * 32, r);
                 tmem_ld_wait();
                 float mx = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (i < p.J) mx = fmaxf(mx, __uint_as_float(r[i]));
+                for (int k = 0; k < 32; ++k)
+                    if (k < p.J) mx = fmaxf(mx, __uint_as_float(r[k]));
                 const float mxs = mx * sl2;
                 float sum = 0.f;
                 uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = (2 * i < p.J) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mxs)) : 0.f;
-                    float p1 = (2 * i + 1 < p.J) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mxs)) : 0.f;
+                for (int k = 0; k < 16; ++k) {
+                    float p0 = (2 * k < p.J) ? ex2_approx(fmaf(__uint_as_float(r[2 * k]), sl2, -mxs)) : 0.f;
+                    float p1 = (2 * k + 1 < p.J) ? ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), sl2, -mxs)) : 0.f;
                     sum += p0 + p1;
-                    split2(p0, p1, hi[i], lo[i]);
+                    split2(p0, p1, hi[k], lo[k]);
                 }
-                tmem_st16(tmem_S + lane_off + quad * 32, hi);
-                if (PASSES == 3) tmem_st16(tmem_S + lane_off + quad * 32 + 16, lo);
-                red_sum[r_in_tile] = sum;
+                tmem_st16(tS + lane_off + quad * 32, hi);
+                if (PASSES == 3) tmem_st16(tS + lane_off + quad * 32 + 16, lo);
+                red_sum[(i % 3) * 128 + r_in_tile] = sum;
             } else {
                 // zero the three off-diagonal blocks of these rows so that frames do not mix in P V
                 uint32_t z[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) z[i] = 0u;
+                for (int k = 0; k < 16; ++k) z[k] = 0u;
 #pragma unroll
                 for (int blk = 0; blk < 4; ++blk) {
                     if (blk != quad) {
-                        tmem_st16(tmem_S + lane_off + blk * 32, z);
-                        if (PASSES == 3) tmem_st16(tmem_S + lane_off + blk * 32 + 16, z);
+                        tmem_st16(tS + lane_off + blk * 32, z);
+                        if (PASSES == 3) tmem_st16(tS + lane_off + blk * 32 + 16, z);
                     }
                 }
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(p_full);
-            named_bar_sync(1, ATT_SM_THREADS);          // red_sum visible to both halves
-            const float inv = 1.0f / red_sum[r_in_tile];
-
-            mbar_wait(o_full, ph);
+            mbar_arrive(&p_full[s]);
+        };
+        auto output = [&](int i) {
+            const int s = i & 1;
+            const int prob = blockIdx.x + i * gridDim.x;
+            const int h = prob % p.H, g = prob / p.H;
+            const uint32_t tO = tmem_base + s * Cfg::TMEM_SET + 128;
+            named_bar_sync(1, ATT_SM_THREADS);           // red_sum slot written by the half-0 warps is visible
+            const float inv = 1.0f / red_sum[(i % 3) * 128 + r_in_tile];
+            mbar_wait(&o_full[s], (i >> 1) & 1);
             tc_fence_after();
             const int frame = g * ATS_FRAMES + quad;
             const bool ok = (lane < p.J) && (frame < p.BF);
             if (HD == 64 || half == 0) {
                 const int c0 = (HD == 64) ? half * 32 : 0;
                 uint32_t r[32];
-                tmem_ld32(tmem_O + lane_off + c0, r);
+                tmem_ld32(tO + lane_off + c0, r);
                 tmem_ld_wait();
                 if (ok) {
                     const size_t ob = (static_cast<size_t>(frame) * p.J + lane) * p.C + h * HD + c0;
                     uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        split2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv, hi[i], lo[i]);
+                    for (int k = 0; k < 16; ++k)
+                        split2(__uint_as_float(r[2 * k]) * inv, __uint_as_float(r[2 * k + 1]) * inv, hi[k], lo[k]);
                     uint4* h4 = reinterpret_cast<uint4*>(p.out_hi + ob);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        h4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                    for (int k = 0; k < 4; ++k)
+                        h4[k] = make_uint4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
                     if (p.out_lo) {
                         uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + ob);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                        for (int k = 0; k < 4; ++k)
+                            l4[k] = make_uint4(lo[4 * k], lo[4 * k + 1], lo[4 * k + 2], lo[4 * k + 3]);
                     }
                 }
             }
             tc_fence_before();
-            mbar_arrive(o_empty);
-            named_bar_sync(1, ATT_SM_THREADS);          // red_sum reused by the next tile only after everyone read it
+            mbar_arrive(&o_empty[s]);
+        };
+        if (n_mine > 0) softmax(0);
+        for (int i = 0; i < n_mine; ++i) {
+            if (i + 1 < n_mine) softmax(i + 1);
+            output(i);
         }
     }
 
@@ -259,7 +266,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 

@@ -20,14 +20,16 @@
 
 namespace mb {
 
-constexpr int G2_STAGES = 4;
+constexpr int G2_STAGES_RESID = 4;   // residual epilogue needs 12 KB staging per warp
+constexpr int G2_STAGES_OTHER = 5;   // split-only / fp32-only epilogues need 8 KB -> one more operand stage
 constexpr int G2_THREADS = 320;
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_EPI_THREADS_PAIR = 2 * G2_EPI_WARPS * 32;   // arrivals on the leader's tmem-empty barrier
-constexpr int G2_STAGING_PER_WARP = 12288;                   // buf0 4 KB | buf1 4 KB | split 4 KB
 
-template <int PASSES>
+template <int PASSES, int EPI>
 struct Gemm2Cfg {
+    static constexpr int STAGES = (EPI == EPI_RESID) ? G2_STAGES_RESID : G2_STAGES_OTHER;
+    static constexpr int STAGING_PER_WARP = (EPI == EPI_RESID) ? 12288 : 8192;   // buf0 4 KB | buf1 4 KB | [split 4 KB]
     static constexpr int BK = (PASSES == 3) ? 32 : 64;
     static constexpr int SWZ = BK * 2;
     static constexpr uint32_t LAYOUT = (SWZ == 128) ? 2u : 4u;
@@ -37,8 +39,8 @@ struct Gemm2Cfg {
     static constexpr int A_BYTES = PLANES * A_PLANE;
     static constexpr int B_BYTES = PLANES * B_PLANE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB
-    static constexpr int OFF_STAGING = G2_STAGES * STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_STAGING + G2_EPI_WARPS * G2_STAGING_PER_WARP;
+    static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_STAGING + G2_EPI_WARPS * STAGING_PER_WARP;
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 };
 
@@ -50,7 +52,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
              const __grid_constant__ CUtensorMap tmX,   // fp32 2D (N, M) output,      box (32, 32)         [RESID/F32]
              const __grid_constant__ CUtensorMap tmS,   // bf16 3D (N, M, plane) out,  box (32, 32, PLANES) [RESID/SPLIT]
              const GemmParams p) {
-    using Cfg = Gemm2Cfg<PASSES>;
+    using Cfg = Gemm2Cfg<PASSES, EPI>;
+    constexpr int G2_STAGES = Cfg::STAGES;
     constexpr bool kResid = (EPI == EPI_RESID);
     constexpr bool kF32Out = (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32);
     constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT);
@@ -170,9 +173,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         const int quad = warp & 3;
         const int half = ew >> 2;
         constexpr int NCH = 4;
-        uint8_t* stg = smem + Cfg::OFF_STAGING + ew * G2_STAGING_PER_WARP;
+        uint8_t* stg = smem + Cfg::OFF_STAGING + ew * Cfg::STAGING_PER_WARP;
         uint8_t* buf[2] = {stg, stg + 4096};
-        uint8_t* bufS = stg + 8192;
+        uint8_t* bufS = stg + 8192;   // only exists (and is only used) for EPI_RESID
         uint64_t* my_rbar = rbar + 2 * ew;
         const int ngrp_out = p.N / STATS_GROUP;
         const uint32_t sw128 = static_cast<uint32_t>(lane & 7);          // SWIZZLE_128B: chunk16 ^= row % 8

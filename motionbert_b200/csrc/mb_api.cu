@@ -145,7 +145,7 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         SET_GEMM(1, EPI_LN_SPLIT); SET_GEMM(1, EPI_LN_GELU_SPLIT); SET_GEMM(1, EPI_RESID);
         SET_GEMM(1, EPI_LN_TANH_F32); SET_GEMM(1, EPI_BIAS_F32);
 #undef SET_GEMM
-#define SET_GEMM2(P, E) CUDA_TRY(set_smem(gemm2_kernel<P, E>, Gemm2Cfg<P>::SMEM_BYTES))
+#define SET_GEMM2(P, E) CUDA_TRY(set_smem(gemm2_kernel<P, E>, Gemm2Cfg<P, E>::SMEM_BYTES))
         SET_GEMM2(3, EPI_LN_SPLIT); SET_GEMM2(3, EPI_LN_GELU_SPLIT); SET_GEMM2(3, EPI_RESID);
         SET_GEMM2(3, EPI_LN_TANH_F32); SET_GEMM2(3, EPI_BIAS_F32);
         SET_GEMM2(1, EPI_LN_SPLIT); SET_GEMM2(1, EPI_LN_GELU_SPLIT); SET_GEMM2(1, EPI_RESID);
@@ -606,9 +606,9 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
         ((EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32) && !em.out_x))
         return fail(MB_ERR_INVALID, "internal: missing epilogue tensor map");
     if (passes == 3)
-        gemm2_kernel<3, EPI><<<grid, G2_THREADS, Gemm2Cfg<3>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
+        gemm2_kernel<3, EPI><<<grid, G2_THREADS, Gemm2Cfg<3, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else
-        gemm2_kernel<1, EPI><<<grid, G2_THREADS, Gemm2Cfg<1>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
+        gemm2_kernel<1, EPI><<<grid, G2_THREADS, Gemm2Cfg<1, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     LAUNCH_CHECK("gemm2_kernel");
     return MB_OK;
 }
@@ -1023,9 +1023,9 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
     do {                                                                                                             \
         if (use_ref == 0) {                                                                                          \
             if (passes == 3)                                                                                         \
-                gemm2_kernel<3, E><<<grid2, G2_THREADS, Gemm2Cfg<3>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
+                gemm2_kernel<3, E><<<grid2, G2_THREADS, Gemm2Cfg<3, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
             else                                                                                                     \
-                gemm2_kernel<1, E><<<grid2, G2_THREADS, Gemm2Cfg<1>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
+                gemm2_kernel<1, E><<<grid2, G2_THREADS, Gemm2Cfg<1, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
         } else if (use_ref == 1) {                                                                                   \
             const long warps = static_cast<long>(M) * (N / STATS_GROUP);                                             \
             gemm_ref_kernel<E><<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(a_hi, passes == 3 ? a_lo : nullptr, w_hi, \
