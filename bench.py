@@ -137,25 +137,36 @@ def synthetic_clips(B, T, seed):
 # ------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference_rate(model, T, budget_s=20.0, batch=2, max_iters=12):
     """The reference's own CPU forward, restated op-for-op with torch CPU ops (oracle/dstformer_torch_cpu.py; the
-    reference itself is PyTorch-only Python and cannot travel to the GPU box).  All host threads."""
+    reference itself is PyTorch-only Python and cannot travel to the GPU box).  Uses the host thread count that a
+    short calibration finds fastest (torch's default = all cores is pathological on 100+-thread hosts)."""
     from oracle import dstformer_oracle as O
     from oracle import dstformer_torch_cpu as OT
     cfg = O.BASE if model == "base" else O.LITE
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     P = {k: torch.from_numpy(v) for k, v in O.make_params(cfg, 0).items()}
+    xs = torch.from_numpy(O.make_input(1, min(T, 81), cfg.num_joints, 2))
+    best_t, best_n = None, cores
+    for n in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8)}, reverse=True):
+        torch.set_num_threads(n)
+        OT.forward(P, xs, cfg.depth, cfg.num_heads, cfg.eps)
+        t0 = time.perf_counter()
+        OT.forward(P, xs, cfg.depth, cfg.num_heads, cfg.eps)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_t, best_n = dt, n
+    torch.set_num_threads(best_n)
     x = torch.from_numpy(O.make_input(batch, T, cfg.num_joints, 1))
     OT.forward(P, x, cfg.depth, cfg.num_heads, cfg.eps)           # warm-up
     times = []
     t_start = time.perf_counter()
-    while len(times) < max_iters and (time.perf_counter() - t_start) < budget_s:
+    while len(times) < max_iters and (not times or (time.perf_counter() - t_start) < budget_s):
         t0 = time.perf_counter()
         OT.forward(P, x, cfg.depth, cfg.num_heads, cfg.eps)
         times.append(time.perf_counter() - t0)
     med = float(np.median(times))
-    return {"value": batch / med, "unit": "sequences/sec", "cores": cores, "kind": "port",
+    return {"value": batch / med, "unit": "sequences/sec", "cores": best_n, "kind": "port",
             "sample": f"{len(times)} forwards of B={batch} x T={T} x 17 ({model}), median {med * 1e3:.0f} ms, "
-                      f"torch {torch.__version__} CPU fp32, {cores} threads"}
+                      f"torch {torch.__version__} CPU fp32, {best_n} of {cores} host threads (fastest in calibration)"}
 
 
 def run_reference_arm(args):
@@ -201,14 +212,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from motionbert_b200 import dist as D
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    dist = D.init("nccl", device) if world > 1 else None
 
     from motionbert_b200 import _lib
     model = build_model(args.model, device, args.math)
@@ -226,11 +233,7 @@ def main():
         torch.cuda.synchronize(device)
 
     def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(v, device)
 
     # ---- warm-up (also builds the handle, packs weights, allocates the workspace)
     with torch.no_grad():

@@ -52,13 +52,15 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-    uint64_t* in_full = bars + 0;    // [2] Q,K,V of a problem landed
-    uint64_t* in_empty = bars + 2;   // [2] P V of that problem retired
-    uint64_t* s_full = bars + 4;     // [2]
-    uint64_t* p_full = bars + 6;     // [2]
-    uint64_t* o_full = bars + 8;     // [2]
-    uint64_t* o_empty = bars + 10;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* qk_full = bars + 0;    // [2] Q and K of a problem landed
+    uint64_t* qk_empty = bars + 2;   // [2] S = Q K^T of that problem retired (Q/K slots reusable early)
+    uint64_t* v_full = bars + 4;     // [2]
+    uint64_t* v_empty = bars + 6;    // [2] P V retired
+    uint64_t* s_full = bars + 8;     // [2]
+    uint64_t* p_full = bars + 10;    // [2]
+    uint64_t* o_full = bars + 12;    // [2]
+    uint64_t* o_empty = bars + 14;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -70,8 +72,10 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1);
-            mbar_init(&in_empty[i], 1);
+            mbar_init(&qk_full[i], 1);
+            mbar_init(&qk_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], ATT_SM_THREADS);
             mbar_init(&o_full[i], 1);
@@ -95,11 +99,13 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
                 const int s = i & 1;
                 const uint32_t ph = (i >> 1) & 1;
                 uint8_t* set = smem + s * Cfg::SET_BYTES;
-                mbar_wait(&in_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&in_full[s], Cfg::SET_BYTES);
-                tma_load_4d(set, &tmQKV, &in_full[s], h * HD, 0, f0, 0);                               // Q
-                tma_load_4d(set + Cfg::TILE_BYTES, &tmQKV, &in_full[s], p.C + h * HD, 0, f0, 0);       // K
-                tma_load_4d(set + 2 * Cfg::TILE_BYTES, &tmQKV, &in_full[s], 2 * p.C + h * HD, 0, f0, 0);   // V
+                mbar_wait(&qk_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&qk_full[s], 2 * Cfg::TILE_BYTES);
+                tma_load_4d(set, &tmQKV, &qk_full[s], h * HD, 0, f0, 0);                               // Q
+                tma_load_4d(set + Cfg::TILE_BYTES, &tmQKV, &qk_full[s], p.C + h * HD, 0, f0, 0);       // K
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[s], Cfg::TILE_BYTES);
+                tma_load_4d(set + 2 * Cfg::TILE_BYTES, &tmQKV, &v_full[s], 2 * p.C + h * HD, 0, f0, 0);   // V
             }
         }
     } else if (warp == 1) {
@@ -108,7 +114,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
         auto issue_S = [&](int i) {
             const int s = i & 1;
-            mbar_wait(&in_full[s], (i >> 1) & 1);
+            mbar_wait(&qk_full[s], (i >> 1) & 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t sQ = smem_u32(smem + s * Cfg::SET_BYTES);
@@ -130,6 +136,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
                     }
                 }
                 tc_commit(&s_full[s]);
+                tc_commit(&qk_empty[s]);
             }
             __syncwarp();
         };
@@ -139,6 +146,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
             const int s = i & 1;
             const uint32_t ph = (i >> 1) & 1;
             mbar_wait(&p_full[s], ph);
+            mbar_wait(&v_full[s], ph);
             mbar_wait(&o_empty[s], ph ^ 1);
             tc_fence_after();
             if (lane == 0) {
@@ -161,7 +169,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
                     }
                 }
                 tc_commit(&o_full[s]);
-                tc_commit(&in_empty[s]);
+                tc_commit(&v_empty[s]);
             }
             __syncwarp();
         }

@@ -308,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,   // 3D (K, M, plane), b
                         for (int i = 0; i < 8; ++i)
                             o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
-                    if (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) {
+                    if ((EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) && p.out_hi) {
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);

@@ -298,7 +298,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         *reinterpret_cast<float4*>(xs + lane * 128 + ((i ^ sw128) << 4)) =
                             make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
-                if (kSplitOut) {
+                const bool do_split = kSplitOut && (!kResid || p.out_hi != nullptr);   // block-final residuals feed
+                if (do_split) {                                                        // only the fp32 fusion kernel
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -315,7 +316,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 __syncwarp();
                 if (lane == 0) {
                     if (kF32Out) tma_store_2d(&tmX, xs, col0, rowb);
-                    if (kSplitOut) tma_store_3d(&tmS, ss, col0, rowb, 0);
+                    if (do_split) tma_store_3d(&tmS, ss, col0, rowb, 0);
                     tma_store_commit();
                 }
             }

@@ -770,7 +770,8 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         return launch_gemm<EPI_RESID>(enc, flags, P.tm_ao, P.ao, P.ao + ao_plane_el, L[temporal ? L_PROJ_T : L_PROJ_S], pk, q, em2, st);
     };
     // one residual MLP sublayer: dst = src + fc2(gelu(fc1(LN(src))))             (DSTformer.py:242,244,247,249)
-    auto mlp_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst) -> int {
+    auto mlp_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst,
+                            bool block_final) -> int {
         GemmParams p = base;
         p.stats_in = src.stats;
         p.out_hi = P.hid;
@@ -783,9 +784,10 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         q.resid = src.x;
         q.row_scale = dp(sub++);
         q.out_f32 = dst.x;
-        q.out_hi = dst.hi;
-        q.out_lo = dst.lo;
-        q.stats_out = dst.stats;
+        // the last sublayer of a Block only feeds the fp32 S/T fusion: no bf16 planes, no LN statistics
+        q.out_hi = block_final ? nullptr : dst.hi;
+        q.out_lo = block_final ? nullptr : dst.lo;
+        q.stats_out = block_final ? nullptr : dst.stats;
         EpiMaps em2;
         em2.resid = &src.tm_x;
         em2.out_x = &dst.tm_x;
@@ -803,14 +805,14 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         sub = i * 8;
         // blocks_st[i] : 'stage_st'  S-attn, S-mlp, T-attn, T-mlp   (DSTformer.py:240-244)  X0 -> S1 -> S2 -> S1 -> S2
         if ((rc = attn_sublayer(Lst, false, X0, S1))) return rc;
-        if ((rc = mlp_sublayer(Lst, false, S1, S2))) return rc;
+        if ((rc = mlp_sublayer(Lst, false, S1, S2, false))) return rc;
         if ((rc = attn_sublayer(Lst, true, S2, S1))) return rc;
-        if ((rc = mlp_sublayer(Lst, true, S1, S2))) return rc;
+        if ((rc = mlp_sublayer(Lst, true, S1, S2, true))) return rc;
         // blocks_ts[i] : 'stage_ts'  T-attn, T-mlp, S-attn, S-mlp   (DSTformer.py:245-249)  X0 -> T1 -> S1 -> T1 -> S1
         if ((rc = attn_sublayer(Lts, true, X0, T1))) return rc;
-        if ((rc = mlp_sublayer(Lts, true, T1, S1))) return rc;
+        if ((rc = mlp_sublayer(Lts, true, T1, S1, false))) return rc;
         if ((rc = attn_sublayer(Lts, false, S1, T1))) return rc;
-        if ((rc = mlp_sublayer(Lts, false, T1, S1))) return rc;
+        if ((rc = mlp_sublayer(Lts, false, T1, S1, true))) return rc;
         // fusion (DSTformer.py:343-349): (x_st = S2, x_ts = S1) -> X0
         prof_mark(enc, st, PC_FUSE);
         ROWK(fuse_kernel,

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256) gemm_ref_kernel(const __nv_bfloat16* __re
         vals[i] = v;
         const size_t o = static_cast<size_t>(row) * p.N + n;
         if (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32) p.out_f32[o] = v;
-        if (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) {
+        if ((EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) && p.out_hi) {
             __nv_bfloat16 h, l;
             split_bf16(v, h, l);
             p.out_hi[o] = h;
