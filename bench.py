@@ -301,10 +301,24 @@ def main():
     achieved_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     total_flop = flops_per_sequence(cfg["dim_feat"], hidden, T) * B
     passes = 3 if args.math == "bf16x3" else 1
+    # DRAM traffic of the GEMM class from the committed ncu --set full capture of this same configuration
+    traffic, traffic_src = None, None
+    if args.model == "base" and B == 256 and T == 243 and passes == 3:
+        import glob
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+            try:
+                with open(f) as fh:
+                    js = json.load(fh)
+                if "gemm_avg_dram_bytes_per_launch" in js:
+                    traffic, traffic_src = js["gemm_avg_dram_bytes_per_launch"], os.path.basename(f)
+                    break
+            except Exception:
+                pass
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all 4 epilogue variants)",
+        "bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05, all 4 epilogue variants)",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_dram_bytes_per_launch": (8.66e9 + 8.66e9 + 6.50e9 + 10.83e9) / 4 * (B / 256.0) if args.model == "base" and T == 243 else None,
         "peak_source": peaks["_source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "mma_passes": passes,
         "note": f"achieved = algorithmic GEMM FLOPs per launch ({gemm_flop / max(gemm_launches, 1) / 1e9:.1f} GFLOP avg over "

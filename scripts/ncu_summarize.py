@@ -1,0 +1,73 @@
+"""Summarise ncu artefacts into small committed text/JSON files under profiles/.
+   ncu_summarize.py <tag>   (reads gpurun_out/<tag>_launches.csv, <tag>_gemm.ncu-rep, <tag>_attn.ncu-rep, <tag>_fuse.ncu-rep)"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+tag = sys.argv[1]
+G = "gpurun_out"
+out = {"tag": tag, "launch_list": [], "kernels": []}
+
+rows = list(csv.reader(open(f"{G}/{tag}_launches.csv")))
+hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+hdr = rows[hi]
+kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+agg = collections.OrderedDict()
+for r in rows[hi + 1:]:
+    if len(r) <= mv:
+        continue
+    name = r[kn].split("(")[0]
+    a = agg.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += float(r[mv].replace(",", ""))
+tot = sum(a[1] for a in agg.values())
+for k, (n, t) in agg.items():
+    out["launch_list"].append({"kernel": k, "launches": n, "total_ms": t / 1e6, "avg_us": t / n / 1e3, "share": t / tot})
+out["launch_list_total_ms"] = tot / 1e6
+
+WANT = {"gpu__time_duration.sum": "time_us", "sm__cycles_elapsed.avg.per_second": "sm_ghz",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_active_pct",
+        "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed": "l1tex_throughput_pct",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+        "launch__registers_per_thread": "regs", "launch__grid_size": "grid", "launch__block_size": "block",
+        "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct"}
+UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+for part in ("gemm", "attn", "fuse"):
+    rep = f"{G}/{tag}_{part}.ncu-rep"
+    if not os.path.exists(rep):
+        continue
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(txt.splitlines()))
+    h, units = rr[0], rr[1]
+    for r in rr[2:]:
+        k = {"kernel": r[h.index("Kernel Name")].split("(CUtensorMap")[0].split("(const")[0]}
+        for i, name in enumerate(h):
+            if name in WANT:
+                v = float(r[i].replace(",", ""))
+                if WANT[name] in ("dram_read", "dram_write"):
+                    v *= UNIT.get(units[i], 1.0)
+                if WANT[name] == "time_us":
+                    v *= {"us": 1.0, "ms": 1e3, "s": 1e6, "ns": 1e-3}.get(units[i], 1.0)
+                k[WANT[name]] = v
+        k["dram_bytes"] = k.get("dram_read", 0) + k.get("dram_write", 0)
+        if k.get("time_us"):
+            k["dram_GBps"] = k["dram_bytes"] / k["time_us"] / 1e3
+        out["kernels"].append(k)
+gem = [k for k in out["kernels"] if "gemm2_kernel<3, " in k["kernel"] or "gemm2_kernel<1, " in k["kernel"]]
+if gem:
+    out["gemm_avg_dram_bytes_per_launch"] = sum(k["dram_bytes"] for k in gem) / len(gem)
+    out["gemm_traffic_note"] = ("mean of dram__bytes_read.sum + dram__bytes_write.sum over one captured launch of each "
+                                "GEMM flavour (qkv, proj, fc1, fc2: 20 launches each per forward), ncu --set full")
+json.dump(out, open(f"profiles/{tag}_ncu_summary.json", "w"), indent=1)
+print(f"launch list ({out['launch_list_total_ms']:.2f} ms under ncu, serialised):")
+for e in out["launch_list"]:
+    print(f"  {e['kernel'][:46]:46s} n={e['launches']:3d} avg {e['avg_us']:9.1f} us  share {e['share']:.3f}")
+for k in out["kernels"]:
+    print(f"  {k['kernel'][:40]:40s} {k.get('time_us',0):9.1f} us  tensor {k.get('tensor_pipe_active_pct',0):5.1f}%  dram {k.get('dram_bytes',0)/1e9:6.2f} GB "
+          f"({k.get('dram_GBps',0):6.0f} GB/s, {k.get('dram_throughput_pct',0):4.1f}%)  L2 {k.get('l2_throughput_pct',0):4.1f}%  L1TEX {k.get('l1tex_throughput_pct',0):4.1f}%  issue {k.get('issue_active_pct',0):4.1f}%  regs {k.get('regs',0):.0f}")
