@@ -295,6 +295,29 @@ class DSTformer(nn.Module):
                 self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr), "mb_forward")
         return out, rep
 
+    def make_graphed(self, B: int, F: int, return_rep: bool = False):
+        """CUDA-graph the inference forward for a fixed (B, F): returns `run(x) -> out` that copies x into a static
+        device buffer, replays the captured 108-launch forward and returns the static output tensor (valid until the
+        next call).  For latency-bound shapes (infer_wild: B=1 clips); weights must not change between calls."""
+        dev = next(self.parameters()).device
+        static_x = torch.zeros(B, F, self.num_joints, self.dim_in, dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(2):                      # warm-up: handle, packed weights, workspace, tensor maps
+                self.forward(static_x, return_rep)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            static_out = self.forward(static_x, return_rep)
+
+        def run(x):
+            static_x.copy_(x, non_blocking=True)
+            graph.replay()
+            return static_out
+        run.graph = graph
+        return run
+
     # ------------------------------------------------------------------ forward (DSTformer.py:329-358)
     def forward(self, x, return_rep=False):
         if x.dim() != 4:

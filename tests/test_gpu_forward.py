@@ -200,3 +200,35 @@ def test_error_paths(cuda_device):
     rc = lib.mb_forward(st.handle, m._aligned_ptr(st.packed), None, out.data_ptr(), None, None,
                         m._aligned_ptr(ws), 1024, 2, 27, 0, None)
     assert rc == -2
+
+
+def test_cuda_graph_capture_and_replay(cuda_device):
+    """The whole forward is capturable (no allocation / sync inside the library) and replays bit-identically."""
+    cfg, P, x, g = load_case("lite_b2_f27")
+    m = build_module(cfg, P, cuda_device)
+    ref_out, _ = _run(m, x, cuda_device)
+    run = m.make_graphed(2, 27)
+    xt = torch.from_numpy(x).to(cuda_device)
+    o1 = run(xt).clone()
+    o2 = run(xt * 0.5).clone()
+    o3 = run(xt).clone()
+    torch.cuda.synchronize()
+    assert np.array_equal(o1.cpu().numpy(), ref_out) and torch.equal(o1, o3) and not torch.equal(o1, o2)
+
+
+def test_data_parallel_wrapper_two_gpus():
+    """The reference wraps the backbone in nn.DataParallel (train.py:256-258): replicas on 2 devices, one Python
+    thread each, must reproduce the single-device result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg, P, x, g = load_case("lite_b5_f30")
+    dev0 = torch.device("cuda:0")
+    m = build_module(cfg, P, dev0)
+    single, _ = _run(m, x, dev0)
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    with torch.no_grad():
+        out = dp(torch.from_numpy(x).to(dev0)).cpu().numpy()
+        out2 = dp(torch.from_numpy(x).to(dev0)).cpu().numpy()
+    assert out.shape == single.shape
+    assert rel_token_err(out, single)[1] < 2e-5 and np.array_equal(out, out2)
+    assert O.mpjpe(out.astype(np.float64), g["out64"]) < MPJPE_UNITS
