@@ -48,7 +48,7 @@ struct AttnCfg {
 };
 
 template <int HD, int PASSES>
-__global__ void __maxnreg__(184)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128, 1, PLANES)
                  const __grid_constant__ CUtensorMap tmKV,   // box (HD, 1, NK , 1, PLANES)
                  const AttnTParams p) {
