@@ -209,26 +209,19 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                 const uint32_t t_ph = t_it & 1;
                 mbar_wait(s_full, t_ph);
                 tc_fence_after();
-                // my (up to) 4 key chunks of this row are read from TMEM ONCE and stay in registers for both passes
-                uint32_t sv[4][32];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (ch_lo + k < ch_hi) tmem_ld32(tmem_S + lane_off + (ch_lo + k) * 32, sv[k]);
-                tmem_ld_wait();
-                // pass 1: row max of the raw scores (scale > 0 commutes with max)
+                // pass 1: row max of the raw scores over my key chunks (scale > 0 commutes with max)
                 float mx = -INFINITY;
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
+                    tmem_ld_wait();
+                    if (ch * 32 + 32 <= p.F) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ch = ch_lo + k;
-                    if (ch < ch_hi) {
-                        if (ch * 32 + 32 <= p.F) {
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[k][i]));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(sv[k][i]));
-                        }
+                        for (int i = 0; i < 32; ++i)
+                            if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
                     }
                 }
                 red_max[half * 128 + r_in_tile] = mx;
@@ -237,26 +230,25 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                 const float mxs = mx * sl2;
                 // pass 2: p = 2^(s*c - max*c), partial row sum, bf16 hi/lo split written back over S
                 float sum = 0.f;
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
+                    tmem_ld_wait();
+                    uint32_t hi[16], lo[16];
+                    const bool full = ch * 32 + 32 <= p.F;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ch = ch_lo + k;
-                    if (ch < ch_hi) {
-                        uint32_t hi[16], lo[16];
-                        const bool full = ch * 32 + 32 <= p.F;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float p0 = ex2_approx(fmaf(__uint_as_float(sv[k][2 * i]), sl2, -mxs));
-                            float p1 = ex2_approx(fmaf(__uint_as_float(sv[k][2 * i + 1]), sl2, -mxs));
-                            if (!full) {
-                                if (ch * 32 + 2 * i >= p.F) p0 = 0.f;
-                                if (ch * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
-                            }
-                            sum += p0 + p1;
-                            split2(p0, p1, hi[i], lo[i]);
+                    for (int i = 0; i < 16; ++i) {
+                        float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mxs));
+                        float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mxs));
+                        if (!full) {
+                            if (ch * 32 + 2 * i >= p.F) p0 = 0.f;
+                            if (ch * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
                         }
-                        tmem_st16(tmem_S + lane_off + ch * 32, hi);
-                        if (PASSES == 3) tmem_st16(tmem_S + lane_off + ch * 32 + 16, lo);
+                        sum += p0 + p1;
+                        split2(p0, p1, hi[i], lo[i]);
                     }
+                    tmem_st16(tmem_S + lane_off + ch * 32, hi);
+                    if (PASSES == 3) tmem_st16(tmem_S + lane_off + ch * 32 + 16, lo);
                 }
                 red_sum[half * 128 + r_in_tile] = sum;
                 tmem_st_wait();
