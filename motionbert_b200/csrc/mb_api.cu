@@ -16,6 +16,7 @@
 #include "../../include/motionbert_b200.h"
 #include "attn_s_tc.cuh"
 #include "attn_t_tc.cuh"
+#include "attn_t_tc2.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "simt_kernels.cuh"
@@ -151,6 +152,10 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         SET_GEMM2(1, EPI_LN_SPLIT); SET_GEMM2(1, EPI_LN_GELU_SPLIT); SET_GEMM2(1, EPI_RESID);
         SET_GEMM2(1, EPI_LN_TANH_F32); SET_GEMM2(1, EPI_BIAS_F32);
 #undef SET_GEMM2
+        CUDA_TRY(set_smem(attn_t2_kernel<64, 3>, Attn2Cfg<64, 3>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_t2_kernel<32, 3>, Attn2Cfg<32, 3>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_t2_kernel<64, 1>, Attn2Cfg<64, 1>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_t2_kernel<32, 1>, Attn2Cfg<32, 1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 3>, AttnCfg<64, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<32, 3>, AttnCfg<32, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 1>, AttnCfg<64, 1>::SMEM_BYTES));
@@ -661,6 +666,14 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     ap.out_lo = o_lo;
     const int prob = B * J * H;
     const int grid = prob < e->dev.sms ? prob : e->dev.sms;
+    if (!(flags & MB_FLAG_ATTN_T_V1)) {
+        if (hd == 64 && passes == 3) attn_t2_kernel<64, 3><<<grid, ATT_THREADS, Attn2Cfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+        else if (hd == 32 && passes == 3) attn_t2_kernel<32, 3><<<grid, ATT_THREADS, Attn2Cfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+        else if (hd == 64) attn_t2_kernel<64, 1><<<grid, ATT_THREADS, Attn2Cfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+        else attn_t2_kernel<32, 1><<<grid, ATT_THREADS, Attn2Cfg<32, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+        LAUNCH_CHECK("attn_t2_kernel");
+        return MB_OK;
+    }
     if (hd == 64 && passes == 3) attn_t_tc_kernel<64, 3><<<grid, ATT_THREADS, AttnCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
     else if (hd == 32 && passes == 3) attn_t_tc_kernel<32, 3><<<grid, ATT_THREADS, AttnCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
     else if (hd == 64) attn_t_tc_kernel<64, 1><<<grid, ATT_THREADS, AttnCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
@@ -1092,7 +1105,7 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(qkv, P.qkv, P.qkv + qkv_plane / 2, n);
         LAUNCH_CHECK("split_flat_kernel");
     }
-    if (!temporal && !use_ref) {
+    if (!temporal && use_ref != 1) {
         const int hd = C / H;
         const uint64_t C3 = 3ull * C;
         const uint64_t dims4[4] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(B) * F, 2};
@@ -1100,7 +1113,7 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         const uint32_t box4[4] = {static_cast<uint32_t>(hd), ATS_SLAB, ATS_FRAMES, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
         if ((rc = make_tmap(&P.tm_qkv_sp, P.qkv, 4, dims4, str4, box4, hd * 2))) return rc;
     }
-    if (temporal && !use_ref) {
+    if (temporal && use_ref != 1) {
         const int hd = C / H;
         const uint64_t C3 = 3ull * C;
         const uint64_t dims[5] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 2};
@@ -1112,8 +1125,8 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         if ((rc = make_tmap(&P.tm_q, P.qkv, 5, dims, str, box_q, hd * 2))) return rc;
         if ((rc = make_tmap(&P.tm_kv, P.qkv, 5, dims, str, box_kv, hd * 2))) return rc;
     }
-    rc = launch_attn(&e, use_ref ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : 0u, temporal != 0, P, B, F, qkv_plane / 2,
-                     ao_plane / 2, st);
+    rc = launch_attn(&e, use_ref == 1 ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : use_ref == 2 ? MB_FLAG_ATTN_T_V1 : 0u,
+                     temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st);
     if (rc) return rc;
     const size_t n = M * C;
     merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(P.ao, passes == 3 ? P.ao + ao_plane / 2 : nullptr, y, n);
