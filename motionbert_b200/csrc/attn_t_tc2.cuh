@@ -176,7 +176,9 @@ attn_t2_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128, 1
                 const int c = from1 ? 4 + k1 : k0;
                 const int slot = from1 ? 2 + (k1 & 1) : (k0 & 1);
                 if (from1) ++k1; else ++k0;
-                if (i == nch - 1 && t + 1 < n_tiles) issue_S(t + 1);     // S(t+1) slips in before the last P V chunk
+                // S(t+1) is issued as soon as every softmax thread has STARTED its last chunk (s_free), i.e. before the
+                // MMA waits for the last chunk of either key half, so it executes under the tail of softmax(t)
+                if (i == (nch >= 2 ? nch - 2 : 0) && t + 1 < n_tiles) issue_S(t + 1);
                 mbar_wait(&p_full[slot], slot_use[slot] & 1);
                 if (i == 0) {
                     if (qt == 0) mbar_wait(v_full, ip & 1);
@@ -271,20 +273,25 @@ attn_t2_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128, 1
             const int par = t & 1;
             mbar_wait(s_full, t & 1);
             tc_fence_after();
-            // pass 1: row max over my key chunks (raw scores; scale > 0 commutes with max)
+            // pass 1: row max over my key chunks (raw scores; scale > 0 commutes with max); the tcgen05.ld of chunk
+            // k+1 is in flight while chunk k is reduced (two register buffers, statically indexed)
             float mx = -INFINITY;
-            for (int k = 0; k < my_nch; ++k) {
-                const int c = my_c0 + k;
-                uint32_t r[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, r);
-                tmem_ld_wait();
-                if (c * 32 + 32 <= p.F) {
+            uint32_t rr[2][32];
+            if (my_nch > 0) tmem_ld32(tmem_S + lane_off + my_c0 * 32, rr[0]);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                } else {
+            for (int k = 0; k < 4; ++k) {
+                if (k < my_nch) {
+                    const int c = my_c0 + k;
+                    tmem_ld_wait();
+                    if (k + 1 < my_nch) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, rr[(k + 1) & 1]);
+                    if (c * 32 + 32 <= p.F) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[k & 1][i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(rr[k & 1][i]));
+                    }
                 }
             }
             red[(par * 2 + half) * 128 + r_in_tile] = mx;
@@ -301,43 +308,47 @@ attn_t2_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128, 1
                 tc_fence_before();
                 mbar_arrive(s_free);
             }
-            for (int k = 0; k < my_nch; ++k) {
-                const int c = my_c0 + k;
-                const int ls = k & 1;
-                const int slot = half * 2 + ls;
-                uint32_t r[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, r);
-                tmem_ld_wait();
-                if (k == my_nch - 1) {                      // that was my last read of S(t)
-                    tc_fence_before();
-                    mbar_arrive(s_free);
-                }
-                uint32_t hi[16], lo[16];
-                const bool full = c * 32 + 32 <= p.F;
+            if (my_nch > 0) tmem_ld32(tmem_S + lane_off + my_c0 * 32, rr[0]);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mxs));
-                    float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mxs));
-                    if (!full) {
-                        if (c * 32 + 2 * i >= p.F) p0 = 0.f;
-                        if (c * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
+            for (int k = 0; k < 4; ++k) {
+                if (k < my_nch) {
+                    const int c = my_c0 + k;
+                    const int ls = k & 1;
+                    const int slot = half * 2 + ls;
+                    tmem_ld_wait();
+                    if (k + 1 < my_nch) {
+                        tmem_ld32(tmem_S + lane_off + (c + 1) * 32, rr[(k + 1) & 1]);
+                    } else {                                    // that was my last read of S(t)
+                        tc_fence_before();
+                        mbar_arrive(s_free);
                     }
-                    sum += p0 + p1;
-                    split2(p0, p1, hi[i], lo[i]);
-                }
-                mbar_wait(&p_empty[slot], (slot_use[ls] & 1) ^ 1);     // P V of the previous user of this slot retired
-                uint8_t* dst = sP + slot * Cfg::P_SLOT + r_in_tile * 64;
+                    uint32_t hi[16], lo[16];
+                    const bool full = c * 32 + 32 <= p.F;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    *reinterpret_cast<uint4*>(dst + ((i ^ sw64) << 4)) =
-                        make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                    if (PASSES == 3)
-                        *reinterpret_cast<uint4*>(dst + Cfg::P_PLANE + ((i ^ sw64) << 4)) =
-                            make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    for (int i = 0; i < 16; ++i) {
+                        float p0 = ex2_approx(fmaf(__uint_as_float(rr[k & 1][2 * i]), sl2, -mxs));
+                        float p1 = ex2_approx(fmaf(__uint_as_float(rr[k & 1][2 * i + 1]), sl2, -mxs));
+                        if (!full) {
+                            if (c * 32 + 2 * i >= p.F) p0 = 0.f;
+                            if (c * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
+                        }
+                        sum += p0 + p1;
+                        split2(p0, p1, hi[i], lo[i]);
+                    }
+                    mbar_wait(&p_empty[slot], (slot_use[ls] & 1) ^ 1);     // P V of the previous user of this slot retired
+                    uint8_t* dst = sP + slot * Cfg::P_SLOT + r_in_tile * 64;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        *reinterpret_cast<uint4*>(dst + ((i ^ sw64) << 4)) =
+                            make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                        if (PASSES == 3)
+                            *reinterpret_cast<uint4*>(dst + Cfg::P_PLANE + ((i ^ sw64) << 4)) =
+                                make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&p_full[slot]);
+                    ++slot_use[ls];
                 }
-                fence_proxy_async_smem();
-                mbar_arrive(&p_full[slot]);
-                ++slot_use[ls];
             }
             named_bar_sync(2, ATT_SM_THREADS);          // both halves have read max(t) before the slot takes sum(t)
             red[(par * 2 + half) * 128 + r_in_tile] = sum;
