@@ -72,7 +72,7 @@ typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 #define MB_FLAG_REF_GEMM   0x1u   /* TEST ONLY: CUDA-core reference GEMM instead of tcgen05           */
 #define MB_FLAG_REF_ATTN_T 0x2u   /* TEST ONLY: CUDA-core reference temporal attention                */
 #define MB_FLAG_REF_ATTN_S 0x8u   /* TEST ONLY: CUDA-core reference spatial attention                 */
-#define MB_FLAG_ATTN_T_V1  0x10u  /* TEST ONLY: first-generation temporal attention (P kept in TMEM)  */
+#define MB_FLAG_ATTN_T_V2  0x10u  /* TEST ONLY: experimental temporal attention with P in a smem ring   */
 #define MB_FLAG_GEMM_1CTA  0x4u   /* TEST ONLY: first-generation 1-CTA tcgen05 GEMM (LSU epilogue)    */
 
 int mb_version(void);

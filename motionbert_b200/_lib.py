@@ -17,7 +17,7 @@ MB_FLAG_REF_GEMM = 0x1
 MB_FLAG_REF_ATTN_T = 0x2
 MB_FLAG_GEMM_1CTA = 0x4
 MB_FLAG_REF_ATTN_S = 0x8
-MB_FLAG_ATTN_T_V1 = 0x10
+MB_FLAG_ATTN_T_V2 = 0x10
 
 # every symbol include/motionbert_b200.h declares
 EXPORTS = [

@@ -209,19 +209,26 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                 const uint32_t t_ph = t_it & 1;
                 mbar_wait(s_full, t_ph);
                 tc_fence_after();
-                // pass 1: row max of the raw scores over my key chunks (scale > 0 commutes with max)
+                // pass 1: row max of the raw scores over my key chunks (scale > 0 commutes with max).  tcgen05.ld of
+                // chunk k+1 is in flight while chunk k is reduced (two statically indexed register buffers).
                 float mx = -INFINITY;
-                for (int ch = ch_lo; ch < ch_hi; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
-                    tmem_ld_wait();
-                    if (ch * 32 + 32 <= p.F) {
+                uint32_t rr[2][32];
+                const int my_n = ch_hi - ch_lo;
+                if (my_n > 0) tmem_ld32(tmem_S + lane_off + ch_lo * 32, rr[0]);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    } else {
+                for (int k = 0; k < 4; ++k) {
+                    if (k < my_n) {
+                        const int ch = ch_lo + k;
+                        tmem_ld_wait();
+                        if (k + 1 < my_n) tmem_ld32(tmem_S + lane_off + (ch + 1) * 32, rr[(k + 1) & 1]);
+                        if (ch * 32 + 32 <= p.F) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
+                            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[k & 1][i]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(rr[k & 1][i]));
+                        }
                     }
                 }
                 red_max[half * 128 + r_in_tile] = mx;
@@ -230,25 +237,31 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                 const float mxs = mx * sl2;
                 // pass 2: p = 2^(s*c - max*c), partial row sum, bf16 hi/lo split written back over S
                 float sum = 0.f;
-                for (int ch = ch_lo; ch < ch_hi; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
-                    tmem_ld_wait();
-                    uint32_t hi[16], lo[16];
-                    const bool full = ch * 32 + 32 <= p.F;
+                if (my_n > 0) tmem_ld32(tmem_S + lane_off + ch_lo * 32, rr[0]);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mxs));
-                        float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mxs));
-                        if (!full) {
-                            if (ch * 32 + 2 * i >= p.F) p0 = 0.f;
-                            if (ch * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
+                for (int k = 0; k < 4; ++k) {
+                    if (k < my_n) {
+                        const int ch = ch_lo + k;
+                        tmem_ld_wait();
+                        if (k + 1 < my_n) tmem_ld32(tmem_S + lane_off + (ch + 1) * 32, rr[(k + 1) & 1]);
+                        uint32_t hi[16], lo[16];
+                        const bool full = ch * 32 + 32 <= p.F;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float p0 = ex2_approx(fmaf(__uint_as_float(rr[k & 1][2 * i]), sl2, -mxs));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(rr[k & 1][2 * i + 1]), sl2, -mxs));
+                            if (!full) {
+                                if (ch * 32 + 2 * i >= p.F) p0 = 0.f;
+                                if (ch * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
+                            }
+                            sum += p0 + p1;
+                            split2(p0, p1, hi[i], lo[i]);
                         }
-                        sum += p0 + p1;
-                        split2(p0, p1, hi[i], lo[i]);
+                        // the next chunk's scores are already on their way to registers: overwriting THIS chunk's
+                        // columns with P cannot race with it (different columns)
+                        tmem_st16(tmem_S + lane_off + ch * 32, hi);
+                        if (PASSES == 3) tmem_st16(tmem_S + lane_off + ch * 32 + 16, lo);
                     }
-                    tmem_st16(tmem_S + lane_off + ch * 32, hi);
-                    if (PASSES == 3) tmem_st16(tmem_S + lane_off + ch * 32 + 16, lo);
                 }
                 red_sum[half * 128 + r_in_tile] = sum;
                 tmem_st_wait();

@@ -1,3 +1,8 @@
+// EXPERIMENTAL (test flag MB_FLAG_ATTN_T_V2, not the product path): measured SLOWER than attn_t_tc.cuh on B200
+// (60.5 ms vs 44 ms per forward at config 2, profiles/README.md) -- the 256 softmax threads, not the tensor pipe,
+// bound this kernel (MUFU.EX2 + two F2FP per score pair), and the smem ring adds STS + proxy fences to exactly them.
+// Kept as the documented negative result of round 1.
+//
 // Temporal attention, second generation: probabilities go to the tensor core through SHARED memory
 // (DSTformer.py:188-200, `Attention.forward_temporal`).
 //

@@ -666,7 +666,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     ap.out_lo = o_lo;
     const int prob = B * J * H;
     const int grid = prob < e->dev.sms ? prob : e->dev.sms;
-    if (!(flags & MB_FLAG_ATTN_T_V1)) {
+    if (flags & MB_FLAG_ATTN_T_V2) {
         if (hd == 64 && passes == 3) attn_t2_kernel<64, 3><<<grid, ATT_THREADS, Attn2Cfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
         else if (hd == 32 && passes == 3) attn_t2_kernel<32, 3><<<grid, ATT_THREADS, Attn2Cfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
         else if (hd == 64) attn_t2_kernel<64, 1><<<grid, ATT_THREADS, Attn2Cfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
@@ -1125,7 +1125,7 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         if ((rc = make_tmap(&P.tm_q, P.qkv, 5, dims, str, box_q, hd * 2))) return rc;
         if ((rc = make_tmap(&P.tm_kv, P.qkv, 5, dims, str, box_kv, hd * 2))) return rc;
     }
-    rc = launch_attn(&e, use_ref == 1 ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : use_ref == 2 ? MB_FLAG_ATTN_T_V1 : 0u,
+    rc = launch_attn(&e, use_ref == 1 ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : use_ref == 2 ? MB_FLAG_ATTN_T_V2 : 0u,
                      temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st);
     if (rc) return rc;
     const size_t n = M * C;

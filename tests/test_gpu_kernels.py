@@ -92,7 +92,7 @@ ATT_SHAPES = [(2, 27, 17, 512, 8), (1, 243, 17, 512, 8), (3, 16, 17, 256, 8), (2
               (2, 243, 17, 256, 8), (5, 30, 17, 512, 8), (9, 200, 17, 512, 8), (3, 81, 17, 256, 8)]
 
 
-@pytest.mark.parametrize("use_ref", [1, 2, 0], ids=["simt_ref", "tcgen05v1", "tcgen05"])
+@pytest.mark.parametrize("use_ref", [1, 2, 0], ids=["simt_ref", "tcgen05v2x", "tcgen05"])
 @pytest.mark.parametrize("B,F,J,C,H", ATT_SHAPES)
 def test_temporal_attention(cuda_device, B, F, J, C, H, use_ref):
     g = torch.Generator().manual_seed(B * 1000 + F)
