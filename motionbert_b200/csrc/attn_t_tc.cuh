@@ -6,7 +6,7 @@
 //   * Q/K/V tiles are gathered straight out of the (B*F*J, 3C) token-major QKV buffer by a 5-D TMA
 //     tensor map (col, joint, frame, batch, plane) - the temporal "permute" is free.
 //   * S = Q K^T  : tcgen05.mma, M=128 query frames x N=NK keys, fp32 accumulator in TMEM (NK <= 256 columns)
-//   * softmax    : 256 threads, 2 per query row (= TMEM lane), each owning half of the keys; probabilities are written back
+//   * softmax    : 512 threads, 4 per query row (= TMEM lane), each owning a quarter of the keys; probabilities are written back
 //                  IN PLACE over S as packed bf16 hi / lo planes (32 score columns -> 16 hi + 16 lo columns)
 //   * O = P V    : tcgen05.mma with the A operand read from TMEM (P) and V as an MN-major smem operand
 //   * epilogue   : O / rowsum -> bf16 hi/lo planes of the (M, C) attention output (token-major again)
@@ -18,8 +18,11 @@
 
 namespace mb {
 
-constexpr int ATT_THREADS = 320;      // TMA warp, MMA warp, 8 softmax/output warps
+constexpr int ATT_THREADS = 320;      // (attn_s_tc / attn_t_tc2) TMA warp, MMA warp, 8 softmax/output warps
 constexpr int ATT_SM_THREADS = 256;
+constexpr int ATT_T_GROUPS = 4;       // temporal kernel: 4 threads per query row, each owning a quarter of the keys
+constexpr int ATT_T_SM_THREADS = ATT_T_GROUPS * 128;      // 16 softmax/output warps: the softmax is latency-bound,
+constexpr int ATT_T_THREADS = 64 + ATT_T_SM_THREADS;      // 4 warps per scheduler hide MUFU / tcgen05.ld latency
 constexpr int ATT_BM = 128;      // query rows per tile
 constexpr int ATT_MAXK = 256;    // max keys (frames)
 
@@ -43,12 +46,12 @@ struct AttnCfg {
     static constexpr int OFF_V = KV_MAX_BYTES;
     static constexpr int OFF_Q = 2 * KV_MAX_BYTES;
     static constexpr int OFF_BAR = OFF_Q + 2 * Q_BYTES;
-    static constexpr int OFF_RED = OFF_BAR + 256;                 // float red_max[2][128], red_sum[2][128]
-    static constexpr int SMEM_BYTES = OFF_RED + 4 * 128 * 4 + 1024;
+    static constexpr int OFF_RED = OFF_BAR + 256;                 // float red_max[4][128], red_sum[4][128]
+    static constexpr int SMEM_BYTES = OFF_RED + 2 * ATT_T_GROUPS * 128 * 4 + 1024;
 };
 
 template <int HD, int PASSES>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_T_THREADS, 1)
 attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128, 1, PLANES)
                  const __grid_constant__ CUtensorMap tmKV,   // box (HD, 1, NK , 1, PLANES)
                  const AttnTParams p) {
@@ -83,9 +86,9 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
         mbar_init(&q_full[0], 1);  mbar_init(&q_full[1], 1);
         mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
         mbar_init(s_full, 1);
-        mbar_init(p_full, ATT_SM_THREADS);
+        mbar_init(p_full, ATT_T_SM_THREADS);
         mbar_init(o_full, 1);
-        mbar_init(o_empty, ATT_SM_THREADS);
+        mbar_init(o_empty, ATT_T_SM_THREADS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -192,15 +195,16 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
             ++kv_it;
         }
     } else {
-        // ---------------------------------------------------------------- softmax + output (warps 2..9)
+        // ---------------------------------------------------------------- softmax + output (warps 2..17)
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;               // which half of the key chunks / output columns
+        const int grp = (warp - 2) >> 2;                // which quarter of the key chunks / output columns
         const int r_in_tile = quad * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
         const int nch = (p.NK + 31) / 32;
-        const int ch_lo = half * 4, ch_hi = (half * 4 + 4 < nch) ? half * 4 + 4 : nch;   // my chunks [ch_lo, ch_hi)
-        float* red_max = reinterpret_cast<float*>(smem + Cfg::OFF_RED);   // [2][128]
-        float* red_sum = red_max + 256;                                   // [2][128]
+        const int ch_lo = grp * 2 < nch ? grp * 2 : nch;
+        const int ch_hi = (grp * 2 + 2 < nch) ? grp * 2 + 2 : nch;       // my chunks [ch_lo, ch_hi)
+        float* red_max = reinterpret_cast<float*>(smem + Cfg::OFF_RED);   // [4][128]
+        float* red_sum = red_max + ATT_T_GROUPS * 128;                    // [4][128]
         const float sl2 = p.scale_log2e;
         uint32_t t_it = 0;
         for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
@@ -209,93 +213,80 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                 const uint32_t t_ph = t_it & 1;
                 mbar_wait(s_full, t_ph);
                 tc_fence_after();
-                // pass 1: row max of the raw scores over my key chunks (scale > 0 commutes with max).  tcgen05.ld of
-                // chunk k+1 is in flight while chunk k is reduced (two statically indexed register buffers).
+                // pass 1: row max of the raw scores over my key chunks (scale > 0 commutes with max)
                 float mx = -INFINITY;
-                uint32_t rr[2][32];
-                const int my_n = ch_hi - ch_lo;
-                if (my_n > 0) tmem_ld32(tmem_S + lane_off + ch_lo * 32, rr[0]);
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
+                    tmem_ld_wait();
+                    if (ch * 32 + 32 <= p.F) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < my_n) {
-                        const int ch = ch_lo + k;
-                        tmem_ld_wait();
-                        if (k + 1 < my_n) tmem_ld32(tmem_S + lane_off + (ch + 1) * 32, rr[(k + 1) & 1]);
-                        if (ch * 32 + 32 <= p.F) {
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[k & 1][i]));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(rr[k & 1][i]));
-                        }
+                        for (int i = 0; i < 32; ++i)
+                            if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
                     }
                 }
-                red_max[half * 128 + r_in_tile] = mx;
-                named_bar_sync(1, ATT_SM_THREADS);
-                mx = fmaxf(red_max[r_in_tile], red_max[128 + r_in_tile]);
+                red_max[grp * 128 + r_in_tile] = mx;
+                named_bar_sync(1, ATT_T_SM_THREADS);
+                mx = fmaxf(fmaxf(red_max[r_in_tile], red_max[128 + r_in_tile]),
+                           fmaxf(red_max[256 + r_in_tile], red_max[384 + r_in_tile]));
                 const float mxs = mx * sl2;
                 // pass 2: p = 2^(s*c - max*c), partial row sum, bf16 hi/lo split written back over S
                 float sum = 0.f;
-                if (my_n > 0) tmem_ld32(tmem_S + lane_off + ch_lo * 32, rr[0]);
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
+                    tmem_ld_wait();
+                    uint32_t hi[16], lo[16];
+                    const bool full = ch * 32 + 32 <= p.F;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < my_n) {
-                        const int ch = ch_lo + k;
-                        tmem_ld_wait();
-                        if (k + 1 < my_n) tmem_ld32(tmem_S + lane_off + (ch + 1) * 32, rr[(k + 1) & 1]);
-                        uint32_t hi[16], lo[16];
-                        const bool full = ch * 32 + 32 <= p.F;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float p0 = ex2_approx(fmaf(__uint_as_float(rr[k & 1][2 * i]), sl2, -mxs));
-                            float p1 = ex2_approx(fmaf(__uint_as_float(rr[k & 1][2 * i + 1]), sl2, -mxs));
-                            if (!full) {
-                                if (ch * 32 + 2 * i >= p.F) p0 = 0.f;
-                                if (ch * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
-                            }
-                            sum += p0 + p1;
-                            split2(p0, p1, hi[i], lo[i]);
+                    for (int i = 0; i < 16; ++i) {
+                        float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mxs));
+                        float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mxs));
+                        if (!full) {
+                            if (ch * 32 + 2 * i >= p.F) p0 = 0.f;
+                            if (ch * 32 + 2 * i + 1 >= p.F) p1 = 0.f;
                         }
-                        // the next chunk's scores are already on their way to registers: overwriting THIS chunk's
-                        // columns with P cannot race with it (different columns)
-                        tmem_st16(tmem_S + lane_off + ch * 32, hi);
-                        if (PASSES == 3) tmem_st16(tmem_S + lane_off + ch * 32 + 16, lo);
+                        sum += p0 + p1;
+                        split2(p0, p1, hi[i], lo[i]);
                     }
+                    tmem_st16(tmem_S + lane_off + ch * 32, hi);
+                    if (PASSES == 3) tmem_st16(tmem_S + lane_off + ch * 32 + 16, lo);
                 }
-                red_sum[half * 128 + r_in_tile] = sum;
+                red_sum[grp * 128 + r_in_tile] = sum;
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(p_full);
-                named_bar_sync(1, ATT_SM_THREADS);
-                const float inv = 1.0f / (red_sum[r_in_tile] + red_sum[128 + r_in_tile]);
+                named_bar_sync(1, ATT_T_SM_THREADS);
+                const float inv = 1.0f / ((red_sum[r_in_tile] + red_sum[128 + r_in_tile]) +
+                                          (red_sum[256 + r_in_tile] + red_sum[384 + r_in_tile]));
 
-                // output tile: thread (row, half) writes HD/2 columns (HD == 32: half 0 writes all 32)
+                // output tile: thread (row, grp) writes 16 of the HD columns (HD == 32: groups 0 and 1 only)
                 mbar_wait(o_full, t_ph);
                 tc_fence_after();
                 const int t = qt * ATT_BM + r_in_tile;
                 const bool ok = t < p.F;
                 const size_t tok = (static_cast<size_t>(b) * p.F + (ok ? t : 0)) * p.J + j;
-                if (HD == 64 || half == 0) {
-                    const int c0 = (HD == 64) ? half * 32 : 0;
+                if (grp * 16 < HD) {
+                    const int c0 = grp * 16;
                     const size_t ob = tok * p.C + h * HD + c0;
-                    uint32_t r[32];
-                    tmem_ld32(tmem_O + lane_off + c0, r);
+                    uint32_t r[16];
+                    tmem_ld16(tmem_O + lane_off + c0, r);
                     tmem_ld_wait();
                     if (ok) {
-                        uint32_t hi[16], lo[16];
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
+                        for (int i = 0; i < 8; ++i)
                             split2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv, hi[i], lo[i]);
                         uint4* h4 = reinterpret_cast<uint4*>(p.out_hi + ob);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            h4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                        h4[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        h4[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                         if (p.out_lo) {
                             uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + ob);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                            l4[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            l4[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                         }
                     }
                 }

@@ -674,10 +674,10 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
         LAUNCH_CHECK("attn_t2_kernel");
         return MB_OK;
     }
-    if (hd == 64 && passes == 3) attn_t_tc_kernel<64, 3><<<grid, ATT_THREADS, AttnCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
-    else if (hd == 32 && passes == 3) attn_t_tc_kernel<32, 3><<<grid, ATT_THREADS, AttnCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
-    else if (hd == 64) attn_t_tc_kernel<64, 1><<<grid, ATT_THREADS, AttnCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
-    else attn_t_tc_kernel<32, 1><<<grid, ATT_THREADS, AttnCfg<32, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    if (hd == 64 && passes == 3) attn_t_tc_kernel<64, 3><<<grid, ATT_T_THREADS, AttnCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    else if (hd == 32 && passes == 3) attn_t_tc_kernel<32, 3><<<grid, ATT_T_THREADS, AttnCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    else if (hd == 64) attn_t_tc_kernel<64, 1><<<grid, ATT_T_THREADS, AttnCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
+    else attn_t_tc_kernel<32, 1><<<grid, ATT_T_THREADS, AttnCfg<32, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
     LAUNCH_CHECK("attn_t_tc_kernel");
     return MB_OK;
 }
