@@ -213,6 +213,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + half * 128 + (static_cast<uint32_t>(quad * 32) << 16);
+            uint32_t racc[kResid ? 1 : 2][32];
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch, ++ci) {
                 const int b = ci & 1;
@@ -234,9 +235,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 } else {
                     if (lane == 0) tma_store_wait_read<1>();           // group ci-2 no longer reads buf[b]
                 }
-                uint32_t r[32];
-                tmem_ld32(t_row + ch * 32, r);
-                tmem_ld_wait();
+                // non-residual epilogues double-buffer the accumulator chunk: tcgen05.ld of chunk ch+1 is in flight while
+                // chunk ch is processed (the residual variant has no registers to spare at 10 warps / 168 registers)
+                uint32_t (&r)[32] = racc[kResid ? 0 : (ch & 1)];
+                if (kResid) {
+                    tmem_ld32(t_row + ch * 32, r);
+                    tmem_ld_wait();
+                } else {
+                    if (ch == 0) tmem_ld32(t_row, racc[0]);
+                    tmem_ld_wait();
+                    if (ch + 1 < NCH) tmem_ld32(t_row + (ch + 1) * 32, racc[(ch + 1) & 1]);
+                }
                 float v[32];
                 if (kResid) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
