@@ -73,6 +73,7 @@ typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 #define MB_FLAG_REF_ATTN_T 0x2u   /* TEST ONLY: CUDA-core reference temporal attention                */
 #define MB_FLAG_REF_ATTN_S 0x8u   /* TEST ONLY: CUDA-core reference spatial attention                 */
 #define MB_FLAG_ATTN_T_V2  0x10u  /* TEST ONLY: experimental temporal attention with P in a smem ring   */
+#define MB_FLAG_ATTN_T_UNPACKED 0x20u /* TEST ONLY: one-sequence-per-tile temporal kernel even when F <= 32 */
 #define MB_FLAG_GEMM_1CTA  0x4u   /* TEST ONLY: first-generation 1-CTA tcgen05 GEMM (LSU epilogue)    */
 
 int mb_version(void);
@@ -141,7 +142,7 @@ int mb_test_linear(int mode, int math, int use_ref /* 0: 2-CTA tcgen05 (product)
 /* Attention over a fp32 qkv buffer [B*F*J, 3C] -> y fp32 [B*F*J, C].  temporal=1: forward_temporal
  * (DSTformer.py:188-200), 0: forward_spatial (:178-186). */
 int mb_test_attention_scratch_bytes(int B, int F, int J, int C, size_t* bytes);
-int mb_test_attention(int temporal, int math, int use_ref, int B, int F, int J, int C, int H, const float* qkv,
+int mb_test_attention(int temporal, int math, int use_ref /* 0 product, 1 CUDA-core ref, 2 smem-ring T variant, 3 unpacked T */, int B, int F, int J, int C, int H, const float* qkv,
                       float* y, void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus

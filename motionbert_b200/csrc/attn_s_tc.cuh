@@ -18,8 +18,15 @@ namespace mb {
 constexpr int ATS_FRAMES = 4;     // frames per tile
 constexpr int ATS_SLAB = 32;      // rows reserved per frame (J <= 32)
 
+// The same packed kernel also serves TEMPORAL attention of short clips (F <= 32 frames: T=27 of BASELINE config 5,
+// T=16 / T=30 of the mesh / PoseTrack datasets): there a "sequence" is one (batch, joint) pair, its rows are the F
+// frames (token stride J), and four such sequences share a tile -- instead of one 128-row tile per sequence with
+// 79 % padding in attn_t_tc.cuh.
 struct AttnSParams {
-    int BF, J, C, H;
+    int nseq;     // sequences: B*F frames (spatial) or B*J (batch, joint) pairs (temporal-packed)
+    int L;        // valid rows per sequence: J (spatial) or F <= 32 (temporal-packed)
+    int F, J;     // clip length and joints (token index math of the temporal-packed mode)
+    int C, H;
     float scale_log2e;
     __nv_bfloat16* out_hi;   // [M, C]
     __nv_bfloat16* out_lo;
@@ -44,9 +51,10 @@ struct AttnSCfg {
 //   MMA      : S(i+1) = Q K^T is issued BEFORE waiting for the probabilities of problem i, so it runs under
 //              softmax(i); O(i) = P V runs under softmax(i+1)
 //   softmax  : softmax(i+1) precedes the output epilogue of problem i
-template <int HD, int PASSES>
+template <int HD, int PASSES, bool TEMPORAL>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF, plane), box (HD, 32, 4, PLANES)
+attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 4-D (3C, J, BF, plane), box (HD, 32, 4, PLANES)
+                                                              // temporal: 5-D (3C, J, F, B, plane), box (HD, 1, 32, 1, 1)
                  const AttnSParams p) {
     using Cfg = AttnSCfg<HD, PASSES>;
     extern __shared__ uint8_t smem_raw[];
@@ -64,7 +72,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_groups = (p.BF + ATS_FRAMES - 1) / ATS_FRAMES;
+    const int num_groups = (p.nseq + ATS_FRAMES - 1) / ATS_FRAMES;
     const int num_prob = num_groups * p.H;
     const int n_mine = (num_prob > static_cast<int>(blockIdx.x))
                            ? (num_prob - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
@@ -99,13 +107,27 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
                 const int s = i & 1;
                 const uint32_t ph = (i >> 1) & 1;
                 uint8_t* set = smem + s * Cfg::SET_BYTES;
+                // one operand tile = [plane][4 slabs x 32 rows][HD]; in the temporal mode every (slab, plane) is its own
+                // 32-frame box of one (batch, joint) sequence (sequences past the end are fully out of bounds -> zeros)
+                auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col) {
+                    if (!TEMPORAL) {
+                        tma_load_4d(dst, &tmQKV, bar, col, 0, f0, 0);
+                    } else {
+                        for (int pl = 0; pl < Cfg::PLANES; ++pl)
+                            for (int f = 0; f < ATS_FRAMES; ++f) {
+                                const int seq = f0 + f;
+                                const int b = seq / p.J, j = seq % p.J;      // b >= B when seq >= nseq: OOB -> zero fill
+                                tma_load_5d(dst + pl * Cfg::PLANE + f * ATS_SLAB * Cfg::SWZ, &tmQKV, bar, col, j, 0, b, pl);
+                            }
+                    }
+                };
                 mbar_wait(&qk_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&qk_full[s], 2 * Cfg::TILE_BYTES);
-                tma_load_4d(set, &tmQKV, &qk_full[s], h * HD, 0, f0, 0);                               // Q
-                tma_load_4d(set + Cfg::TILE_BYTES, &tmQKV, &qk_full[s], p.C + h * HD, 0, f0, 0);       // K
+                load_tile(set, &qk_full[s], h * HD);                                 // Q
+                load_tile(set + Cfg::TILE_BYTES, &qk_full[s], p.C + h * HD);         // K
                 mbar_wait(&v_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&v_full[s], Cfg::TILE_BYTES);
-                tma_load_4d(set + 2 * Cfg::TILE_BYTES, &tmQKV, &v_full[s], 2 * p.C + h * HD, 0, f0, 0);   // V
+                load_tile(set + 2 * Cfg::TILE_BYTES, &v_full[s], 2 * p.C + h * HD);  // V
             }
         }
     } else if (warp == 1) {
@@ -195,14 +217,14 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
                 float mx = -INFINITY;
 #pragma unroll
                 for (int k = 0; k < 32; ++k)
-                    if (k < p.J) mx = fmaxf(mx, __uint_as_float(r[k]));
+                    if (k < p.L) mx = fmaxf(mx, __uint_as_float(r[k]));
                 const float mxs = mx * sl2;
                 float sum = 0.f;
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    float p0 = (2 * k < p.J) ? ex2_approx(fmaf(__uint_as_float(r[2 * k]), sl2, -mxs)) : 0.f;
-                    float p1 = (2 * k + 1 < p.J) ? ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), sl2, -mxs)) : 0.f;
+                    float p0 = (2 * k < p.L) ? ex2_approx(fmaf(__uint_as_float(r[2 * k]), sl2, -mxs)) : 0.f;
+                    float p1 = (2 * k + 1 < p.L) ? ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), sl2, -mxs)) : 0.f;
                     sum += p0 + p1;
                     split2(p0, p1, hi[k], lo[k]);
                 }
@@ -235,15 +257,18 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // 4-D (3C, J, BF,
             const float inv = 1.0f / red_sum[(i % 3) * 128 + r_in_tile];
             mbar_wait(&o_full[s], (i >> 1) & 1);
             tc_fence_after();
-            const int frame = g * ATS_FRAMES + quad;
-            const bool ok = (lane < p.J) && (frame < p.BF);
+            const int seq = g * ATS_FRAMES + quad;
+            const bool ok = (lane < p.L) && (seq < p.nseq);
+            // token row of (sequence, lane): frame-major spatial tokens, or frame `lane` of the (b, j) sequence
+            const size_t tok = !TEMPORAL ? static_cast<size_t>(seq) * p.J + lane
+                                         : (static_cast<size_t>(seq / p.J) * p.F + lane) * p.J + (seq % p.J);
             if (HD == 64 || half == 0) {
                 const int c0 = (HD == 64) ? half * 32 : 0;
                 uint32_t r[32];
                 tmem_ld32(tO + lane_off + c0, r);
                 tmem_ld_wait();
                 if (ok) {
-                    const size_t ob = (static_cast<size_t>(frame) * p.J + lane) * p.C + h * HD + c0;
+                    const size_t ob = tok * p.C + h * HD + c0;
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int k = 0; k < 16; ++k)

@@ -160,10 +160,11 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(attn_t_tc_kernel<32, 3>, AttnCfg<32, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 1>, AttnCfg<64, 1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<32, 1>, AttnCfg<32, 1>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_s_tc_kernel<64, 3>, AttnSCfg<64, 3>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_s_tc_kernel<32, 3>, AttnSCfg<32, 3>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_s_tc_kernel<64, 1>, AttnSCfg<64, 1>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_s_tc_kernel<32, 1>, AttnSCfg<32, 1>::SMEM_BYTES));
+#define SET_ATS(HD_, P_) \
+        CUDA_TRY(set_smem(attn_s_tc_kernel<HD_, P_, false>, AttnSCfg<HD_, P_>::SMEM_BYTES)); \
+        CUDA_TRY(set_smem(attn_s_tc_kernel<HD_, P_, true>, AttnSCfg<HD_, P_>::SMEM_BYTES))
+        SET_ATS(64, 3); SET_ATS(32, 3); SET_ATS(64, 1); SET_ATS(32, 1);
+#undef SET_ATS
         CUDA_TRY(set_smem(attn_s_kernel<64>, 200 * 1024));
         CUDA_TRY(set_smem(attn_s_kernel<32>, 200 * 1024));
         CUDA_TRY(set_smem(attn_t_ref_kernel<64>, 200 * 1024));
@@ -208,6 +209,7 @@ struct Plan {
     CUtensorMap tm_hid, tm_ao, tm_q, tm_kv;
     CUtensorMap tm_qkv_st, tm_hid_st;   // split-store maps of the qkv / hidden buffers
     CUtensorMap tm_qkv_sp;              // 4-D (col, joint, frame, plane) view of qkv for spatial attention
+    CUtensorMap tm_qkv_t32;             // 5-D view, box (d, 1, 32 frames, 1, 1): packed temporal attention (F <= 32)
 };
 
 struct MbEncoder {
@@ -556,6 +558,8 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
         const uint64_t str4[3] = {C3, C3 * d.num_joints, qkv_plane_el};
         const uint32_t box4[4] = {static_cast<uint32_t>(hd), ATS_SLAB, ATS_FRAMES, planes};
         if ((rc = make_tmap(&P->tm_qkv_sp, P->qkv, 4, dims4, str4, box4, hd * 2))) return rc;
+        const uint32_t box_t32[5] = {static_cast<uint32_t>(hd), 1, ATS_SLAB, 1, 1};
+        if ((rc = make_tmap(&P->tm_qkv_t32, P->qkv, 5, dims, str, box_t32, hd * 2))) return rc;
     }
     return MB_OK;
 }
@@ -638,17 +642,33 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     }
     if (!temporal) {
         AttnSParams sp;
-        sp.BF = B * F; sp.J = J; sp.C = C; sp.H = H;
+        sp.nseq = B * F; sp.L = J; sp.F = F; sp.J = J; sp.C = C; sp.H = H;
         sp.scale_log2e = scale * 1.4426950408889634f;
         sp.out_hi = o_hi;
         sp.out_lo = o_lo;
         const int prob = ((B * F + ATS_FRAMES - 1) / ATS_FRAMES) * H;
         const int grid = prob < e->dev.sms ? prob : e->dev.sms;
-        if (hd == 64 && passes == 3) attn_s_tc_kernel<64, 3><<<grid, ATT_THREADS, AttnSCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
-        else if (hd == 32 && passes == 3) attn_s_tc_kernel<32, 3><<<grid, ATT_THREADS, AttnSCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
-        else if (hd == 64) attn_s_tc_kernel<64, 1><<<grid, ATT_THREADS, AttnSCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
-        else attn_s_tc_kernel<32, 1><<<grid, ATT_THREADS, AttnSCfg<32, 1>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        if (hd == 64 && passes == 3) attn_s_tc_kernel<64, 3, false><<<grid, ATT_THREADS, AttnSCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        else if (hd == 32 && passes == 3) attn_s_tc_kernel<32, 3, false><<<grid, ATT_THREADS, AttnSCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        else if (hd == 64) attn_s_tc_kernel<64, 1, false><<<grid, ATT_THREADS, AttnSCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
+        else attn_s_tc_kernel<32, 1, false><<<grid, ATT_THREADS, AttnSCfg<32, 1>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
         LAUNCH_CHECK("attn_s_tc_kernel");
+        return MB_OK;
+    }
+    if (F <= ATS_SLAB && !(flags & (MB_FLAG_REF_ATTN_T | MB_FLAG_ATTN_T_V2 | MB_FLAG_ATTN_T_UNPACKED))) {
+        // short clips: four (batch, joint) sequences per 128-row tile (same kernel as the spatial attention)
+        AttnSParams sp;
+        sp.nseq = B * J; sp.L = F; sp.F = F; sp.J = J; sp.C = C; sp.H = H;
+        sp.scale_log2e = scale * 1.4426950408889634f;
+        sp.out_hi = o_hi;
+        sp.out_lo = o_lo;
+        const int prob = ((B * J + ATS_FRAMES - 1) / ATS_FRAMES) * H;
+        const int grid = prob < e->dev.sms ? prob : e->dev.sms;
+        if (hd == 64 && passes == 3) attn_s_tc_kernel<64, 3, true><<<grid, ATT_THREADS, AttnSCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_qkv_t32, sp);
+        else if (hd == 32 && passes == 3) attn_s_tc_kernel<32, 3, true><<<grid, ATT_THREADS, AttnSCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_qkv_t32, sp);
+        else if (hd == 64) attn_s_tc_kernel<64, 1, true><<<grid, ATT_THREADS, AttnSCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_qkv_t32, sp);
+        else attn_s_tc_kernel<32, 1, true><<<grid, ATT_THREADS, AttnSCfg<32, 1>::SMEM_BYTES, st>>>(P.tm_qkv_t32, sp);
+        LAUNCH_CHECK("attn_s_tc_kernel<temporal-packed>");
         return MB_OK;
     }
     if (flags & MB_FLAG_REF_ATTN_T) {
@@ -1124,8 +1144,10 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         const uint32_t box_kv[5] = {static_cast<uint32_t>(hd), 1, NK, 1, planes};
         if ((rc = make_tmap(&P.tm_q, P.qkv, 5, dims, str, box_q, hd * 2))) return rc;
         if ((rc = make_tmap(&P.tm_kv, P.qkv, 5, dims, str, box_kv, hd * 2))) return rc;
+        const uint32_t box_t32[5] = {static_cast<uint32_t>(hd), 1, ATS_SLAB, 1, 1};
+        if ((rc = make_tmap(&P.tm_qkv_t32, P.qkv, 5, dims, str, box_t32, hd * 2))) return rc;
     }
-    rc = launch_attn(&e, use_ref == 1 ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : use_ref == 2 ? MB_FLAG_ATTN_T_V2 : 0u,
+    rc = launch_attn(&e, use_ref == 3 ? MB_FLAG_ATTN_T_UNPACKED : use_ref == 1 ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : use_ref == 2 ? MB_FLAG_ATTN_T_V2 : 0u,
                      temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st);
     if (rc) return rc;
     const size_t n = M * C;
