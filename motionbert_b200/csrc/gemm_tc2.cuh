@@ -10,11 +10,9 @@
 //     128 A rows and HALF of the B tile (32 KB / stage instead of 48 KB), the leader CTA's single thread issues the
 //     MMAs for both SMs, completion is multicast to both CTAs' barriers (tcgen05.commit ... multicast::cluster);
 //   * the epilogue never touches global memory with LSU instructions for tile data: the residual tile arrives by
-//     TMA into swizzled smem (one 128-row x 32-column fp32 box per column half, prefetched one chunk ahead), results
-//     are written to swizzled smem staging and leave through TMA stores (cp.async.bulk.tensor ... bulk_group), fully
-//     coalesced, rows beyond M clipped by the tensor map.  The four quadrant warps of a column half share one box per
-//     chunk (one elected thread issues the TMA ops, two 128-thread named barriers per chunk): 4x fewer TMA operations
-//     than per-warp 32-row boxes, which had made short-K GEMMs (Lite, K = 256) epilogue-bound.
+//     TMA into swizzled smem (one 32x32 fp32 box per warp, prefetched one chunk ahead), results are written to
+//     swizzled smem staging and leave through TMA stores (cp.async.bulk.tensor ... bulk_group), fully coalesced,
+//     rows beyond M clipped by the tensor map.
 // Warp roles per CTA (320 threads): w0 TMA producer, w1 MMA issuer (leader CTA only) + TMEM alloc,
 // w2..w9 epilogue (lane quadrant = warp%4, column half = (warp-2)/4, 4 chunks of 32 columns each).
 #pragma once
@@ -31,7 +29,7 @@ constexpr int G2_EPI_THREADS_PAIR = 2 * G2_EPI_WARPS * 32;   // arrivals on the 
 template <int PASSES, int EPI>
 struct Gemm2Cfg {
     static constexpr int STAGES = (EPI == EPI_RESID) ? G2_STAGES_RESID : G2_STAGES_OTHER;
-    static constexpr int STAGING_PER_HALF = (EPI == EPI_RESID) ? 49152 : 32768;  // per column half: buf0 16 KB | buf1 16 KB | [split 16 KB]
+    static constexpr int STAGING_PER_WARP = (EPI == EPI_RESID) ? 12288 : 8192;   // buf0 4 KB | buf1 4 KB | [split 4 KB]
     static constexpr int BK = (PASSES == 3) ? 32 : 64;
     static constexpr int SWZ = BK * 2;
     static constexpr uint32_t LAYOUT = (SWZ == 128) ? 2u : 4u;
@@ -42,7 +40,7 @@ struct Gemm2Cfg {
     static constexpr int B_BYTES = PLANES * B_PLANE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB
     static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_STAGING + 2 * STAGING_PER_HALF;
+    static constexpr int OFF_BAR = OFF_STAGING + G2_EPI_WARPS * STAGING_PER_WARP;
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 };
 
@@ -50,9 +48,9 @@ template <int PASSES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane), box (BK, 128, PLANES)
              const __grid_constant__ CUtensorMap tmB,   // bf16 3D (K, N, plane), box (BK, 128, PLANES)
-             const __grid_constant__ CUtensorMap tmR,   // fp32 2D (N, M) residual,    box (32, 128)         [RESID]
-             const __grid_constant__ CUtensorMap tmX,   // fp32 2D (N, M) output,      box (32, 128)         [RESID/F32]
-             const __grid_constant__ CUtensorMap tmS,   // bf16 3D (N, M, plane) out,  box (32, 128, PLANES) [RESID/SPLIT]
+             const __grid_constant__ CUtensorMap tmR,   // fp32 2D (N, M) residual,    box (32, 32)         [RESID]
+             const __grid_constant__ CUtensorMap tmX,   // fp32 2D (N, M) output,      box (32, 32)         [RESID/F32]
+             const __grid_constant__ CUtensorMap tmS,   // bf16 3D (N, M, plane) out,  box (32, 32, PLANES) [RESID/SPLIT]
              const GemmParams p) {
     using Cfg = Gemm2Cfg<PASSES, EPI>;
     constexpr int G2_STAGES = Cfg::STAGES;
@@ -68,7 +66,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     uint64_t* empty_bar = bars + G2_STAGES;                // [STAGES] per CTA, multicast-committed by the leader
     uint64_t* tfull_bar = bars + 2 * G2_STAGES;            // [2]      per CTA, multicast-committed by the leader
     uint64_t* tempty_bar = bars + 2 * G2_STAGES + 2;       // [2]      leader's: 512 epilogue threads of the pair
-    uint64_t* rbar = bars + 2 * G2_STAGES + 4;             // [2 halves][2] residual box landed (slots sized for 16)
+    uint64_t* rbar = bars + 2 * G2_STAGES + 4;             // [8 warps][2] residual-tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + 2 * G2_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
@@ -175,13 +173,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         const int quad = warp & 3;
         const int half = ew >> 2;
         constexpr int NCH = 4;
-        const int r128 = quad * 32 + lane;                              // my row inside the CTA's 128-row slab
-        const bool issuer = (quad == 0 && lane == 0);                   // one TMA-issuing thread per column half
-        const int bar_id = 1 + half;                                    // named barrier of this half's 128 threads
-        uint8_t* stg = smem + Cfg::OFF_STAGING + half * Cfg::STAGING_PER_HALF;
-        uint8_t* buf[2] = {stg, stg + 16384};
-        uint8_t* bufS = stg + 32768;   // only exists (and is only used) for EPI_RESID
-        uint64_t* my_rbar = rbar + 2 * half;
+        uint8_t* stg = smem + Cfg::OFF_STAGING + ew * Cfg::STAGING_PER_WARP;
+        uint8_t* buf[2] = {stg, stg + 4096};
+        uint8_t* bufS = stg + 8192;   // only exists (and is only used) for EPI_RESID
+        uint64_t* my_rbar = rbar + 2 * ew;
         const int ngrp_out = p.N / STATS_GROUP;
         const uint32_t sw128 = static_cast<uint32_t>(lane & 7);          // SWIZZLE_128B: chunk16 ^= row % 8
         const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3);    // SWIZZLE_64B : chunk16 ^= (row / 2) % 4
@@ -189,20 +184,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         auto chunk_coords = [&](int tile, int ch, int& col0, int& rowb) {
             const int m_pair = tile / num_n, n_idx = tile % num_n;
             col0 = n_idx * 256 + half * 128 + ch * 32;
-            rowb = m_pair * 256 + static_cast<int>(rank) * 128;
+            rowb = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32;
         };
-        uint32_t ci = 0;   // chunks processed by this half (buffer parity / rbar phase)
-        if (kResid && issuer && pair < num_tiles) {
+        uint32_t ci = 0;   // chunks processed by this warp (buffer parity / rbar phase)
+        if (kResid && lane == 0 && pair < num_tiles) {
             int c0, r0;
             chunk_coords(pair, 0, c0, r0);
-            mbar_arrive_expect_tx(&my_rbar[0], 16384);
+            mbar_arrive_expect_tx(&my_rbar[0], 4096);
             tma_load_2d(buf[0], &tmR, &my_rbar[0], c0, r0);
         }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair; tile < num_tiles; tile += npairs) {
             const int m_pair = tile / num_n, n_idx = tile % num_n;
-            const int row = m_pair * 256 + static_cast<int>(rank) * 128 + r128;
+            const int row = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32 + lane;
             const bool row_ok = row < p.M;
 
             float mean = 0.f, rstd = 1.f, rscale = 1.f;
@@ -225,20 +220,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 int col0, rowb;
                 chunk_coords(tile, ch, col0, rowb);
                 if (kResid) {
-                    mbar_wait(&my_rbar[b], (ci >> 1) & 1);            // residual box landed in buf[b]
-                    if (issuer) {
+                    mbar_wait(&my_rbar[b], (ci >> 1) & 1);            // residual chunk landed in buf[b]
+                    if (lane == 0) {
                         tma_store_wait_read<0>();                      // group ci-1 no longer reads buf[b^1] / bufS
                         int nt = tile, nc = ch + 1;
                         if (nc == NCH) { nc = 0; nt = tile + npairs; }
                         if (nt < num_tiles) {
                             int c1, r1;
                             chunk_coords(nt, nc, c1, r1);
-                            mbar_arrive_expect_tx(&my_rbar[b ^ 1], 16384);
+                            mbar_arrive_expect_tx(&my_rbar[b ^ 1], 4096);
                             tma_load_2d(buf[b ^ 1], &tmR, &my_rbar[b ^ 1], c1, r1);
                         }
                     }
                 } else {
-                    if (issuer) tma_store_wait_read<1>();              // group ci-2 no longer reads buf[b]
+                    if (lane == 0) tma_store_wait_read<1>();           // group ci-2 no longer reads buf[b]
                 }
                 // non-residual epilogues double-buffer the accumulator chunk: tcgen05.ld of chunk ch+1 is in flight while
                 // chunk ch is processed (the residual variant has no registers to spare at 10 warps / 168 registers)
@@ -257,7 +252,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 bb = __ldg(b4 + i);
-                        const float4 x = *reinterpret_cast<const float4*>(buf[b] + r128 * 128 + ((i ^ sw128) << 4));
+                        const float4 x = *reinterpret_cast<const float4*>(buf[b] + lane * 128 + ((i ^ sw128) << 4));
                         v[4 * i + 0] = x.x + rscale * (__uint_as_float(r[4 * i + 0]) + bb.x);
                         v[4 * i + 1] = x.y + rscale * (__uint_as_float(r[4 * i + 1]) + bb.y);
                         v[4 * i + 2] = x.z + rscale * (__uint_as_float(r[4 * i + 2]) + bb.z);
@@ -287,11 +282,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 c = __ldg(c4 + i);
-                        const float4 sv = __ldg(s4 + i);
-                        v[4 * i + 0] = fmaf(rstd, __uint_as_float(r[4 * i + 0]), fmaf(ms, sv.x, c.x));
-                        v[4 * i + 1] = fmaf(rstd, __uint_as_float(r[4 * i + 1]), fmaf(ms, sv.y, c.y));
-                        v[4 * i + 2] = fmaf(rstd, __uint_as_float(r[4 * i + 2]), fmaf(ms, sv.z, c.z));
-                        v[4 * i + 3] = fmaf(rstd, __uint_as_float(r[4 * i + 3]), fmaf(ms, sv.w, c.w));
+                        const float4 s = __ldg(s4 + i);
+                        v[4 * i + 0] = fmaf(rstd, __uint_as_float(r[4 * i + 0]), fmaf(ms, s.x, c.x));
+                        v[4 * i + 1] = fmaf(rstd, __uint_as_float(r[4 * i + 1]), fmaf(ms, s.y, c.y));
+                        v[4 * i + 2] = fmaf(rstd, __uint_as_float(r[4 * i + 2]), fmaf(ms, s.z, c.z));
+                        v[4 * i + 3] = fmaf(rstd, __uint_as_float(r[4 * i + 3]), fmaf(ms, s.w, c.w));
                     }
                     if (EPI == EPI_LN_GELU_SPLIT) {
 #pragma unroll
@@ -302,34 +297,33 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
                     }
                 }
-                // every thread of this half has consumed buf[b] (residual) and the issuer has seen the older store
-                // groups retire: the staging buffers may be overwritten
-                named_bar_sync(bar_id, 128);
-                uint8_t* xs = buf[b];                                   // fp32 staging (aliases the residual box)
+                // all lanes have consumed buf[b] (residual) and lane 0 has seen the older store groups retire
+                __syncwarp();
+                uint8_t* xs = buf[b];                                   // fp32 staging (aliases the residual tile)
                 uint8_t* ss = kResid ? bufS : buf[b];                   // split staging
-                const bool do_split = kSplitOut && (!kResid || p.out_hi != nullptr);   // block-final residuals feed
-                if (kF32Out) {                                                         // only the fp32 fusion kernel
+                if (kF32Out) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4*>(xs + r128 * 128 + ((i ^ sw128) << 4)) =
+                        *reinterpret_cast<float4*>(xs + lane * 128 + ((i ^ sw128) << 4)) =
                             make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
-                if (do_split) {
+                const bool do_split = kSplitOut && (!kResid || p.out_hi != nullptr);   // block-final residuals feed
+                if (do_split) {                                                        // only the fp32 fusion kernel
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        *reinterpret_cast<uint4*>(ss + r128 * 64 + ((i ^ sw64) << 4)) =
+                        *reinterpret_cast<uint4*>(ss + lane * 64 + ((i ^ sw64) << 4)) =
                             make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
                         if (PASSES == 3)
-                            *reinterpret_cast<uint4*>(ss + 8192 + r128 * 64 + ((i ^ sw64) << 4)) =
+                            *reinterpret_cast<uint4*>(ss + 2048 + lane * 64 + ((i ^ sw64) << 4)) =
                                 make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (issuer) {
+                __syncwarp();
+                if (lane == 0) {
                     if (kF32Out) tma_store_2d(&tmX, xs, col0, rowb);
                     if (do_split) tma_store_3d(&tmS, ss, col0, rowb, 0);
                     tma_store_commit();
@@ -349,7 +343,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (issuer) tma_store_wait_all();
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();

@@ -98,19 +98,19 @@ static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_
     return MB_OK;
 }
 
-// fp32 [rows, cols] row-major matrix, 32-column x 128-row boxes, SWIZZLE_128B (epilogue residual loads / fp32 stores)
+// fp32 [rows, cols] row-major matrix, 32x32 boxes, SWIZZLE_128B (epilogue residual loads / fp32 stores)
 static int make_f32_tile_tmap(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols) {
     const uint64_t dims[2] = {cols, rows};
     const uint64_t str[1] = {cols};
-    const uint32_t box[2] = {32, 128};
+    const uint32_t box[2] = {32, 32};
     return make_tmap(out, base, 2, dims, str, box, 128, 4);
 }
-// bf16 hi/lo planes [2][rows, cols] (plane stride in elements), 32 x 128 x planes boxes, SWIZZLE_64B (epilogue split stores)
+// bf16 hi/lo planes [2][rows, cols] (plane stride in elements), 32x32xplanes boxes, SWIZZLE_64B (epilogue split stores)
 static int make_split_store_tmap(CUtensorMap* out, const void* hi, uint64_t rows, uint64_t cols, uint64_t plane_el,
                                  int passes) {
     const uint64_t dims[3] = {cols, rows, 2};
     const uint64_t str[2] = {cols, plane_el};
-    const uint32_t box[3] = {32, 128, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
+    const uint32_t box[3] = {32, 32, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
     return make_tmap(out, hi, 3, dims, str, box, 64, 2);
 }
 
