@@ -145,6 +145,13 @@ int mb_test_attention_scratch_bytes(int B, int F, int J, int C, size_t* bytes);
 int mb_test_attention(int temporal, int math, int use_ref /* 0 product, 1 CUDA-core ref, 2 smem-ring T variant, 3 unpacked T */, int B, int F, int J, int C, int H, const float* qkv,
                       float* y, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Backward groundwork (not yet wired into a native backward pass):
+ * dW[N,K] = G[M,N]^T . X[M,K] with the split-K tcgen05 weight-gradient kernel (both operands MN-major, no transposes).
+ * G = dL/dy and X = the layer input, token-major fp32 on the device; dW fp32 (overwritten).  N % 128 == 0, K % 256 == 0. */
+int mb_test_wgrad_scratch_bytes(int M, int N, int K, size_t* bytes);
+int mb_test_wgrad(int math, int M, int N, int K, const float* G, const float* X, float* dW, void* scratch,
+                  size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "simt_kernels.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace mb;
 
@@ -152,6 +153,8 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         SET_GEMM2(1, EPI_LN_SPLIT); SET_GEMM2(1, EPI_LN_GELU_SPLIT); SET_GEMM2(1, EPI_RESID);
         SET_GEMM2(1, EPI_LN_TANH_F32); SET_GEMM2(1, EPI_BIAS_F32);
 #undef SET_GEMM2
+        CUDA_TRY(set_smem(wgrad_kernel<3>, WgradCfg<3>::SMEM_BYTES));
+        CUDA_TRY(set_smem(wgrad_kernel<1>, WgradCfg<1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t2_kernel<64, 3>, Attn2Cfg<64, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t2_kernel<32, 3>, Attn2Cfg<32, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t2_kernel<64, 1>, Attn2Cfg<64, 1>::SMEM_BYTES));
@@ -1153,5 +1156,64 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
     const size_t n = M * C;
     merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(P.ao, passes == 3 ? P.ao + ao_plane / 2 : nullptr, y, n);
     LAUNCH_CHECK("merge_planes_kernel");
+    return MB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------ backward groundwork (row a15)
+extern "C" int mb_test_wgrad_scratch_bytes(int M, int N, int K, size_t* bytes) {
+    if (!bytes) return fail(MB_ERR_NULL, "NULL argument");
+    *bytes = 2 * align_up(static_cast<size_t>(M) * N * 2, 1024) + 2 * align_up(static_cast<size_t>(M) * K * 2, 1024);
+    return MB_OK;
+}
+
+// dW[N,K] = G[M,N]^T X[M,K] with the tcgen05 split-K weight-gradient kernel (G, X, dW fp32 on the device).
+extern "C" int mb_test_wgrad(int math, int M, int N, int K, const float* G, const float* X, float* dW, void* scratch,
+                             size_t scratch_bytes, void* stream_) {
+    if (!G || !X || !dW || !scratch) return fail(MB_ERR_NULL, "NULL argument");
+    if (M < 1 || N % 128 || K % 256 || N < 128 || K < 256) return fail(MB_ERR_INVALID, "bad shape M=%d N=%d K=%d", M, N, K);
+    size_t need;
+    mb_test_wgrad_scratch_bytes(M, N, K, &need);
+    if (scratch_bytes < need) return fail(MB_ERR_WORKSPACE, "scratch too small");
+    int dev;
+    DevInfo info;
+    int rc = device_init(&dev, &info);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const int passes = math == MB_MATH_BF16 ? 1 : 3;
+    const size_t g_plane = align_up(static_cast<size_t>(M) * N * 2, 1024);
+    const size_t x_plane = align_up(static_cast<size_t>(M) * K * 2, 1024);
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    auto* g_hi = reinterpret_cast<__nv_bfloat16*>(b);
+    auto* x_hi = reinterpret_cast<__nv_bfloat16*>(b + 2 * g_plane);
+    {
+        const size_t n = static_cast<size_t>(M) * N;
+        split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(G, g_hi, g_hi + g_plane / 2, n);
+        const size_t n2 = static_cast<size_t>(M) * K;
+        split_flat_kernel<<<static_cast<int>((n2 + 255) / 256), 256, 0, st>>>(X, x_hi, x_hi + x_plane / 2, n2);
+        LAUNCH_CHECK("split_flat_kernel");
+    }
+    CUtensorMap tmG, tmX;
+    {
+        const uint32_t box[3] = {64, WG_BT, 1};
+        const uint64_t dG[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 2};
+        const uint64_t sG[2] = {static_cast<uint64_t>(N), g_plane / 2};
+        if ((rc = make_tmap(&tmG, g_hi, 3, dG, sG, box, 128))) return rc;
+        const uint64_t dX[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), 2};
+        const uint64_t sX[2] = {static_cast<uint64_t>(K), x_plane / 2};
+        if ((rc = make_tmap(&tmX, x_hi, 3, dX, sX, box, 128))) return rc;
+    }
+    CUDA_TRY(cudaMemsetAsync(dW, 0, static_cast<size_t>(N) * K * 4, st));
+    WgradParams wp;
+    wp.M = M; wp.N = N; wp.K = K; wp.dW = dW;
+    const int tiles = (N / 128) * (K / 256);
+    int splits = info.sms / tiles;
+    if (splits < 1) splits = 1;
+    const int max_splits = (M + WG_BT - 1) / WG_BT;
+    if (splits > max_splits) splits = max_splits;
+    wp.tokens_per_split = static_cast<int>(align_up((static_cast<size_t>(M) + splits - 1) / splits, WG_BT));
+    if (passes == 3) wgrad_kernel<3><<<tiles * splits, WG_THREADS, WgradCfg<3>::SMEM_BYTES, st>>>(tmG, tmX, wp);
+    else wgrad_kernel<1><<<tiles * splits, WG_THREADS, WgradCfg<1>::SMEM_BYTES, st>>>(tmG, tmX, wp);
+    LAUNCH_CHECK("wgrad_kernel");
     return MB_OK;
 }

@@ -44,3 +44,20 @@ def test_attention(temporal, qkv, B, F, J, C, H, math=0, use_ref=0):
                                          sp, nb.value, st), "mb_test_attention")
         torch.cuda.synchronize(dev)
     return y
+
+
+def test_wgrad(G_, X, math=0):
+    """dW = G^T X through the tcgen05 weight-gradient kernel."""
+    lib = _lib.load()
+    dev = G_.device
+    M, N = G_.shape
+    K = X.shape[1]
+    nb = ctypes.c_size_t()
+    _lib.check(lib.mb_test_wgrad_scratch_bytes(M, N, K, ctypes.byref(nb)))
+    keep, sp = _scratch(nb.value, dev)
+    dW = torch.full((N, K), float("nan"), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mb_test_wgrad(math, M, N, K, G_.data_ptr(), X.data_ptr(), dW.data_ptr(), sp, nb.value, st), "mb_test_wgrad")
+        torch.cuda.synchronize(dev)
+    return dW

@@ -126,3 +126,17 @@ def test_temporal_attention_bf16_single_pass(cuda_device, B, F, J, C, H):
     assert torch.isfinite(y).all()
     rel, mx = _rel(y, exp)
     assert rel < 1.5e-2, f"rel {rel:.3e} max {mx:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 256), (1000, 512, 512), (4131, 1536, 512), (20000, 512, 1024), (33, 256, 256)])
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["bf16x3", "bf16"])
+def test_weight_gradient_kernel(cuda_device, M, N, K, math_mode):
+    """Groundwork for the native backward: dW = dY^T X (split-K over the tokens, both operands MN-major)."""
+    g = torch.Generator().manual_seed(M + N)
+    Gm = torch.randn(M, N, generator=g).to(cuda_device)
+    X = (torch.randn(M, K, generator=g) * 1.3 + 0.2).to(cuda_device)
+    dW = G.test_wgrad(Gm, X, math=math_mode)
+    exp = Gm.double().T @ X.double()
+    assert torch.isfinite(dW).all()
+    rel, mx = _rel(dW, exp)
+    assert rel < (3e-5 if math_mode == 0 else 8e-3), f"rel {rel:.3e} max {mx:.3e}"
