@@ -151,6 +151,11 @@ int mb_test_attention(int temporal, int math, int use_ref /* 0 product, 1 CUDA-c
 int mb_test_wgrad_scratch_bytes(int M, int N, int K, size_t* bytes);
 int mb_test_wgrad(int math, int M, int N, int K, const float* G, const float* X, float* dW, void* scratch,
                   size_t scratch_bytes, void* stream);
+/* dX[M,K] = G[M,N] . W[N,K]: the production 2-CTA GEMM reading W in its forward layout as an MN-major operand
+ * (no transposed weight copy).  N % 64 == 0 (32 for BF16x3), K % 256 == 0. */
+int mb_test_dgrad_scratch_bytes(int M, int N, int K, size_t* bytes);
+int mb_test_dgrad(int math, int M, int N, int K, const float* G, const float* W, float* dX, void* scratch,
+                  size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,10 +44,13 @@ struct Gemm2Cfg {
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 };
 
-template <int PASSES, int EPI>
+// B_MN = true is the data-gradient form  dX[M, Kf] = G[M, Nf] * W[Nf, Kf]  (backward groundwork, row a15): the
+// contraction runs over W's ROW index, so the very same packed W planes are consumed as an MN-major B operand
+// (64-column SWIZZLE_128B blocks, LBO = block stride) instead of packing a transposed copy of every weight.
+template <int PASSES, int EPI, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane), box (BK, 128, PLANES)
-             const __grid_constant__ CUtensorMap tmB,   // bf16 3D (K, N, plane), box (BK, 128, PLANES)
+             const __grid_constant__ CUtensorMap tmB,   // bf16 3D (K, N, plane), box (BK, 128, PLANES); B_MN: (Kf, Nf, plane), box (64, BK, 1)
              const __grid_constant__ CUtensorMap tmR,   // fp32 2D (N, M) residual,    box (32, 32)         [RESID]
              const __grid_constant__ CUtensorMap tmX,   // fp32 2D (N, M) output,      box (32, 32)         [RESID/F32]
              const __grid_constant__ CUtensorMap tmS,   // bf16 3D (N, M, plane) out,  box (32, 32, PLANES) [RESID/SPLIT]
@@ -119,7 +122,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                     tma_load_3d_2cta(sA, &tmA, full_leader, kb * Cfg::BK, a_row, 0);
-                    tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::BK, b_row, 0);
+                    if (!B_MN) {
+                        tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::BK, b_row, 0);
+                    } else {
+                        // this CTA's 128 output columns = two 64-column blocks of [BK contraction rows][128 B] per plane
+                        for (int pl = 0; pl < Cfg::PLANES; ++pl)
+                            for (int blk = 0; blk < 2; ++blk)
+                                tma_load_3d_2cta(sB + pl * Cfg::B_PLANE + blk * (Cfg::BK * 128), &tmB, full_leader,
+                                                 b_row + blk * 64, kb * Cfg::BK, pl);
+                    }
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -127,7 +138,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
         if (rank == 0) {
-            constexpr uint32_t IDESC = umma_idesc_bf16(256, 256, 0, 0);
+            constexpr uint32_t IDESC = umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -143,18 +154,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                         const uint32_t sB = sA + Cfg::A_BYTES;
                         const uint64_t a_hi = umma_smem_desc(sA, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
-                        const uint64_t b_hi = umma_smem_desc(sB, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                         const uint64_t a_lo = umma_smem_desc(sA + Cfg::A_PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
-                        const uint64_t b_lo = umma_smem_desc(sB + Cfg::B_PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        // B: K-major rows of SWZ bytes, or (B_MN) MN-major 64-column blocks of [BK rows][128 B], SWIZZLE_128B
+                        const uint64_t b_hi = B_MN ? umma_smem_desc(sB, Cfg::BK * 128, 1024, 2u)
+                                                   : umma_smem_desc(sB, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        const uint64_t b_lo = B_MN ? umma_smem_desc(sB + Cfg::B_PLANE, Cfg::BK * 128, 1024, 2u)
+                                                   : umma_smem_desc(sB + Cfg::B_PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
 #pragma unroll
                         for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
                             const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
+                            const uint64_t boff = B_MN ? static_cast<uint64_t>((ks * 16 * 128) >> 4) : koff;   // 16 rows down
                             if (PASSES == 3) {
-                                umma_ss_2cta(d_tmem, a_lo + koff, b_hi + koff, IDESC, (kb | ks) != 0);
-                                umma_ss_2cta(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1);
-                                umma_ss_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1);
+                                umma_ss_2cta(d_tmem, a_lo + koff, b_hi + boff, IDESC, (kb | ks) != 0);
+                                umma_ss_2cta(d_tmem, a_hi + koff, b_lo + boff, IDESC, 1);
+                                umma_ss_2cta(d_tmem, a_hi + koff, b_hi + boff, IDESC, 1);
                             } else {
-                                umma_ss_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, (kb | ks) != 0);
+                                umma_ss_2cta(d_tmem, a_hi + koff, b_hi + boff, IDESC, (kb | ks) != 0);
                             }
                         }
                         tc_commit_2cta(&empty_bar[stage], 3);

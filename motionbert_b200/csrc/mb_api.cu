@@ -153,6 +153,8 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         SET_GEMM2(1, EPI_LN_SPLIT); SET_GEMM2(1, EPI_LN_GELU_SPLIT); SET_GEMM2(1, EPI_RESID);
         SET_GEMM2(1, EPI_LN_TANH_F32); SET_GEMM2(1, EPI_BIAS_F32);
 #undef SET_GEMM2
+        CUDA_TRY(set_smem(gemm2_kernel<3, EPI_BIAS_F32, true>, Gemm2Cfg<3, EPI_BIAS_F32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<3>, WgradCfg<3>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<1>, WgradCfg<1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t2_kernel<64, 3>, Attn2Cfg<64, 3>::SMEM_BYTES));
@@ -1215,5 +1217,72 @@ extern "C" int mb_test_wgrad(int math, int M, int N, int K, const float* G, cons
     if (passes == 3) wgrad_kernel<3><<<tiles * splits, WG_THREADS, WgradCfg<3>::SMEM_BYTES, st>>>(tmG, tmX, wp);
     else wgrad_kernel<1><<<tiles * splits, WG_THREADS, WgradCfg<1>::SMEM_BYTES, st>>>(tmG, tmX, wp);
     LAUNCH_CHECK("wgrad_kernel");
+    return MB_OK;
+}
+
+
+extern "C" int mb_test_dgrad_scratch_bytes(int M, int N, int K, size_t* bytes) {
+    if (!bytes) return fail(MB_ERR_NULL, "NULL argument");
+    *bytes = 2 * align_up(static_cast<size_t>(M) * N * 2, 1024) + 2 * align_up(static_cast<size_t>(N) * K * 2, 1024) +
+             align_up(static_cast<size_t>(K) * 4, 1024);
+    return MB_OK;
+}
+
+// dX[M,K] = G[M,N] W[N,K] with the 2-CTA GEMM consuming W (forward layout [N][K]) as an MN-major B operand.
+extern "C" int mb_test_dgrad(int math, int M, int N, int K, const float* G, const float* W, float* dX, void* scratch,
+                             size_t scratch_bytes, void* stream_) {
+    if (!G || !W || !dX || !scratch) return fail(MB_ERR_NULL, "NULL argument");
+    if (M < 1 || N % 64 || K % 256 || N < 64 || K < 256) return fail(MB_ERR_INVALID, "bad shape M=%d N=%d K=%d", M, N, K);
+    size_t need;
+    mb_test_dgrad_scratch_bytes(M, N, K, &need);
+    if (scratch_bytes < need) return fail(MB_ERR_WORKSPACE, "scratch too small");
+    int dev;
+    DevInfo info;
+    int rc = device_init(&dev, &info);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const int passes = math == MB_MATH_BF16 ? 1 : 3;
+    const size_t g_plane = align_up(static_cast<size_t>(M) * N * 2, 1024);
+    const size_t w_plane = align_up(static_cast<size_t>(N) * K * 2, 1024);
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    auto* g_hi = reinterpret_cast<__nv_bfloat16*>(b);
+    auto* w_hi = reinterpret_cast<__nv_bfloat16*>(b + 2 * g_plane);
+    float* zero_bias = reinterpret_cast<float*>(b + 2 * g_plane + 2 * w_plane);
+    {
+        const size_t n = static_cast<size_t>(M) * N;
+        split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(G, g_hi, g_hi + g_plane / 2, n);
+        const size_t n2 = static_cast<size_t>(N) * K;
+        split_flat_kernel<<<static_cast<int>((n2 + 255) / 256), 256, 0, st>>>(W, w_hi, w_hi + w_plane / 2, n2);
+        LAUNCH_CHECK("split_flat_kernel");
+        CUDA_TRY(cudaMemsetAsync(zero_bias, 0, static_cast<size_t>(K) * 4, st));
+    }
+    const int BK = passes == 3 ? 32 : 64;
+    if (N % BK) return fail(MB_ERR_INVALID, "contraction length %d must be a multiple of %d", N, BK);
+    CUtensorMap tmA, tmB, tmX;
+    {
+        const uint32_t pl = passes == 3 ? 2 : 1;
+        const uint64_t dA[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 2};       // A = G: contraction over N
+        const uint64_t sA[2] = {static_cast<uint64_t>(N), g_plane / 2};
+        const uint32_t bA[3] = {static_cast<uint32_t>(BK), 128u, pl};
+        if ((rc = make_tmap(&tmA, g_hi, 3, dA, sA, bA, BK * 2))) return rc;
+        const uint64_t dB[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), 2};       // B = W [N][K], MN-major view
+        const uint64_t sB[2] = {static_cast<uint64_t>(K), w_plane / 2};
+        const uint32_t bB[3] = {64u, static_cast<uint32_t>(BK), 1u};
+        if ((rc = make_tmap(&tmB, w_hi, 3, dB, sB, bB, 128))) return rc;
+        if ((rc = make_f32_tile_tmap(&tmX, dX, M, K))) return rc;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = K; p.K = N;          // GEMM view: output columns = K features, contraction = N
+    p.vec0 = zero_bias;
+    p.out_f32 = dX;
+    p.J = 1;
+    const int tiles2 = ((M + 255) / 256) * (K / 256);
+    const int grid2 = 2 * (tiles2 < info.sms / 2 ? tiles2 : info.sms / 2);
+    if (passes == 3)
+        gemm2_kernel<3, EPI_BIAS_F32, true><<<grid2, G2_THREADS, Gemm2Cfg<3, EPI_BIAS_F32>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmX, tmA, p);
+    else
+        gemm2_kernel<1, EPI_BIAS_F32, true><<<grid2, G2_THREADS, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmX, tmA, p);
+    LAUNCH_CHECK("gemm2_kernel<dgrad>");
     return MB_OK;
 }

@@ -61,3 +61,20 @@ def test_wgrad(G_, X, math=0):
         _lib.check(lib.mb_test_wgrad(math, M, N, K, G_.data_ptr(), X.data_ptr(), dW.data_ptr(), sp, nb.value, st), "mb_test_wgrad")
         torch.cuda.synchronize(dev)
     return dW
+
+
+def test_dgrad(G_, W, math=0):
+    """dX = G W through the 2-CTA GEMM with W consumed MN-major."""
+    lib = _lib.load()
+    dev = G_.device
+    M, N = G_.shape
+    K = W.shape[1]
+    nb = ctypes.c_size_t()
+    _lib.check(lib.mb_test_dgrad_scratch_bytes(M, N, K, ctypes.byref(nb)))
+    keep, sp = _scratch(nb.value, dev)
+    dX = torch.full((M, K), float("nan"), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mb_test_dgrad(math, M, N, K, G_.data_ptr(), W.data_ptr(), dX.data_ptr(), sp, nb.value, st), "mb_test_dgrad")
+        torch.cuda.synchronize(dev)
+    return dX

@@ -140,3 +140,17 @@ def test_weight_gradient_kernel(cuda_device, M, N, K, math_mode):
     assert torch.isfinite(dW).all()
     rel, mx = _rel(dW, exp)
     assert rel < (3e-5 if math_mode == 0 else 8e-3), f"rel {rel:.3e} max {mx:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (4131, 1536, 512), (1000, 1024, 512), (77, 512, 1024), (459, 256, 256)])
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["bf16x3", "bf16"])
+def test_data_gradient_kernel(cuda_device, M, N, K, math_mode):
+    """Groundwork for the native backward: dX = dY W with W read in its forward [N][K] layout (MN-major B operand)."""
+    g = torch.Generator().manual_seed(M + K)
+    Gm = torch.randn(M, N, generator=g).to(cuda_device)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(N)).to(cuda_device)
+    dX = G.test_dgrad(Gm, W, math=math_mode)
+    exp = Gm.double() @ W.double()
+    assert torch.isfinite(dX).all()
+    rel, mx = _rel(dX, exp)
+    assert rel < (3e-5 if math_mode == 0 else 8e-3), f"rel {rel:.3e} max {mx:.3e}"
