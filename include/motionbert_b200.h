@@ -153,6 +153,11 @@ int mb_test_wgrad(int math, int M, int N, int K, const float* G, const float* X,
                   size_t scratch_bytes, void* stream);
 /* dX[M,K] = G[M,N] . W[N,K]: the production 2-CTA GEMM reading W in its forward layout as an MN-major operand
  * (no transposed weight copy).  N % 64 == 0 (32 for BF16x3), K % 256 == 0. */
+/* d(qkv) [M,3C] of the attention core softmax(q k^T d^-1/2) v for a given d(out) [M,C] (fp32 in/out on the device):
+ * flash-style tcgen05 backward in bf16 single-pass arithmetic (attn_bwd_tc.cuh). */
+int mb_test_attention_backward_scratch_bytes(int B, int F, int J, int C, size_t* bytes);
+int mb_test_attention_backward(int temporal, int B, int F, int J, int C, int H, const float* qkv, const float* dO,
+                               float* dqkv, void* scratch, size_t scratch_bytes, void* stream);
 int mb_test_dgrad_scratch_bytes(int M, int N, int K, size_t* bytes);
 int mb_test_dgrad(int math, int M, int N, int K, const float* G, const float* W, float* dX, void* scratch,
                   size_t scratch_bytes, void* stream);

@@ -28,6 +28,7 @@ EXPORTS = [
     "mb_test_linear_scratch_bytes", "mb_test_linear",
     "mb_test_attention_scratch_bytes", "mb_test_attention", "mb_test_wgrad_scratch_bytes", "mb_test_wgrad",
     "mb_test_dgrad_scratch_bytes", "mb_test_dgrad",
+    "mb_test_attention_backward_scratch_bytes", "mb_test_attention_backward",
 ]
 
 
@@ -81,6 +82,8 @@ def load() -> C.CDLL:
     lib.mb_test_wgrad.argtypes = [i32, i32, i32, i32, fp, fp, fp, vp, sz, vp]
     lib.mb_test_dgrad_scratch_bytes.argtypes = [i32, i32, i32, C.POINTER(sz)]
     lib.mb_test_dgrad.argtypes = [i32, i32, i32, i32, fp, fp, fp, vp, sz, vp]
+    lib.mb_test_attention_backward_scratch_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
+    lib.mb_test_attention_backward.argtypes = [i32, i32, i32, i32, i32, i32, fp, fp, fp, vp, sz, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("mb_last_error", "mb_destroy"):

@@ -1,0 +1,489 @@
+// Attention-core backward on tcgen05 (bf16 single-pass arithmetic, fp32 accumulate).
+//
+// Forward (DSTformer.py:178-200):  S = Q K^T * c,  P = softmax_row(S),  O = P V          (per batch b, joint j, head h)
+// Backward, flash-style (P is recomputed on chip, never stored):
+//   delta_i = sum_d dO[i,d] O[i,d]        dP = dO V^T        dS = P (dP - delta) * c
+//   dQ = dS K            dK = dS^T Q            dV = P^T dO
+// Two kernels, both shaped like the forward temporal kernel (one 128-row tile at a time, 5-D TMA gathers):
+//   attn_bwd_q_kernel : rows = queries.  S and dP as two UMMA accumulators (2 x 256 TMEM columns), softmax statistics,
+//                       dS written back in place as packed bf16, dQ = dS K with dS read from TMEM and K as an
+//                       MN-major operand; also stores log2-sum-exp and delta per query for the second kernel.
+//   attn_bwd_kv_kernel: rows = keys.  S^T = K Q^T and dP^T = V dO^T, P^T / dS^T rebuilt from the stored statistics
+//                       (column vectors now), dV = P^T dO and dK = dS^T Q with dO / Q as MN-major operands.
+// The spatial attention is the same problem with (B' = B*F, F' = J, J' = 1): the host passes those dimensions.
+#pragma once
+#include "attn_t_tc.cuh"
+
+namespace mb {
+
+constexpr int ABW_THREADS = 320;       // w0 TMA, w1 MMA, w2..w9 SIMT (2 threads per row, each half of the columns)
+constexpr int ABW_SIMT = 256;
+
+struct AttnBwdParams {
+    int B, F, J, C, H;
+    int NK;                     // round_up(F, 16)
+    float scale;                // d^-1/2
+    float scale_log2e;
+    const __nv_bfloat16* O;     // [M, C]   forward attention output (for delta)          (q kernel)
+    const __nv_bfloat16* dO;    // [M, C]   gradient w.r.t. the attention output            (q kernel: row reads)
+    float* lse2;                // [B*J*H*F] log2-sum-exp of the scaled scores per query   (q kernel writes, kv reads)
+    float* delta;               // [B*J*H*F]
+    __nv_bfloat16* dqkv;        // [M, 3C]  output gradient (q part: q kernel; k, v parts: kv kernel)
+};
+
+template <int HD>
+struct AttnBwdCfg {
+    static constexpr int SWZ = HD * 2;
+    static constexpr uint32_t LAYOUT = (SWZ == 128) ? 2u : 4u;
+    static constexpr int TILE = ATT_BM * SWZ;                 // a 128-row operand tile
+    static constexpr int SEQ = ATT_MAXK * SWZ;                // a whole-sequence operand (<= 256 rows)
+    static constexpr int OFF_A = 0;                           // q kernel: Q tile   | kv kernel: K tile
+    static constexpr int OFF_B = TILE;                        // q kernel: dO tile  | kv kernel: V tile
+    static constexpr int OFF_C = 2 * TILE;                    // q kernel: K (seq)  | kv kernel: Q (seq)
+    static constexpr int OFF_D = 2 * TILE + SEQ;              // q kernel: V (seq)  | kv kernel: dO (seq)
+    static constexpr int OFF_BAR = 2 * TILE + 2 * SEQ;
+    static constexpr int OFF_VEC = OFF_BAR + 128;             // floats: red[2][128] | lse2[256], delta[256]
+    static constexpr int SMEM_BYTES = OFF_VEC + 2 * 256 * 4 + 1024;
+};
+
+// ------------------------------------------------------------------------------------------------- dQ kernel
+template <int HD>
+__global__ void __launch_bounds__(ABW_THREADS, 1)
+attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box (HD, 1, 128, 1, 1)
+                  const __grid_constant__ CUtensorMap tmQKV_s,   // qkv 5-D, box (HD, 1, NK , 1, 1)
+                  const __grid_constant__ CUtensorMap tmDO_t,    // dO  5-D, box (HD, 1, 128, 1, 1)
+                  const AttnBwdParams p) {
+    using Cfg = AttnBwdCfg<HD>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* kv_full = bars + 0;
+    uint64_t* kv_empty = bars + 1;
+    uint64_t* t_full = bars + 2;      // Q and dO tile landed
+    uint64_t* t_empty = bars + 3;
+    uint64_t* sd_full = bars + 4;     // S and dP accumulators ready
+    uint64_t* ds_full = bars + 5;     // dS written (256 threads)
+    uint64_t* dq_full = bars + 6;
+    uint64_t* dq_empty = bars + 7;    // 256 threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* red = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);   // [2][128] max, then [2][128] sum
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_prob = p.B * p.J * p.H;
+    const int num_qt = (p.F + ATT_BM - 1) / ATT_BM;
+    const uint32_t seq_bytes = static_cast<uint32_t>(p.NK) * Cfg::SWZ;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV_t); tma_prefetch_desc(&tmQKV_s); tma_prefetch_desc(&tmDO_t);
+        mbar_init(kv_full, 1);  mbar_init(kv_empty, 1);
+        mbar_init(t_full, 1);   mbar_init(t_empty, 1);
+        mbar_init(sd_full, 1);  mbar_init(ds_full, ABW_SIMT);
+        mbar_init(dq_full, 1);  mbar_init(dq_empty, ABW_SIMT);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;             // [0,256): S, then dS (packed bf16) in place
+    const uint32_t tmem_dP = tmem_base + 256;      // [256,512): dP, then dQ accumulator in its first HD columns
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t t_it = 0;
+            int ip = 0;
+            for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++ip) {
+                const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
+                mbar_wait(kv_empty, (ip & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full, 2 * seq_bytes);
+                tma_load_5d(smem + Cfg::OFF_C, &tmQKV_s, kv_full, p.C + h * HD, j, 0, b, 0);       // K
+                tma_load_5d(smem + Cfg::OFF_D, &tmQKV_s, kv_full, 2 * p.C + h * HD, j, 0, b, 0);   // V
+                for (int qt = 0; qt < num_qt; ++qt, ++t_it) {
+                    mbar_wait(t_empty, (t_it & 1) ^ 1);
+                    mbar_arrive_expect_tx(t_full, 2 * Cfg::TILE);
+                    tma_load_5d(smem + Cfg::OFF_A, &tmQKV_t, t_full, h * HD, j, qt * ATT_BM, b, 0);   // Q tile
+                    tma_load_5d(smem + Cfg::OFF_B, &tmDO_t, t_full, h * HD, j, qt * ATT_BM, b, 0);    // dO tile
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, p.NK, 0, 0);
+        const uint32_t idesc_q = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // dQ = dS K: B (=K) MN-major
+        const uint32_t sQ = smem_u32(smem + Cfg::OFF_A), sDO = smem_u32(smem + Cfg::OFF_B);
+        const uint32_t sK = smem_u32(smem + Cfg::OFF_C), sV = smem_u32(smem + Cfg::OFF_D);
+        uint32_t t_it = 0;
+        int ip = 0;
+        for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++ip) {
+            mbar_wait(kv_full, ip & 1);
+            for (int qt = 0; qt < num_qt; ++qt, ++t_it) {
+                const uint32_t ph = t_it & 1;
+                mbar_wait(t_full, ph);
+                mbar_wait(dq_empty, ph ^ 1);          // previous tile's dQ (aliases dP) has been read out
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t dq_ = umma_smem_desc(sQ, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                    const uint64_t ddo = umma_smem_desc(sDO, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                    const uint64_t dk = umma_smem_desc(sK, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                    const uint64_t dv = umma_smem_desc(sV, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) {
+                        const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
+                        umma_ss(tmem_S, dq_ + koff, dk + koff, idesc_s, ks != 0);      // S  = Q  K^T
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) {
+                        const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
+                        umma_ss(tmem_dP, ddo + koff, dv + koff, idesc_s, ks != 0);     // dP = dO V^T
+                    }
+                    tc_commit(sd_full);
+                    tc_commit(t_empty);
+                }
+                __syncwarp();
+                mbar_wait(ds_full, ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const int nks = p.NK / 16;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t a = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);      // packed bf16 dS
+                        const uint32_t koff = static_cast<uint32_t>(ks) * 16 * Cfg::SWZ;
+                        const uint64_t kmn = umma_smem_desc(sK + koff, 8 * Cfg::SWZ, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        umma_ts(tmem_dP, a, kmn, idesc_q, ks != 0);                     // dQ = dS K
+                    }
+                    tc_commit(dq_full);
+                    if (qt == num_qt - 1) tc_commit(kv_empty);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r_in_tile = quad * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const int nch = (p.NK + 31) / 32;
+        const int ch_lo = half * 4 < nch ? half * 4 : nch;
+        const int ch_hi = (half * 4 + 4 < nch) ? half * 4 + 4 : nch;
+        const float sl2 = p.scale_log2e;
+        uint32_t t_it = 0;
+        for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
+            const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
+            for (int qt = 0; qt < num_qt; ++qt, ++t_it) {
+                const uint32_t ph = t_it & 1;
+                const int tq = qt * ATT_BM + r_in_tile;
+                const bool ok = tq < p.F;
+                const size_t tok = (static_cast<size_t>(b) * p.F + (ok ? tq : 0)) * p.J + j;
+                // delta = dO . O of my row (both threads of the row compute it redundantly)
+                float delta = 0.f;
+                if (ok) {
+                    const uint4* o4 = reinterpret_cast<const uint4*>(p.O + tok * p.C + h * HD);
+                    const uint4* g4 = reinterpret_cast<const uint4*>(p.dO + tok * p.C + h * HD);
+#pragma unroll
+                    for (int i = 0; i < HD / 8; ++i) {
+                        const uint4 a = o4[i], g = g4[i];
+                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            delta = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), delta);
+                            delta = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(gw[e] & 0xffff0000u), delta);
+                        }
+                    }
+                }
+                mbar_wait(sd_full, ph);
+                tc_fence_after();
+                float mx = -INFINITY;
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
+                }
+                red[half * 128 + r_in_tile] = mx;
+                named_bar_sync(1, ABW_SIMT);
+                mx = fmaxf(red[r_in_tile], red[128 + r_in_tile]);
+                const float mxs = mx * sl2;
+                float sum = 0.f;
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i < p.F) sum += ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs));
+                }
+                red[256 + half * 128 + r_in_tile] = sum;
+                named_bar_sync(1, ABW_SIMT);
+                sum = red[256 + r_in_tile] + red[256 + 128 + r_in_tile];
+                const float lse2 = mxs + log2f(sum);                 // P = 2^(s*c*log2e - lse2)
+                if (ok && half == 0) {
+                    const size_t si = (static_cast<size_t>(prob)) * p.F + tq;
+                    p.lse2[si] = lse2;
+                    p.delta[si] = delta;
+                }
+                // dS = P (dP - delta) * scale  -> packed bf16 over S
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t s[32], g[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, s);
+                    tmem_ld32(tmem_dP + lane_off + ch * 32, g);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float d0 = 0.f, d1 = 0.f;
+                        if (ch * 32 + 2 * i < p.F) {
+                            const float pv = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -lse2));
+                            d0 = pv * (__uint_as_float(g[2 * i]) - delta) * p.scale;
+                        }
+                        if (ch * 32 + 2 * i + 1 < p.F) {
+                            const float pv = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -lse2));
+                            d1 = pv * (__uint_as_float(g[2 * i + 1]) - delta) * p.scale;
+                        }
+                        const __nv_bfloat162 t2 = __floats2bfloat162_rn(d0, d1);
+                        pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
+                    }
+                    tmem_st16(tmem_S + lane_off + ch * 32, pk);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(ds_full);
+                // dQ tile
+                mbar_wait(dq_full, ph);
+                tc_fence_after();
+                if (HD == 64 || half == 0) {
+                    const int c0 = (HD == 64) ? half * 32 : 0;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_dP + lane_off + c0, r);
+                    tmem_ld_wait();
+                    if (ok) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                            pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
+                        }
+                        uint4* d4 = reinterpret_cast<uint4*>(p.dqkv + tok * (3 * p.C) + h * HD + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(dq_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- dK / dV kernel
+template <int HD>
+__global__ void __launch_bounds__(ABW_THREADS, 1)
+attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box (HD, 1, 128, 1, 1)
+                   const __grid_constant__ CUtensorMap tmQKV_s,   // qkv 5-D, box (HD, 1, NK , 1, 1)
+                   const __grid_constant__ CUtensorMap tmDO_s,    // dO  5-D, box (HD, 1, NK , 1, 1)
+                   const AttnBwdParams p) {
+    using Cfg = AttnBwdCfg<HD>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* seq_full = bars + 0;    // Q and dO of the whole sequence
+    uint64_t* seq_empty = bars + 1;
+    uint64_t* t_full = bars + 2;      // K and V tile
+    uint64_t* t_empty = bars + 3;
+    uint64_t* sd_full = bars + 4;
+    uint64_t* ps_full = bars + 5;     // P^T and dS^T written (256 threads)
+    uint64_t* g_full = bars + 6;      // dV, dK accumulators ready
+    uint64_t* g_empty = bars + 7;     // 256 threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* v_lse = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);   // [256]
+    float* v_delta = v_lse + 256;                                   // [256]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_prob = p.B * p.J * p.H;
+    const int num_kt = (p.F + ATT_BM - 1) / ATT_BM;
+    const uint32_t seq_bytes = static_cast<uint32_t>(p.NK) * Cfg::SWZ;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV_t); tma_prefetch_desc(&tmQKV_s); tma_prefetch_desc(&tmDO_s);
+        mbar_init(seq_full, 1); mbar_init(seq_empty, 1);
+        mbar_init(t_full, 1);   mbar_init(t_empty, 1);
+        mbar_init(sd_full, 1);  mbar_init(ps_full, ABW_SIMT);
+        mbar_init(g_full, 1);   mbar_init(g_empty, ABW_SIMT);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;             // [0,256): S^T, then per 32-column chunk: 16 cols P^T | 16 cols dS^T
+    const uint32_t tmem_dP = tmem_base + 256;      // [256,512): dP^T, then dV at [256,256+HD), dK at [256+HD,256+2HD)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t t_it = 0;
+            int ip = 0;
+            for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++ip) {
+                const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
+                mbar_wait(seq_empty, (ip & 1) ^ 1);
+                mbar_arrive_expect_tx(seq_full, 2 * seq_bytes);
+                tma_load_5d(smem + Cfg::OFF_C, &tmQKV_s, seq_full, h * HD, j, 0, b, 0);     // Q (all queries)
+                tma_load_5d(smem + Cfg::OFF_D, &tmDO_s, seq_full, h * HD, j, 0, b, 0);      // dO (all queries)
+                for (int kt = 0; kt < num_kt; ++kt, ++t_it) {
+                    mbar_wait(t_empty, (t_it & 1) ^ 1);
+                    mbar_arrive_expect_tx(t_full, 2 * Cfg::TILE);
+                    tma_load_5d(smem + Cfg::OFF_A, &tmQKV_t, t_full, p.C + h * HD, j, kt * ATT_BM, b, 0);       // K tile
+                    tma_load_5d(smem + Cfg::OFF_B, &tmQKV_t, t_full, 2 * p.C + h * HD, j, kt * ATT_BM, b, 0);   // V tile
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, p.NK, 0, 0);
+        const uint32_t idesc_g = umma_idesc_bf16(ATT_BM, HD, 0, 1);
+        const uint32_t sK = smem_u32(smem + Cfg::OFF_A), sV = smem_u32(smem + Cfg::OFF_B);
+        const uint32_t sQ = smem_u32(smem + Cfg::OFF_C), sDO = smem_u32(smem + Cfg::OFF_D);
+        uint32_t t_it = 0;
+        int ip = 0;
+        for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++ip) {
+            mbar_wait(seq_full, ip & 1);
+            for (int kt = 0; kt < num_kt; ++kt, ++t_it) {
+                const uint32_t ph = t_it & 1;
+                mbar_wait(t_full, ph);
+                mbar_wait(g_empty, ph ^ 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t dk = umma_smem_desc(sK, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                    const uint64_t dv = umma_smem_desc(sV, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                    const uint64_t dq_ = umma_smem_desc(sQ, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                    const uint64_t ddo = umma_smem_desc(sDO, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) {
+                        const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
+                        umma_ss(tmem_S, dk + koff, dq_ + koff, idesc_s, ks != 0);       // S^T  = K Q^T
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) {
+                        const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
+                        umma_ss(tmem_dP, dv + koff, ddo + koff, idesc_s, ks != 0);      // dP^T = V dO^T
+                    }
+                    tc_commit(sd_full);
+                    tc_commit(t_empty);
+                }
+                __syncwarp();
+                mbar_wait(ps_full, ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const int nks = p.NK / 16;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t a_p = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);     // P^T  : first 16 columns of the chunk
+                        const uint32_t a_ds = a_p + 16;                                  // dS^T : last 16 columns
+                        const uint32_t roff = static_cast<uint32_t>(ks) * 16 * Cfg::SWZ;
+                        const uint64_t do_mn = umma_smem_desc(sDO + roff, 8 * Cfg::SWZ, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        const uint64_t q_mn = umma_smem_desc(sQ + roff, 8 * Cfg::SWZ, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        umma_ts(tmem_dP, a_p, do_mn, idesc_g, ks != 0);                  // dV = P^T  dO
+                        umma_ts(tmem_dP + HD, a_ds, q_mn, idesc_g, ks != 0);             // dK = dS^T Q
+                    }
+                    tc_commit(g_full);
+                    if (kt == num_kt - 1) tc_commit(seq_empty);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int r_in_tile = quad * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const int nch = (p.NK + 31) / 32;
+        const int ch_lo = half * 4 < nch ? half * 4 : nch;
+        const int ch_hi = (half * 4 + 4 < nch) ? half * 4 + 4 : nch;
+        const float sl2 = p.scale_log2e;
+        const int sid = threadIdx.x - 64;             // 0..255
+        uint32_t t_it = 0;
+        for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
+            const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
+            // per-query statistics of this sequence -> smem (queries >= F get p = 0)
+            named_bar_sync(1, ABW_SIMT);               // previous problem's readers are done
+            {
+                const size_t si = static_cast<size_t>(prob) * p.F;
+                v_lse[sid] = sid < p.F ? p.lse2[si + sid] : 3.0e38f;
+                v_delta[sid] = sid < p.F ? p.delta[si + sid] : 0.f;
+            }
+            named_bar_sync(1, ABW_SIMT);
+            for (int kt = 0; kt < num_kt; ++kt, ++t_it) {
+                const uint32_t ph = t_it & 1;
+                mbar_wait(sd_full, ph);
+                tc_fence_after();
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t s[32], g[32];
+                    tmem_ld32(tmem_S + lane_off + ch * 32, s);
+                    tmem_ld32(tmem_dP + lane_off + ch * 32, g);
+                    tmem_ld_wait();
+                    uint32_t pp[16], pd[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int q0 = ch * 32 + 2 * i;
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -v_lse[q0]));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -v_lse[q0 + 1]));
+                        const float d0 = p0 * (__uint_as_float(g[2 * i]) - v_delta[q0]) * p.scale;
+                        const float d1 = p1 * (__uint_as_float(g[2 * i + 1]) - v_delta[q0 + 1]) * p.scale;
+                        const __nv_bfloat162 a2 = __floats2bfloat162_rn(p0, p1);
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+                        pp[i] = *reinterpret_cast<const uint32_t*>(&a2);
+                        pd[i] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    tmem_st16(tmem_S + lane_off + ch * 32, pp);
+                    tmem_st16(tmem_S + lane_off + ch * 32 + 16, pd);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(ps_full);
+                mbar_wait(g_full, ph);
+                tc_fence_after();
+                const int tk = kt * ATT_BM + r_in_tile;
+                const bool ok = tk < p.F;
+                const size_t tok = (static_cast<size_t>(b) * p.F + (ok ? tk : 0)) * p.J + j;
+                // half 0 drains dV, half 1 drains dK (HD columns each)
+                {
+                    const uint32_t src = tmem_dP + half * HD;
+                    const int part = half == 0 ? 2 : 1;              // v part / k part of the qkv gradient
+#pragma unroll
+                    for (int c0 = 0; c0 < HD; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(src + lane_off + c0, r);
+                        tmem_ld_wait();
+                        if (ok) {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                                pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
+                            }
+                            uint4* d4 = reinterpret_cast<uint4*>(p.dqkv + tok * (3 * p.C) + part * p.C + h * HD + c0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(g_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace mb

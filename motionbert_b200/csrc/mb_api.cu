@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/motionbert_b200.h"
+#include "attn_bwd_tc.cuh"
 #include "attn_s_tc.cuh"
 #include "attn_t_tc.cuh"
 #include "attn_t_tc2.cuh"
@@ -155,6 +156,10 @@ static int device_init(int* dev_out, DevInfo* info_out) {
 #undef SET_GEMM2
         CUDA_TRY(set_smem(gemm2_kernel<3, EPI_BIAS_F32, true>, Gemm2Cfg<3, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_q_kernel<64>, AttnBwdCfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_q_kernel<32>, AttnBwdCfg<32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_kv_kernel<64>, AttnBwdCfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_kv_kernel<32>, AttnBwdCfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<3>, WgradCfg<3>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<1>, WgradCfg<1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t2_kernel<64, 3>, Attn2Cfg<64, 3>::SMEM_BYTES));
@@ -1284,5 +1289,130 @@ extern "C" int mb_test_dgrad(int math, int M, int N, int K, const float* G, cons
     else
         gemm2_kernel<1, EPI_BIAS_F32, true><<<grid2, G2_THREADS, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmX, tmA, p);
     LAUNCH_CHECK("gemm2_kernel<dgrad>");
+    return MB_OK;
+}
+
+
+// Attention-core backward launcher: all tensors bf16 (single plane), token-major.  For the spatial attention pass
+// (B*F, J, 1) as (B, F, J): one "sequence" per frame, J rows, token stride 1.
+static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H, float scale, const __nv_bfloat16* qkv,
+                           const __nv_bfloat16* O, const __nv_bfloat16* dO, float* lse2, float* delta,
+                           __nv_bfloat16* dqkv, cudaStream_t st) {
+    const int hd = C / H;
+    if (hd != 32 && hd != 64) return fail(MB_ERR_INVALID, "head_dim %d unsupported", hd);
+    if (F < 1 || F > ATT_MAXK) return fail(MB_ERR_INVALID, "sequence length %d unsupported", F);
+    const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
+    const uint64_t C3 = 3ull * C, Cc = static_cast<uint64_t>(C);
+    CUtensorMap q_t, q_s, do_t, do_s;
+    int rc;
+    {
+        const uint64_t dq[5] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 1};
+        const uint64_t sq[4] = {C3, C3 * J, C3 * J * F, C3 * J * F * B};
+        const uint64_t dd[5] = {Cc, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 1};
+        const uint64_t sd[4] = {Cc, Cc * J, Cc * J * F, Cc * J * F * B};
+        const uint32_t bt[5] = {static_cast<uint32_t>(hd), 1, ATT_BM, 1, 1};
+        const uint32_t bs[5] = {static_cast<uint32_t>(hd), 1, NK, 1, 1};
+        if ((rc = make_tmap(&q_t, qkv, 5, dq, sq, bt, hd * 2))) return rc;
+        if ((rc = make_tmap(&q_s, qkv, 5, dq, sq, bs, hd * 2))) return rc;
+        if ((rc = make_tmap(&do_t, dO, 5, dd, sd, bt, hd * 2))) return rc;
+        if ((rc = make_tmap(&do_s, dO, 5, dd, sd, bs, hd * 2))) return rc;
+    }
+    AttnBwdParams bp;
+    bp.B = B; bp.F = F; bp.J = J; bp.C = C; bp.H = H;
+    bp.NK = static_cast<int>(NK);
+    bp.scale = scale;
+    bp.scale_log2e = scale * 1.4426950408889634f;
+    bp.O = O; bp.dO = dO; bp.lse2 = lse2; bp.delta = delta; bp.dqkv = dqkv;
+    const int prob = B * J * H;
+    const int grid = prob < dev.sms ? prob : dev.sms;
+    if (hd == 64) {
+        attn_bwd_q_kernel<64><<<grid, ABW_THREADS, AttnBwdCfg<64>::SMEM_BYTES, st>>>(q_t, q_s, do_t, bp);
+        LAUNCH_CHECK("attn_bwd_q_kernel");
+        attn_bwd_kv_kernel<64><<<grid, ABW_THREADS, AttnBwdCfg<64>::SMEM_BYTES, st>>>(q_t, q_s, do_s, bp);
+        LAUNCH_CHECK("attn_bwd_kv_kernel");
+    } else {
+        attn_bwd_q_kernel<32><<<grid, ABW_THREADS, AttnBwdCfg<32>::SMEM_BYTES, st>>>(q_t, q_s, do_t, bp);
+        LAUNCH_CHECK("attn_bwd_q_kernel");
+        attn_bwd_kv_kernel<32><<<grid, ABW_THREADS, AttnBwdCfg<32>::SMEM_BYTES, st>>>(q_t, q_s, do_s, bp);
+        LAUNCH_CHECK("attn_bwd_kv_kernel");
+    }
+    return MB_OK;
+}
+
+extern "C" int mb_test_attention_backward_scratch_bytes(int B, int F, int J, int C, size_t* bytes) {
+    if (!bytes) return fail(MB_ERR_NULL, "NULL argument");
+    const size_t M = static_cast<size_t>(B) * F * J;
+    *bytes = 2 * align_up(M * 3 * C * 2, 1024)      /* qkv planes (forward hook layout) */
+             + 2 * align_up(M * C * 2, 1024)        /* O planes */
+             + align_up(M * C * 2, 1024)            /* dO */
+             + align_up(M * 3 * C * 2, 1024)        /* dqkv */
+             + 2 * align_up(M * (C / 32) * 4, 1024);   /* lse2, delta (>= B*J*H*F floats) */
+    return MB_OK;
+}
+
+// d(qkv) of softmax(q k^T d^-1/2) v given d(out): bf16 single-pass tensor-core backward.
+extern "C" int mb_test_attention_backward(int temporal, int B, int F, int J, int C, int H, const float* qkv,
+                                          const float* dO, float* dqkv, void* scratch, size_t scratch_bytes,
+                                          void* stream_) {
+    if (!qkv || !dO || !dqkv || !scratch) return fail(MB_ERR_NULL, "NULL argument");
+    size_t need;
+    mb_test_attention_backward_scratch_bytes(B, F, J, C, &need);
+    if (scratch_bytes < need) return fail(MB_ERR_WORKSPACE, "scratch too small");
+    if (H < 1 || C % H || (C / H != 32 && C / H != 64) || F < 1 || F > 256 || J < 1 || J > 32)
+        return fail(MB_ERR_INVALID, "bad attention shape");
+    MbDesc d;
+    memset(&d, 0, sizeof(d));
+    d.dim_in = 3; d.dim_out = 3; d.dim_feat = C; d.dim_rep = 256; d.depth = 1; d.num_heads = H; d.hidden = 256;
+    d.num_joints = J; d.maxlen = 256; d.eps = 1e-6f; d.math = MB_MATH_BF16;
+    MbEncoder e;
+    e.d = d;
+    int rc = device_init(&e.device, &e.dev);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const size_t M = static_cast<size_t>(B) * F * J;
+    const size_t qkv_plane = align_up(M * 3 * C * 2, 1024);
+    const size_t ao_plane = align_up(M * C * 2, 1024);
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    Plan P;
+    P.qkv = reinterpret_cast<__nv_bfloat16*>(b);
+    P.ao = reinterpret_cast<__nv_bfloat16*>(b + 2 * qkv_plane);
+    auto* dO_b = reinterpret_cast<__nv_bfloat16*>(b + 2 * qkv_plane + 2 * ao_plane);
+    auto* dqkv_b = reinterpret_cast<__nv_bfloat16*>(b + 2 * qkv_plane + 3 * ao_plane);
+    float* lse2 = reinterpret_cast<float*>(b + 3 * qkv_plane + 3 * ao_plane);
+    float* delta = lse2 + align_up(M * (C / 32) * 4, 1024) / 4;
+    {
+        const size_t n = M * 3 * C;
+        split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(qkv, P.qkv, nullptr, n);
+        const size_t n2 = M * C;
+        split_flat_kernel<<<static_cast<int>((n2 + 255) / 256), 256, 0, st>>>(dO, dO_b, nullptr, n2);
+        LAUNCH_CHECK("split_flat_kernel");
+        CUDA_TRY(cudaMemsetAsync(dqkv_b, 0, M * 3 * C * 2, st));
+    }
+    // forward output O (bf16) with the production forward kernels in single-pass mode
+    {
+        const int hd = C / H;
+        const uint64_t C3 = 3ull * C;
+        const uint64_t dims[5] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 2};
+        const uint64_t str[4] = {C3, C3 * J, C3 * J * F, qkv_plane / 2};
+        const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
+        const uint32_t box_q[5] = {static_cast<uint32_t>(hd), 1, ATT_BM, 1, 1};
+        const uint32_t box_kv[5] = {static_cast<uint32_t>(hd), 1, NK, 1, 1};
+        const uint32_t box_t32[5] = {static_cast<uint32_t>(hd), 1, ATS_SLAB, 1, 1};
+        if ((rc = make_tmap(&P.tm_q, P.qkv, 5, dims, str, box_q, hd * 2))) return rc;
+        if ((rc = make_tmap(&P.tm_kv, P.qkv, 5, dims, str, box_kv, hd * 2))) return rc;
+        if ((rc = make_tmap(&P.tm_qkv_t32, P.qkv, 5, dims, str, box_t32, hd * 2))) return rc;
+        const uint64_t dims4[4] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(B) * F, 2};
+        const uint64_t str4[3] = {C3, C3 * J, qkv_plane / 2};
+        const uint32_t box4[4] = {static_cast<uint32_t>(hd), ATS_SLAB, ATS_FRAMES, 1};
+        if ((rc = make_tmap(&P.tm_qkv_sp, P.qkv, 4, dims4, str4, box4, hd * 2))) return rc;
+        if ((rc = launch_attn(&e, 0u, temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st))) return rc;
+    }
+    const float scale = 1.0f / sqrtf(static_cast<float>(C / H));
+    if (temporal) rc = launch_attn_bwd(e.dev, B, F, J, C, H, scale, P.qkv, P.ao, dO_b, lse2, delta, dqkv_b, st);
+    else rc = launch_attn_bwd(e.dev, B * F, J, 1, C, H, scale, P.qkv, P.ao, dO_b, lse2, delta, dqkv_b, st);
+    if (rc) return rc;
+    const size_t n = M * 3 * C;
+    merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(dqkv_b, nullptr, dqkv, n);
+    LAUNCH_CHECK("merge_planes_kernel");
     return MB_OK;
 }

@@ -78,3 +78,18 @@ def test_dgrad(G_, W, math=0):
         _lib.check(lib.mb_test_dgrad(math, M, N, K, G_.data_ptr(), W.data_ptr(), dX.data_ptr(), sp, nb.value, st), "mb_test_dgrad")
         torch.cuda.synchronize(dev)
     return dX
+
+
+def test_attention_backward(temporal, qkv, dO, B, F, J, C, H):
+    lib = _lib.load()
+    dev = qkv.device
+    nb = ctypes.c_size_t()
+    _lib.check(lib.mb_test_attention_backward_scratch_bytes(B, F, J, C, ctypes.byref(nb)))
+    keep, sp = _scratch(nb.value, dev)
+    dqkv = torch.full((B * F * J, 3 * C), float("nan"), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mb_test_attention_backward(int(temporal), B, F, J, C, H, qkv.data_ptr(), dO.data_ptr(),
+                                                  dqkv.data_ptr(), sp, nb.value, st), "mb_test_attention_backward")
+        torch.cuda.synchronize(dev)
+    return dqkv

@@ -232,3 +232,39 @@ def test_data_parallel_wrapper_two_gpus():
     assert out.shape == single.shape
     assert rel_token_err(out, single)[1] < 2e-5 and np.array_equal(out, out2)
     assert O.mpjpe(out.astype(np.float64), g["out64"]) < MPJPE_UNITS
+
+
+def test_input_variants_noncontiguous_strided_and_double(cuda_device):
+    """Callers hand over slices / permuted views (train.py:160-172 builds batch_input on the fly); the module must
+    accept any strided float tensor and produce a fresh contiguous writable result."""
+    cfg, P, x, g = load_case("lite_b2_f27")
+    m = build_module(cfg, P, cuda_device)
+    ref, _ = _run(m, x, cuda_device)
+    xt = torch.from_numpy(x).to(cuda_device)
+    big = torch.zeros(2, 27, 17, 5, device=cuda_device)
+    big[..., 1:4] = xt
+    with torch.no_grad():
+        o1 = m(big[..., 1:4])                                   # non-contiguous last-dim slice
+        o2 = m(xt.permute(1, 0, 2, 3).contiguous().permute(1, 0, 2, 3))   # permuted strides
+        o3 = m(xt.double())                                     # wrong dtype is converted, not rejected
+    for o in (o1, o2, o3):
+        assert o.is_contiguous() and o.dtype == torch.float32
+        assert np.array_equal(o.cpu().numpy(), ref)
+    o1 += 1.0                                                   # callers edit the result in place (infer_wild.py:82-87)
+
+
+def test_two_streams_and_odd_batch_tail(cuda_device):
+    """Work is enqueued on the caller's current stream; odd batches leave a partial 256-row tile at the end."""
+    cfg, P, x, g = load_case("base_b3_f16")
+    m = build_module(cfg, P, cuda_device)
+    ref, _ = _run(m, x, cuda_device)
+    xt = torch.from_numpy(x).to(cuda_device)
+    s1 = torch.cuda.Stream(device=cuda_device)
+    torch.cuda.synchronize()
+    with torch.no_grad(), torch.cuda.stream(s1):
+        o = m(xt)
+    s1.synchronize()
+    assert np.array_equal(o.cpu().numpy(), ref)
+    with torch.no_grad():
+        o5 = m(torch.cat([xt, xt[:2]], 0))                      # B = 5
+    assert np.array_equal(o5[:3].cpu().numpy(), ref) and np.array_equal(o5[3:].cpu().numpy(), ref[:2])

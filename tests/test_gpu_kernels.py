@@ -154,3 +154,34 @@ def test_data_gradient_kernel(cuda_device, M, N, K, math_mode):
     assert torch.isfinite(dX).all()
     rel, mx = _rel(dX, exp)
     assert rel < (3e-5 if math_mode == 0 else 8e-3), f"rel {rel:.3e} max {mx:.3e}"
+
+
+def _attn_autograd(qkv, dO, B, F, J, C, H, temporal):
+    d = C // H
+    x = qkv.double().clone().requires_grad_(True)
+    q, k, v = x.reshape(B * F, J, 3, H, d).permute(2, 0, 3, 1, 4)
+    if temporal:
+        q, k, v = [t.reshape(B, F, H, J, d).permute(0, 2, 3, 1, 4) for t in (q, k, v)]
+        o = (((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(-1) @ v).permute(0, 3, 2, 1, 4).reshape(B * F * J, C)
+    else:
+        o = (((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B * F * J, C)
+    o.backward(dO.double())
+    return x.grad
+
+
+@pytest.mark.parametrize("temporal", [1, 0], ids=["temporal", "spatial"])
+@pytest.mark.parametrize("B,F,J,C,H", [(2, 27, 17, 512, 8), (1, 243, 17, 512, 8), (2, 130, 17, 256, 8), (3, 16, 17, 512, 8),
+                                       (1, 1, 17, 256, 8)])
+def test_attention_core_backward(cuda_device, B, F, J, C, H, temporal):
+    """Groundwork for the native backward: flash-style tcgen05 attention backward (bf16 single pass) vs autograd."""
+    g = torch.Generator().manual_seed(B * 31 + F)
+    qkv = torch.randn(B * F * J, 3 * C, generator=g).to(cuda_device)
+    dO = torch.randn(B * F * J, C, generator=g).to(cuda_device)
+    # the kernels see bf16-rounded inputs: compare against autograd on the same rounded values
+    qkv_r, dO_r = qkv.bfloat16().float(), dO.bfloat16().float()
+    got = G.test_attention_backward(temporal, qkv, dO, B, F, J, C, H)
+    exp = _attn_autograd(qkv_r, dO_r, B, F, J, C, H, bool(temporal))
+    assert torch.isfinite(got).all(), "non-finite / unwritten gradient"
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        rel, mx = _rel(got[:, sl], exp[:, sl])
+        assert rel < 2e-2, f"{name}: rel {rel:.3e} max {mx:.3e}"
