@@ -115,6 +115,28 @@ int mb_workspace_bytes_host(const MbEncoder* enc, int B, int F, int want_out, in
 int mb_forward_host(MbEncoder* enc, const void* packed, const float* x_host, float* out_host, float* rep_host,
                     void* workspace, size_t workspace_bytes, int B, int F, uint32_t flags, void* stream);
 
+/* ---- training: forward with saved activations + analytic backward (loss.backward() through DSTformer.forward,
+ * train.py:149-176 / lib/model/DSTformer.py:329-358; row a15 of SURVEY.md section 8) ------------------------------
+ * mb_forward_train : mb_forward (drop_path_scale = NULL) that additionally keeps every residual-stream tensor
+ *                    (fp32 + LayerNorm partial statistics, 9 per depth + 1) in the caller's `saved` region of
+ *                    mb_saved_bytes() bytes (1024-byte aligned).  `rep` is mandatory (the backward needs it).
+ * mb_backward      : gradients of all mb_param_count() parameters for given d_out (B,F,J,dim_out) and/or d_rep
+ *                    (B,F,J,dim_rep) (either may be NULL).  bf16 single-pass tensor-core arithmetic with fp32
+ *                    accumulation; qkv / hidden activations / attention probabilities are recomputed, not stored.
+ *     params : the same device pointers given to mb_pack_weights (fp32, state_dict order)
+ *     grads  : device pointers, same order and sizes, ZERO-FILLED by the caller (the kernels accumulate into them)
+ *     x, rep, saved : the input / output / saved region of the matching mb_forward_train call
+ *     workspace : mb_backward_workspace_bytes() bytes, 1024-byte aligned (independent of the forward workspace)
+ * No gradient w.r.t. x is produced (the pose input never requires grad in the reference's training scripts). */
+int mb_saved_bytes(const MbEncoder* enc, int B, int F, size_t* bytes);
+int mb_forward_train(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep, void* saved,
+                     size_t saved_bytes, void* workspace, size_t workspace_bytes, int B, int F, uint32_t flags,
+                     void* stream);
+int mb_backward_workspace_bytes(const MbEncoder* enc, int B, int F, size_t* bytes);
+int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x, const float* rep,
+                const void* saved, size_t saved_bytes, const float* d_out, const float* d_rep, float* const* grads,
+                void* workspace, size_t workspace_bytes, int B, int F, void* stream);
+
 /* Number of kernels one mb_forward call launches for this (B, F) (for bench.py's gpu_launches). */
 int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags);
 

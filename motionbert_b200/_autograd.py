@@ -1,10 +1,11 @@
 """autograd glue for the drop-in DSTformer.
 
-Forward = the sm_100a CUDA library (one `mb_forward` call).  Backward is
-NOT yet a hand-written kernel path: this round it recomputes the sublayer chain with torch CUDA ops
-under autograd and back-propagates through that (flash-style "recompute in backward", but with
-library kernels).  It exists so `train.py:205 loss.backward()` keeps working behind the unchanged
-boundary; it is not used by any forward / inference call and is documented as a gap in DESIGN.md.
+Forward = the sm_100a CUDA library (`mb_forward`, or `mb_forward_train` when a gradient is needed).
+Backward = `mb_backward`: hand-written tcgen05 data-/weight-gradient GEMMs,
+attention-core backward and CUDA-core LayerNorm / GELU / fusion / embed kernels, bf16 single-pass arithmetic.
+`recompute_forward` below is a differentiable torch-op restatement kept for (a) the gradient-parity tests and
+(b) the configurations the native backward does not cover (DropPath rate > 0, input gradients): there the
+backward recomputes the chain with torch CUDA ops under autograd.  No forward / inference call uses it.
 """
 from __future__ import annotations
 
@@ -85,18 +86,37 @@ def recompute_forward(mod, x, return_rep, dp_scale, P):
 
 
 class DSTformerFunction(torch.autograd.Function):
+    """forward = mb_forward_train (or mb_forward), backward = mb_backward (hand-written sm_100a kernels).
+    Configurations the native backward does not cover (DropPath rate > 0, gradient w.r.t. the input, missing
+    fusion head) fall back to back-propagating through `recompute_forward` with torch CUDA ops."""
+
     @staticmethod
     def forward(ctx, mod, x, return_rep, dp_scale, *params):
-        with torch.no_grad():
-            out, rep = mod._launch(x, not return_rep, return_rep, dp_scale)
         ctx.mod = mod
         ctx.return_rep = return_rep
         ctx.dp_scale = dp_scale
-        ctx.save_for_backward(x, *params)
+        ctx.native = mod._native_backward_ok(x, dp_scale)
+        with torch.no_grad():
+            if ctx.native:
+                out, rep, saved = mod._launch_train(x, not return_rep)
+                ctx.saved_region = saved
+                ctx.save_for_backward(x, rep)
+                ctx.pack_versions = tuple(p._version for p in params)
+            else:
+                out, rep = mod._launch(x, not return_rep, return_rep, dp_scale)
+                ctx.save_for_backward(x, *params)
         return rep if return_rep else out
 
     @staticmethod
     def backward(ctx, grad):
+        if ctx.native:
+            x, rep = ctx.saved_tensors
+            g = grad.contiguous().float()
+            grads = ctx.mod._launch_backward(x, rep, ctx.saved_region, None if ctx.return_rep else g,
+                                             g if ctx.return_rep else None)
+            ctx.saved_region = None
+            gp = [gr if ctx.needs_input_grad[4 + i] else None for i, gr in enumerate(grads)]
+            return (None, None, None, None, *gp)
         x, *params = ctx.saved_tensors
         with torch.enable_grad():
             xs = x.detach().requires_grad_(ctx.needs_input_grad[1])

@@ -24,7 +24,8 @@
 
 namespace mb {
 
-enum : int { EPI_LN_SPLIT = 0, EPI_LN_GELU_SPLIT = 1, EPI_RESID = 2, EPI_LN_TANH_F32 = 3, EPI_BIAS_F32 = 4 };
+enum : int { EPI_LN_SPLIT = 0, EPI_LN_GELU_SPLIT = 1, EPI_RESID = 2, EPI_LN_TANH_F32 = 3, EPI_BIAS_F32 = 4,
+              EPI_BIAS_SPLIT = 5 /* y = acc + b[n] -> bf16 planes; 2-CTA kernel only (backward recompute / dgrad) */ };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;

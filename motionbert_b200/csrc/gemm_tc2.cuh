@@ -59,7 +59,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     constexpr int G2_STAGES = Cfg::STAGES;
     constexpr bool kResid = (EPI == EPI_RESID);
     constexpr bool kF32Out = (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32);
-    constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT);
+    constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT);
     constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32);
 
     extern __shared__ uint8_t smem_raw[];
@@ -280,7 +280,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         st_sum += d;
                         st_sq = fmaf(d, d, st_sq);
                     }
-                } else if (EPI == EPI_BIAS_F32) {
+                } else if (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_SPLIT) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {

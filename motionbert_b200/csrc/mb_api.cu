@@ -18,6 +18,7 @@
 #include "attn_s_tc.cuh"
 #include "attn_t_tc.cuh"
 #include "attn_t_tc2.cuh"
+#include "backward_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "simt_kernels.cuh"
@@ -156,6 +157,8 @@ static int device_init(int* dev_out, DevInfo* info_out) {
 #undef SET_GEMM2
         CUDA_TRY(set_smem(gemm2_kernel<3, EPI_BIAS_F32, true>, Gemm2Cfg<3, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, false>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, true>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_q_kernel<64>, AttnBwdCfg<64>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_q_kernel<32>, AttnBwdCfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_kv_kernel<64>, AttnBwdCfg<64>::SMEM_BYTES));
@@ -196,6 +199,8 @@ struct LinearPack {
     size_t off_hi = 0, off_lo = 0, off_c = 0, off_s = 0;   // byte offsets into the packed buffer
     CUtensorMap tmap;                                   // 1-CTA kernel: box rows 256; valid for `packed_ptr`
     CUtensorMap tmap2;                                  // 2-CTA kernel: box rows 128 (half of the W tile per CTA)
+    CUtensorMap tmap_k1;                                // backward recompute: hi plane only, K-major, box (64, 128, 1)
+    CUtensorMap tmap_mn;                                // backward dgrad: hi plane as MN-major B, box (64, 64, 1)
 };
 
 struct ActBuf {
@@ -454,6 +459,10 @@ extern "C" int mb_pack_weights(MbEncoder* enc, const float* const* params, void*
         if (rc) return rc;
         const uint32_t box2[3] = {static_cast<uint32_t>(BK), 128u, static_cast<uint32_t>(passes == 3 ? 2 : 1)};
         if ((rc = make_tmap(&L.tmap2, base + L.off_hi, 3, dims, str, box2, BK * 2))) return rc;
+        const uint32_t box_k1[3] = {64u, 128u, 1u};
+        if ((rc = make_tmap(&L.tmap_k1, base + L.off_hi, 3, dims, str, box_k1, 128))) return rc;
+        const uint32_t box_mn[3] = {64u, 64u, 1u};
+        if ((rc = make_tmap(&L.tmap_mn, base + L.off_hi, 3, dims, str, box_mn, 128))) return rc;
     }
     const MbDesc& d = enc->d;
     auto copy = [&](size_t off, const float* src, size_t n) {
@@ -720,9 +729,27 @@ extern "C" int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint3
     return 1 + enc->d.depth * (2 * 10 + 1) + 1 + (want_out ? 1 : 0);
 }
 
-extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
-                          const float* drop_path_scale, void* workspace, size_t workspace_bytes, int B, int F,
-                          uint32_t flags, void* stream_) {
+// Saved-for-backward region of a training forward: one slot per residual-stream tensor (fp32 x + LN partial statistics).
+// Slots per depth i (base 9 i): 0 block input X0 | 1..4 blocks_st sublayer outputs | 5..8 blocks_ts sublayer outputs;
+// slot 9*depth = the fused output that feeds the final LayerNorm.
+struct SavedLayout {
+    size_t x_bytes, st_bytes, slot_bytes, total;
+    int slots;
+};
+static SavedLayout saved_layout(const MbDesc& d, int B, int F) {
+    SavedLayout s;
+    const size_t M = static_cast<size_t>(B) * F * d.num_joints;
+    s.x_bytes = align_up(M * d.dim_feat * 4, 1024);
+    s.st_bytes = align_up(M * (d.dim_feat / STATS_GROUP) * 3 * 4, 1024);
+    s.slot_bytes = s.x_bytes + s.st_bytes;
+    s.slots = 9 * d.depth + 1;
+    s.total = s.slot_bytes * s.slots;
+    return s;
+}
+
+static int forward_impl(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
+                        const float* drop_path_scale, void* workspace, size_t workspace_bytes, int B, int F,
+                        uint32_t flags, void* stream_, uint8_t* saved) {
     if (!enc || !packed || !x || !workspace) return fail(MB_ERR_NULL, "NULL argument");
     if (!out && !rep) return fail(MB_ERR_NULL, "both out and rep are NULL");
     const MbDesc& d = enc->d;
@@ -765,13 +792,27 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
     const int passes = passes_of(d);
     int rc;
 
-    // embed (DSTformer.py:330-337) -> act[0]
+    // Residual-stream buffers.  Inference: four rotating buffers.  Training (saved != null): the bf16 operand planes
+    // still rotate, but every fp32 tensor + its LN statistics goes to its own slot of the saved region.
+    const SavedLayout sl = saved_layout(d, B, F);
+    auto slot_buf = [&](int plane_idx, int slot, ActBuf* dst) -> int {
+        *dst = P.act[plane_idx];
+        if (!saved) return MB_OK;
+        uint8_t* sp = saved + static_cast<size_t>(slot) * sl.slot_bytes;
+        dst->x = reinterpret_cast<float*>(sp);
+        dst->stats = reinterpret_cast<float*>(sp + sl.x_bytes);
+        return make_f32_tile_tmap(&dst->tm_x, dst->x, M_, C);
+    };
+    ActBuf X0, S1, S2, T1, S1b, S2b, T1b, S1c, S1d;
+    if ((rc = slot_buf(0, 0, &X0))) return rc;
+
+    // embed (DSTformer.py:330-337) -> X0
     prof_mark(enc, st, PC_EMBED);
     ROWK(embed_kernel,
         x, d.dim_in, reinterpret_cast<const float*>(pk + enc->off_small[0]),
         reinterpret_cast<const float*>(pk + enc->off_small[1]), reinterpret_cast<const float*>(pk + enc->off_small[2]),
-        reinterpret_cast<const float*>(pk + enc->off_small[3]), M, F, J, C, P.act[0].x, P.act[0].hi,
-        passes == 3 ? P.act[0].lo : nullptr, P.act[0].stats);
+        reinterpret_cast<const float*>(pk + enc->off_small[3]), M, F, J, C, X0.x, X0.hi,
+        passes == 3 ? X0.lo : nullptr, X0.stats);
     LAUNCH_CHECK("embed_kernel");
 
     GemmParams base;
@@ -838,31 +879,36 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
         return launch_gemm<EPI_RESID>(enc, flags, P.tm_hid, P.hid, P.hid + qkv_plane_el, L[temporal ? L_FC2_T : L_FC2_S], pk, q, em2, st);
     };
 
-    const ActBuf& X0 = P.act[0];
-    const ActBuf& S1 = P.act[1];
-    const ActBuf& S2 = P.act[2];
-    const ActBuf& T1 = P.act[3];
     for (int i = 0; i < d.depth; ++i) {
         const LinearPack* Lst = &enc->lin[(0 * d.depth + i) * L_PER_BLOCK];
         const LinearPack* Lts = &enc->lin[(1 * d.depth + i) * L_PER_BLOCK];
         sub = i * 8;
+        const int sb = 9 * i;
+        // plane buffers: st chain 1,2,1,2 ; ts chain 3,1,3,1 (as in inference); slots: see SavedLayout
+        if ((rc = slot_buf(1, sb + 1, &S1)) || (rc = slot_buf(2, sb + 2, &S2)) || (rc = slot_buf(1, sb + 3, &S1b)) ||
+            (rc = slot_buf(2, sb + 4, &S2b)) || (rc = slot_buf(3, sb + 5, &T1)) || (rc = slot_buf(1, sb + 6, &S1c)) ||
+            (rc = slot_buf(3, sb + 7, &T1b)) || (rc = slot_buf(1, sb + 8, &S1d)))
+            return rc;
         // blocks_st[i] : 'stage_st'  S-attn, S-mlp, T-attn, T-mlp   (DSTformer.py:240-244)  X0 -> S1 -> S2 -> S1 -> S2
         if ((rc = attn_sublayer(Lst, false, X0, S1))) return rc;
         if ((rc = mlp_sublayer(Lst, false, S1, S2, false))) return rc;
-        if ((rc = attn_sublayer(Lst, true, S2, S1))) return rc;
-        if ((rc = mlp_sublayer(Lst, true, S1, S2, true))) return rc;
+        if ((rc = attn_sublayer(Lst, true, S2, S1b))) return rc;
+        if ((rc = mlp_sublayer(Lst, true, S1b, S2b, true))) return rc;
         // blocks_ts[i] : 'stage_ts'  T-attn, T-mlp, S-attn, S-mlp   (DSTformer.py:245-249)  X0 -> T1 -> S1 -> T1 -> S1
         if ((rc = attn_sublayer(Lts, true, X0, T1))) return rc;
-        if ((rc = mlp_sublayer(Lts, true, T1, S1, false))) return rc;
-        if ((rc = attn_sublayer(Lts, false, S1, T1))) return rc;
-        if ((rc = mlp_sublayer(Lts, false, T1, S1, true))) return rc;
-        // fusion (DSTformer.py:343-349): (x_st = S2, x_ts = S1) -> X0
+        if ((rc = mlp_sublayer(Lts, true, T1, S1c, false))) return rc;
+        if ((rc = attn_sublayer(Lts, false, S1c, T1b))) return rc;
+        if ((rc = mlp_sublayer(Lts, false, T1b, S1d, true))) return rc;
+        // fusion (DSTformer.py:343-349): (x_st = S2b, x_ts = S1d) -> X0 of the next depth
+        ActBuf Xn;
+        if ((rc = slot_buf(0, sb + 9, &Xn))) return rc;
         prof_mark(enc, st, PC_FUSE);
         ROWK(fuse_kernel,
-            S2.x, S1.x, reinterpret_cast<const float*>(pk + enc->off_small[6]) + static_cast<size_t>(i) * 4 * C,
-            reinterpret_cast<const float*>(pk + enc->off_small[7]) + static_cast<size_t>(i) * 2, M, C, X0.x, X0.hi,
-            passes == 3 ? X0.lo : nullptr, X0.stats);
+            S2b.x, S1d.x, reinterpret_cast<const float*>(pk + enc->off_small[6]) + static_cast<size_t>(i) * 4 * C,
+            reinterpret_cast<const float*>(pk + enc->off_small[7]) + static_cast<size_t>(i) * 2, M, C, Xn.x, Xn.hi,
+            passes == 3 ? Xn.lo : nullptr, Xn.stats);
         LAUNCH_CHECK("fuse_kernel");
+        X0 = Xn;
     }
     // tail (DSTformer.py:352-357): rep = tanh(Linear(LN(x))), out = Linear(rep)
     float* rep_buf = rep ? rep : P.rep_ws;
@@ -885,6 +931,12 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
     }
     prof_mark(enc, st, -1);
     return MB_OK;
+}
+
+extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
+                          const float* drop_path_scale, void* workspace, size_t workspace_bytes, int B, int F,
+                          uint32_t flags, void* stream_) {
+    return forward_impl(enc, packed, x, out, rep, drop_path_scale, workspace, workspace_bytes, B, F, flags, stream_, nullptr);
 }
 
 extern "C" int mb_profile_enable(MbEncoder* enc, int on) {
@@ -1414,5 +1466,357 @@ extern "C" int mb_test_attention_backward(int temporal, int B, int F, int J, int
     const size_t n = M * 3 * C;
     merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(dqkv_b, nullptr, dqkv, n);
     LAUNCH_CHECK("merge_planes_kernel");
+    return MB_OK;
+}
+
+
+// ==================================================================================== training path (row a15)
+// mb_forward_train = the inference forward, with every residual-stream tensor kept in the caller's `saved` region.
+// mb_backward      = analytic backward of DSTformer.forward (DSTformer.py:329-358) in bf16 single-pass arithmetic
+//                    (fp32 accumulation, fp32 residual-stream gradients): per residual sublayer it recomputes the
+//                    branch from the saved input (flash-style: qkv / hidden / attention probabilities are never
+//                    stored), then runs data-gradient GEMMs (weights consumed MN-major, no transposed copies),
+//                    weight-gradient GEMMs (split-K over the tokens, fp32 atomics) and the attention-core backward.
+extern "C" int mb_saved_bytes(const MbEncoder* enc, int B, int F, size_t* bytes) {
+    if (!enc || !bytes) return fail(MB_ERR_NULL, "NULL argument");
+    if (B < 1 || F < 1 || F > enc->d.maxlen) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d (maxlen %d)", B, F, enc->d.maxlen);
+    *bytes = saved_layout(enc->d, B, F).total;
+    return MB_OK;
+}
+
+extern "C" int mb_forward_train(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
+                                void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, int B, int F,
+                                uint32_t flags, void* stream_) {
+    if (!enc || !saved || !rep) return fail(MB_ERR_NULL, "NULL argument (training forward needs saved and rep)");
+    if (reinterpret_cast<uintptr_t>(saved) & 1023) return fail(MB_ERR_ALIGN, "saved region must be 1024-byte aligned");
+    if (B < 1 || F < 1 || F > enc->d.maxlen) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d", B, F);
+    const SavedLayout sl = saved_layout(enc->d, B, F);
+    if (saved_bytes < sl.total) return fail(MB_ERR_WORKSPACE, "saved region %zu < required %zu", saved_bytes, sl.total);
+    return forward_impl(enc, packed, x, out, rep, nullptr, workspace, workspace_bytes, B, F, flags, stream_,
+                        static_cast<uint8_t*>(saved));
+}
+
+struct BwdLayout {
+    size_t xhat, wide[3], o, d_o, g_x[3], g_p[3], dxhat, lse2, delta, dwp, dc, zero, drep, dz, total;
+    size_t wide_cols, max_n;
+};
+static BwdLayout bwd_layout(const MbDesc& d, int B, int F) {
+    BwdLayout w;
+    const size_t M = static_cast<size_t>(B) * F * d.num_joints;
+    const size_t C = d.dim_feat;
+    w.wide_cols = static_cast<size_t>(3 * d.dim_feat > d.hidden ? 3 * d.dim_feat : d.hidden);
+    w.max_n = w.wide_cols > static_cast<size_t>(d.dim_rep) ? w.wide_cols : static_cast<size_t>(d.dim_rep);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    w.xhat = take(M * C * 2);
+    for (int i = 0; i < 3; ++i) w.wide[i] = take(M * w.wide_cols * 2);
+    w.o = take(M * C * 2);
+    w.d_o = take(M * C * 2);
+    for (int i = 0; i < 3; ++i) { w.g_x[i] = take(M * C * 4); w.g_p[i] = take(M * C * 2); }
+    w.dxhat = take(M * C * 4);
+    w.lse2 = take(M * d.num_heads * 4);
+    w.delta = take(M * d.num_heads * 4);
+    w.dwp = take(w.max_n * C * 4);
+    w.dc = take(w.max_n * 4);
+    w.zero = take((w.max_n > C ? w.max_n : C) * 4);
+    w.drep = take(M * d.dim_rep * 4);
+    w.dz = take(M * d.dim_rep * 2);
+    w.total = off;
+    return w;
+}
+
+extern "C" int mb_backward_workspace_bytes(const MbEncoder* enc, int B, int F, size_t* bytes) {
+    if (!enc || !bytes) return fail(MB_ERR_NULL, "NULL argument");
+    if (B < 1 || F < 1 || F > enc->d.maxlen) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d (maxlen %d)", B, F, enc->d.maxlen);
+    *bytes = bwd_layout(enc->d, B, F).total;
+    return MB_OK;
+}
+
+// bf16 single-plane [rows, cols] matrix as the A operand of the 1-pass 2-CTA GEMM
+static int make_plane_a_tmap(CUtensorMap* out, const __nv_bfloat16* base, uint64_t rows, uint64_t cols) {
+    const uint64_t dims[3] = {cols, rows, 1};
+    const uint64_t str[2] = {cols, rows * cols};
+    const uint32_t box[3] = {64u, 128u, 1u};
+    return make_tmap(out, base, 3, dims, str, box, 128);
+}
+
+// out[M, ncols] = A[M, kc] (bf16 plane) x W (K-major [ncols, kc] or, BMN, MN-major [kc, ncols]) + bias[ncols]
+template <int EPI, bool BMN>
+static int bwd_gemm(const DevInfo& dev, const __nv_bfloat16* A, int M, int kc, int ncols, const CUtensorMap& tmB,
+                    const float* bias, float* out_f32, __nv_bfloat16* out_plane, cudaStream_t st) {
+    if (kc % 64 || ncols % 256) return fail(MB_ERR_INVALID, "internal: backward GEMM shape kc=%d ncols=%d", kc, ncols);
+    CUtensorMap tmA, tmO;
+    int rc;
+    if ((rc = make_plane_a_tmap(&tmA, A, M, kc))) return rc;
+    if (EPI == EPI_BIAS_F32) rc = make_f32_tile_tmap(&tmO, out_f32, M, ncols);
+    else rc = make_split_store_tmap(&tmO, out_plane, M, ncols, static_cast<uint64_t>(M) * ncols, 1);
+    if (rc) return rc;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = ncols; p.K = kc;
+    p.vec0 = bias;
+    p.out_f32 = out_f32;
+    p.out_hi = out_plane;
+    p.J = 1;
+    const int tiles = ((M + 255) / 256) * (ncols / 256);
+    const int grid = 2 * (tiles < dev.sms / 2 ? tiles : dev.sms / 2);
+    gemm2_kernel<1, EPI, BMN><<<grid, G2_THREADS, Gemm2Cfg<1, EPI>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmO, tmO, p);
+    LAUNCH_CHECK("gemm2_kernel<backward>");
+    return MB_OK;
+}
+
+// dW[N, K] += G[M, N]^T X[M, K]   (bf16 planes, fp32 atomics into a zero-initialised / accumulating buffer)
+static int bwd_wgrad(const DevInfo& dev, const __nv_bfloat16* G, int N, const __nv_bfloat16* X, int K, int M, float* dW,
+                     cudaStream_t st) {
+    if (N % 128 || K % 256) return fail(MB_ERR_INVALID, "internal: wgrad shape N=%d K=%d", N, K);
+    CUtensorMap tmG, tmX;
+    int rc;
+    const uint32_t box[3] = {64, WG_BT, 1};
+    const uint64_t dG[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 1};
+    const uint64_t sG[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M) * N};
+    if ((rc = make_tmap(&tmG, G, 3, dG, sG, box, 128))) return rc;
+    const uint64_t dX[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), 1};
+    const uint64_t sX[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M) * K};
+    if ((rc = make_tmap(&tmX, X, 3, dX, sX, box, 128))) return rc;
+    WgradParams wp;
+    wp.M = M; wp.N = N; wp.K = K; wp.dW = dW;
+    const int tiles = (N / 128) * (K / 256);
+    int splits = dev.sms / tiles;
+    if (splits < 1) splits = 1;
+    const int max_splits = (M + WG_BT - 1) / WG_BT;
+    if (splits > max_splits) splits = max_splits;
+    wp.tokens_per_split = static_cast<int>(align_up((static_cast<size_t>(M) + splits - 1) / splits, WG_BT));
+    wgrad_kernel<1><<<tiles * splits, WG_THREADS, WgradCfg<1>::SMEM_BYTES, st>>>(tmG, tmX, wp);
+    LAUNCH_CHECK("wgrad_kernel");
+    return MB_OK;
+}
+
+extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x_in,
+                           const float* rep, const void* saved_, size_t saved_bytes, const float* d_out,
+                           const float* d_rep, float* const* grads, void* workspace, size_t workspace_bytes, int B,
+                           int F, void* stream_) {
+    if (!enc || !packed || !params || !x_in || !rep || !saved_ || !grads || !workspace)
+        return fail(MB_ERR_NULL, "NULL argument");
+    if (!d_out && !d_rep) return fail(MB_ERR_NULL, "both d_out and d_rep are NULL");
+    const MbDesc& d = enc->d;
+    if (B < 1 || F < 1 || F > d.maxlen) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d", B, F);
+    if (d.dim_out > 8) return fail(MB_ERR_INVALID, "native backward supports dim_out <= 8 (got %d)", d.dim_out);
+    const size_t M_ = static_cast<size_t>(B) * F * d.num_joints;
+    if (M_ > 0x7fffffffULL / 4) return fail(MB_ERR_INVALID, "B*F*J=%zu too large", M_);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(saved_) & 1023) ||
+        (reinterpret_cast<uintptr_t>(rep) & 15))
+        return fail(MB_ERR_ALIGN, "misaligned buffer (workspace / saved: 1024 B, rep: 16 B)");
+    const SavedLayout sl = saved_layout(d, B, F);
+    if (saved_bytes < sl.total) return fail(MB_ERR_WORKSPACE, "saved region %zu < required %zu", saved_bytes, sl.total);
+    const BwdLayout wl = bwd_layout(d, B, F);
+    if (workspace_bytes < wl.total) return fail(MB_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, wl.total);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != enc->device) return fail(MB_ERR_INVALID, "handle was created on device %d, current device is %d", enc->device, dev);
+    {
+        std::lock_guard<std::mutex> lk(enc->mu);
+        if (packed != enc->packed_ptr) return fail(MB_ERR_INVALID, "packed buffer differs from the one given to mb_pack_weights");
+    }
+    const int np = static_cast<int>(enc->names.size());
+    for (int i = 0; i < np; ++i)
+        if (!params[i] || !grads[i]) return fail(MB_ERR_NULL, "params[%d] / grads[%d] (%s) is NULL", i, i, enc->names[i].c_str());
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const DevInfo& di = enc->dev;
+    const uint8_t* pk = static_cast<const uint8_t*>(packed);
+    const uint8_t* saved = static_cast<const uint8_t*>(saved_);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const int M = static_cast<int>(M_);
+    const int C = d.dim_feat, J = d.num_joints, H = d.num_heads, hid = d.hidden, R = d.dim_rep, hd = C / H;
+    const int rows_grid = (M + 7) / 8;
+    const float scale = d.qk_scale > 0.f ? d.qk_scale : 1.0f / sqrtf(static_cast<float>(hd));
+    int rc;
+
+    auto* xhat = reinterpret_cast<__nv_bfloat16*>(ws + wl.xhat);
+    __nv_bfloat16* wide[3];
+    for (int i = 0; i < 3; ++i) wide[i] = reinterpret_cast<__nv_bfloat16*>(ws + wl.wide[i]);
+    auto* o_pl = reinterpret_cast<__nv_bfloat16*>(ws + wl.o);
+    auto* do_pl = reinterpret_cast<__nv_bfloat16*>(ws + wl.d_o);
+    float* g_x[3];
+    __nv_bfloat16* g_p[3];
+    for (int i = 0; i < 3; ++i) {
+        g_x[i] = reinterpret_cast<float*>(ws + wl.g_x[i]);
+        g_p[i] = reinterpret_cast<__nv_bfloat16*>(ws + wl.g_p[i]);
+    }
+    float* dxhat = reinterpret_cast<float*>(ws + wl.dxhat);
+    float* lse2 = reinterpret_cast<float*>(ws + wl.lse2);
+    float* delta = reinterpret_cast<float*>(ws + wl.delta);
+    float* dwp = reinterpret_cast<float*>(ws + wl.dwp);
+    float* dc = reinterpret_cast<float*>(ws + wl.dc);
+    float* zero = reinterpret_cast<float*>(ws + wl.zero);
+    float* drep = reinterpret_cast<float*>(ws + wl.drep);
+    auto* dz = reinterpret_cast<__nv_bfloat16*>(ws + wl.dz);
+    CUDA_TRY(cudaMemsetAsync(zero, 0, (wl.max_n > static_cast<size_t>(C) ? wl.max_n : static_cast<size_t>(C)) * 4, st));
+
+    auto slot_x = [&](int slot) { return reinterpret_cast<const float*>(saved + static_cast<size_t>(slot) * sl.slot_bytes); };
+    auto slot_st = [&](int slot) { return reinterpret_cast<const float*>(saved + static_cast<size_t>(slot) * sl.slot_bytes + sl.x_bytes); };
+    auto P = [&](const LinearPack& L, int which) -> const float* {      // original fp32 parameter of a linear
+        return params[which == 0 ? L.p_w : which == 1 ? L.p_b : which == 2 ? L.p_g : L.p_beta];
+    };
+    auto G = [&](const LinearPack& L, int which) -> float* {
+        return grads[which == 0 ? L.p_w : which == 1 ? L.p_b : which == 2 ? L.p_g : L.p_beta];
+    };
+    auto colsum_f32 = [&](const float* g, int n, float* out) -> int {
+        colsum_kernel<float><<<dim3((n + 255) / 256, (M + 127) / 128), 256, 0, st>>>(g, M, n, out);
+        LAUNCH_CHECK("colsum_kernel<float>");
+        return MB_OK;
+    };
+    auto colsum_bf16 = [&](const __nv_bfloat16* g, int n, float* out) -> int {
+        colsum_kernel<__nv_bfloat16><<<dim3((n + 255) / 256, (M + 127) / 128), 256, 0, st>>>(g, M, n, out);
+        LAUNCH_CHECK("colsum_kernel<bf16>");
+        return MB_OK;
+    };
+    // LayerNorm-folded linear y = xhat W'^T + c: given dY (bf16 plane [M, N]) and xhat:
+    //   parameter gradients (W, b, gamma, beta) and dxhat = dY W'  (fp32)
+    auto ln_linear_backward = [&](const LinearPack& L, const __nv_bfloat16* dY) -> int {
+        int r;
+        CUDA_TRY(cudaMemsetAsync(dwp, 0, static_cast<size_t>(L.N) * L.K * 4, st));
+        CUDA_TRY(cudaMemsetAsync(dc, 0, static_cast<size_t>(L.N) * 4, st));
+        if ((r = bwd_wgrad(di, dY, L.N, xhat, L.K, M, dwp, st))) return r;
+        if ((r = colsum_bf16(dY, L.N, dc))) return r;
+        ln_linear_grad_kernel<<<dim3((L.K + 255) / 256, (L.N + 63) / 64), 256, 0, st>>>(
+            dwp, dc, P(L, 0), P(L, 2), P(L, 3), L.N, L.K, G(L, 0), G(L, 1), G(L, 2), G(L, 3));
+        LAUNCH_CHECK("ln_linear_grad_kernel");
+        return bwd_gemm<EPI_BIAS_F32, true>(di, dY, M, L.N, L.K, L.tmap_mn, zero, dxhat, nullptr, st);
+    };
+    auto make_xhat = [&](int slot) -> int {
+        ROWK(ln_xhat_kernel, slot_x(slot), slot_st(slot), M, C, d.eps, xhat);
+        LAUNCH_CHECK("ln_xhat_kernel");
+        return MB_OK;
+    };
+    // dx = dy + [extra] + LN-backward(dxhat) for the sublayer whose input lives in `slot`
+    auto finalize = [&](int slot, int g_in, const float* extra, int g_out) -> int {
+        ROWK(ln_bwd_finalize_kernel, dxhat, slot_x(slot), slot_st(slot), g_in >= 0 ? g_x[g_in] : nullptr, extra, M, C, d.eps,
+             g_x[g_out], g_p[g_out]);
+        LAUNCH_CHECK("ln_bwd_finalize_kernel");
+        return MB_OK;
+    };
+    const size_t n8_hid = M_ * hid / 8;
+    // MLP sublayer  y = x + fc2(gelu(fc1(LN(x))))   (DSTformer.py:242,244,247,249), x in `slot`, dy in g[g_in] -> dx in g[g_out]
+    auto mlp_backward = [&](const LinearPack* L, bool temporal, int slot, int g_in, const float* extra, int g_out) -> int {
+        const LinearPack& L1 = L[temporal ? L_FC1_T : L_FC1_S];
+        const LinearPack& L2 = L[temporal ? L_FC2_T : L_FC2_S];
+        int r;
+        if ((r = make_xhat(slot))) return r;
+        // recompute h_pre = xhat W1'^T + c1 and h = gelu(h_pre)
+        if ((r = bwd_gemm<EPI_BIAS_SPLIT, false>(di, xhat, M, C, hid, L1.tmap_k1, reinterpret_cast<const float*>(pk + L1.off_c),
+                                                 nullptr, wide[0], st))) return r;
+        gelu_plane_kernel<<<static_cast<unsigned>((n8_hid + 255) / 256), 256, 0, st>>>(wide[0], n8_hid, wide[1]);
+        LAUNCH_CHECK("gelu_plane_kernel");
+        // fc2: dW2 += dy^T h ; db2 += sum dy ; dh = dy W2
+        if ((r = bwd_wgrad(di, g_p[g_in], C, wide[1], hid, M, G(L2, 0), st))) return r;
+        if ((r = colsum_f32(g_x[g_in], C, G(L2, 1)))) return r;
+        if ((r = bwd_gemm<EPI_BIAS_SPLIT, true>(di, g_p[g_in], M, C, hid, L2.tmap_mn, zero, nullptr, wide[2], st))) return r;
+        // dh_pre = dh * gelu'(h_pre)   (in place over dh)
+        gelu_bwd_plane_kernel<<<static_cast<unsigned>((n8_hid + 255) / 256), 256, 0, st>>>(wide[2], wide[0], n8_hid, wide[2]);
+        LAUNCH_CHECK("gelu_bwd_plane_kernel");
+        if ((r = ln_linear_backward(L1, wide[2]))) return r;
+        return finalize(slot, g_in, extra, g_out);
+    };
+
+    // 1-pass tensor maps over the recomputed qkv plane for the forward attention kernels
+    Plan AP;
+    AP.qkv = wide[0];
+    AP.ao = o_pl;
+    {
+        const uint64_t C3 = 3ull * C;
+        const uint64_t plane = M_ * C3;
+        const uint64_t dims[5] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 1};
+        const uint64_t str[4] = {C3, C3 * J, C3 * J * F, plane};
+        const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
+        const uint32_t box_q[5] = {static_cast<uint32_t>(hd), 1, ATT_BM, 1, 1};
+        const uint32_t box_kv[5] = {static_cast<uint32_t>(hd), 1, NK, 1, 1};
+        const uint32_t box_t32[5] = {static_cast<uint32_t>(hd), 1, ATS_SLAB, 1, 1};
+        if ((rc = make_tmap(&AP.tm_q, AP.qkv, 5, dims, str, box_q, hd * 2))) return rc;
+        if ((rc = make_tmap(&AP.tm_kv, AP.qkv, 5, dims, str, box_kv, hd * 2))) return rc;
+        if ((rc = make_tmap(&AP.tm_qkv_t32, AP.qkv, 5, dims, str, box_t32, hd * 2))) return rc;
+        const uint64_t dims4[4] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(B) * F, 1};
+        const uint64_t str4[3] = {C3, C3 * J, plane};
+        const uint32_t box4[4] = {static_cast<uint32_t>(hd), ATS_SLAB, ATS_FRAMES, 1};
+        if ((rc = make_tmap(&AP.tm_qkv_sp, AP.qkv, 4, dims4, str4, box4, hd * 2))) return rc;
+    }
+    MbEncoder one_pass;                    // launch_attn only reads d / dev / profiling from the handle
+    one_pass.d = d;
+    one_pass.d.math = MB_MATH_BF16;
+    one_pass.device = enc->device;
+    one_pass.dev = enc->dev;
+    // attention sublayer  y = x + proj(attn(qkv(LN(x))))   (DSTformer.py:241,243,246,248)
+    auto attn_backward = [&](const LinearPack* L, bool temporal, int slot, int g_in, const float* extra, int g_out) -> int {
+        const LinearPack& Lq = L[temporal ? L_QKV_T : L_QKV_S];
+        const LinearPack& Lp = L[temporal ? L_PROJ_T : L_PROJ_S];
+        int r;
+        if ((r = make_xhat(slot))) return r;
+        // recompute qkv = xhat Wq'^T + cq and the attention output O
+        if ((r = bwd_gemm<EPI_BIAS_SPLIT, false>(di, xhat, M, C, 3 * C, Lq.tmap_k1, reinterpret_cast<const float*>(pk + Lq.off_c),
+                                                 nullptr, wide[0], st))) return r;
+        if ((r = launch_attn(&one_pass, 0u, temporal, AP, B, F, M_ * 3 * C, M_ * C, st))) return r;
+        // proj: dWp += dy^T O ; dbp += sum dy ; dO = dy Wp
+        if ((r = bwd_wgrad(di, g_p[g_in], C, o_pl, C, M, G(Lp, 0), st))) return r;
+        if ((r = colsum_f32(g_x[g_in], C, G(Lp, 1)))) return r;
+        if ((r = bwd_gemm<EPI_BIAS_SPLIT, true>(di, g_p[g_in], M, C, C, Lp.tmap_mn, zero, nullptr, do_pl, st))) return r;
+        // attention core: (qkv, O, dO) -> dqkv
+        if (temporal) r = launch_attn_bwd(di, B, F, J, C, H, scale, wide[0], o_pl, do_pl, lse2, delta, wide[1], st);
+        else r = launch_attn_bwd(di, B * F, J, 1, C, H, scale, wide[0], o_pl, do_pl, lse2, delta, wide[1], st);
+        if (r) return r;
+        if ((r = ln_linear_backward(Lq, wide[1]))) return r;
+        return finalize(slot, g_in, extra, g_out);
+    };
+
+    // ---- tail (DSTformer.py:352-357): rep = tanh(pre_logits(LN(x))), out = head(rep)
+    const int i_hw = enc->index.at("head.weight"), i_hb = enc->index.at("head.bias");
+    head_bwd_kernel<<<(M + 63) / 64, 256, 0, st>>>(d_out, rep, params[i_hw], M, R, d.dim_out, d_rep, drep, grads[i_hw],
+                                                   grads[i_hb]);
+    LAUNCH_CHECK("head_bwd_kernel");
+    {
+        const size_t n2 = M_ * R / 2;
+        to_plane_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(drep, rep, n2, dz);
+        LAUNCH_CHECK("to_plane_kernel");
+    }
+    const int final_slot = 9 * d.depth;
+    if ((rc = make_xhat(final_slot))) return rc;
+    if ((rc = ln_linear_backward(enc->lin.back(), dz))) return rc;
+    int cur = 0;                                            // g[cur] = gradient w.r.t. the fused output of depth i
+    if ((rc = finalize(final_slot, -1, nullptr, cur))) return rc;
+
+    for (int i = d.depth - 1; i >= 0; --i) {
+        const LinearPack* Lst = &enc->lin[(0 * d.depth + i) * L_PER_BLOCK];
+        const LinearPack* Lts = &enc->lin[(1 * d.depth + i) * L_PER_BLOCK];
+        const int sb = 9 * i;
+        const int a = (cur + 1) % 3, b = (cur + 2) % 3;     // a: d x_st, b: d x_ts
+        // fusion backward (DSTformer.py:343-349)
+        {
+            const int i_w = enc->index.at("ts_attn." + std::to_string(i) + ".weight");
+            const int i_b = enc->index.at("ts_attn." + std::to_string(i) + ".bias");
+            const int fgrid = (M + 8 * FUSE_ROWS - 1) / (8 * FUSE_ROWS);
+            const size_t fsm = (static_cast<size_t>(4) * C + 2) * 4;
+            switch (C / 128) {
+                case 2: fuse_bwd_kernel<2><<<fgrid, 256, fsm, st>>>(g_x[cur], slot_x(sb + 4), slot_x(sb + 8), params[i_w], params[i_b], M, C, g_x[a], g_x[b], g_p[a], g_p[b], grads[i_w], grads[i_b]); break;
+                case 4: fuse_bwd_kernel<4><<<fgrid, 256, fsm, st>>>(g_x[cur], slot_x(sb + 4), slot_x(sb + 8), params[i_w], params[i_b], M, C, g_x[a], g_x[b], g_p[a], g_p[b], grads[i_w], grads[i_b]); break;
+                case 6: fuse_bwd_kernel<6><<<fgrid, 256, fsm, st>>>(g_x[cur], slot_x(sb + 4), slot_x(sb + 8), params[i_w], params[i_b], M, C, g_x[a], g_x[b], g_p[a], g_p[b], grads[i_w], grads[i_b]); break;
+                default: fuse_bwd_kernel<8><<<fgrid, 256, fsm, st>>>(g_x[cur], slot_x(sb + 4), slot_x(sb + 8), params[i_w], params[i_b], M, C, g_x[a], g_x[b], g_p[a], g_p[b], grads[i_w], grads[i_b]); break;
+            }
+            LAUNCH_CHECK("fuse_bwd_kernel");
+        }
+        // blocks_st[i] backward: T-mlp(in slot 3), T-attn(2), S-mlp(1), S-attn(0); gradient ping-pongs a <-> cur
+        if ((rc = mlp_backward(Lst, true, sb + 3, a, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lst, true, sb + 2, cur, nullptr, a))) return rc;
+        if ((rc = mlp_backward(Lst, false, sb + 1, a, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lst, false, sb + 0, cur, nullptr, a))) return rc;      // d X0 via the st stream in g[a]
+        // blocks_ts[i] backward: S-mlp(in slot 7), S-attn(6), T-mlp(5), T-attn(0); ping-pong b <-> cur, sum with g[a]
+        if ((rc = mlp_backward(Lts, false, sb + 7, b, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lts, false, sb + 6, cur, nullptr, b))) return rc;
+        if ((rc = mlp_backward(Lts, true, sb + 5, b, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lts, true, sb + 0, cur, g_x[a], b))) return rc;       // total d X0 in g[b]
+        cur = b;
+    }
+    // ---- embed (DSTformer.py:333-337)
+    embed_bwd_kernel<<<dim3(F, (B + EMB_BATCH - 1) / EMB_BATCH), 256, 0, st>>>(
+        g_x[cur], x_in, d.dim_in, B, F, J, C, grads[enc->index.at("joints_embed.weight")],
+        grads[enc->index.at("joints_embed.bias")], grads[enc->index.at("pos_embed")], grads[enc->index.at("temp_embed")]);
+    LAUNCH_CHECK("embed_bwd_kernel");
     return MB_OK;
 }

@@ -13,6 +13,7 @@ library raises.
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 from collections import OrderedDict
 
@@ -294,6 +295,75 @@ class DSTformer(nn.Module):
                 dp_scale.data_ptr() if dp_scale is not None else None,
                 self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr), "mb_forward")
         return out, rep
+
+    # ------------------------------------------------------------------ training (mb_forward_train / mb_backward)
+    def _native_backward_ok(self, x: torch.Tensor, dp_scale) -> bool:
+        """The hand-written backward covers the configuration every reference training script uses: DropPath rate 0,
+        fusion head present, no gradient w.r.t. the pose input, fp32 contiguous parameters."""
+        if dp_scale is not None or x.requires_grad or os.environ.get("MB_TORCH_BACKWARD") == "1":
+            return False
+        params = self._ordered_params()
+        return all(p is not None and p.dtype == torch.float32 and p.is_contiguous() and p.device == x.device
+                   for p in params) and self.dim_out <= 8
+
+    def _launch_train(self, x: torch.Tensor, want_out: bool):
+        """mb_forward_train on the current stream: returns (out, rep, saved) with `saved` the activation region."""
+        device = x.device
+        B, F, J, _ = x.shape
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            st = self._state_for(device)
+            stream_ptr = torch.cuda.current_stream(device).cuda_stream
+            self._ensure_packed(st, device, stream_ptr)
+            ws = st.workspaces.get((B, F))
+            if ws is None:
+                nb = ctypes.c_size_t()
+                _lib.check(lib.mb_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_workspace_bytes")
+                if len(st.workspaces) >= 4:
+                    st.workspaces.clear()
+                ws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
+                st.workspaces[(B, F)] = ws
+            nb = ctypes.c_size_t()
+            _lib.check(lib.mb_saved_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_saved_bytes")
+            saved = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)   # one per forward call
+            out = torch.empty(B, F, J, self.dim_out, dtype=torch.float32, device=device) if want_out else None
+            rep = torch.empty(B, F, J, self.dim_rep, dtype=torch.float32, device=device)
+            _lib.check(lib.mb_forward_train(
+                st.handle, self._aligned_ptr(st.packed), x.data_ptr(), out.data_ptr() if out is not None else None,
+                rep.data_ptr(), self._aligned_ptr(saved), saved.numel() - 1024, self._aligned_ptr(ws),
+                ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr), "mb_forward_train")
+        return out, rep, saved
+
+    def _launch_backward(self, x, rep, saved, d_out, d_rep):
+        """mb_backward on the current stream: returns the parameter gradients in `_ordered_params()` order."""
+        device = x.device
+        B, F, J, _ = x.shape
+        lib = _lib.load()
+        params = self._ordered_params()
+        with torch.cuda.device(device):
+            st = self._state_for(device)
+            stream_ptr = torch.cuda.current_stream(device).cuda_stream
+            self._ensure_packed(st, device, stream_ptr)      # no-op unless the weights changed since the forward
+            bws = st.workspaces.get(("bwd", B, F))
+            if bws is None:
+                nb = ctypes.c_size_t()
+                _lib.check(lib.mb_backward_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_backward_workspace_bytes")
+                bws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
+                st.workspaces[("bwd", B, F)] = bws
+            sizes = [(p.numel() + 63) // 64 * 64 for p in params]          # 256-byte aligned sub-buffers
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+            grads, off = [], 0
+            for p, n in zip(params, sizes):
+                grads.append(flat[off:off + p.numel()].view(p.shape))
+                off += n
+            pp = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+            gp = (ctypes.c_void_p * len(params))(*[g.data_ptr() for g in grads])
+            _lib.check(lib.mb_backward(
+                st.handle, self._aligned_ptr(st.packed), pp, x.data_ptr(), rep.data_ptr(), self._aligned_ptr(saved),
+                saved.numel() - 1024, d_out.data_ptr() if d_out is not None else None,
+                d_rep.data_ptr() if d_rep is not None else None, gp, self._aligned_ptr(bws), bws.numel() - 1024,
+                B, F, stream_ptr), "mb_backward")
+        return grads
 
     def make_graphed(self, B: int, F: int, return_rep: bool = False):
         """CUDA-graph the inference forward for a fixed (B, F): returns `run(x) -> out` that copies x into a static

@@ -1,0 +1,164 @@
+"""Gradient parity of the native backward (mb_forward_train + mb_backward).
+
+The checker is an fp64 back-propagation through `recompute_forward` (a torch-op restatement of
+lib/model/DSTformer.py:329-358 that test_gpu_forward.py pins against the library forward and, through it, against
+the reference fixtures).  The native backward computes in bf16 single-pass arithmetic with fp32 accumulation -- the
+arithmetic of the reference's own mixed-precision training -- so the bar is a per-parameter relative L2 error of a
+few percent, with the exact numbers printed per parameter class."""
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from motionbert_b200 import DSTformer
+from motionbert_b200._autograd import recompute_forward
+from oracle import dstformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 4e-2        # bf16 single-pass backward vs fp64: per-parameter ||g - g_ref|| / ||g_ref||
+COS_MIN = 0.999
+
+
+def _module(dev, dim_feat, depth, heads, mlp_ratio, dim_rep=512, maxlen=243, seed=0):
+    torch.manual_seed(seed)
+    m = DSTformer(dim_in=3, dim_out=3, dim_feat=dim_feat, dim_rep=dim_rep, depth=depth, num_heads=heads,
+                  mlp_ratio=mlp_ratio, norm_layer=partial(nn.LayerNorm, eps=1e-6), maxlen=maxlen)
+    # the reference init leaves biases 0 and LayerNorm at (1, 0): perturb so every gradient path is exercised
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith(".bias") or "norm" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            if n in ("temp_embed", "pos_embed"):
+                p.add_(0.02 * torch.randn(p.shape, generator=g))
+    return m.to(dev).train()
+
+
+def _reference_grads(m, x, w_out, return_rep):
+    ps = [p.detach().double().requires_grad_(True) for p in m._ordered_params()]
+    y = recompute_forward(m, x.double(), return_rep, None, ps)
+    loss = (y * w_out.double()).sum()
+    return torch.autograd.grad(loss, ps), y.detach()
+
+
+def _compare(m, grads_ref, label):
+    names = [n for n, _ in m.named_parameters()]
+    order = {id(p): i for i, p in enumerate(m._ordered_params())}
+    rows, worst = [], (0.0, "")
+    for n, p in m.named_parameters():
+        gr = grads_ref[order[id(p)]]
+        g = p.grad
+        assert g is not None, f"{label}: {n} has no gradient"
+        g = g.double()
+        assert torch.isfinite(g).all(), f"{label}: non-finite gradient in {n}"
+        den = float(gr.norm())
+        rel = float((g - gr).norm()) / (den + 1e-30)
+        cos = float((g * gr).sum()) / (float(g.norm()) * den + 1e-30)
+        rows.append((n, rel, cos, den))
+        if den > 0 and rel > worst[0]:
+            worst = (rel, n)
+    # report: worst 12 and per-class medians
+    rows_sorted = sorted(rows, key=lambda r: -r[1])
+    print(f"\n[{label}] {len(names)} parameters; worst relative L2 errors:")
+    for n, rel, cos, den in rows_sorted[:12]:
+        print(f"    {n:44s} rel {rel:.3e}  cos {cos:.6f}  |g_ref| {den:.3e}")
+    classes = {}
+    for n, rel, cos, den in rows:
+        key = ".".join(t for t in n.split(".") if not t.isdigit())
+        classes.setdefault(key, []).append(rel)
+    print("    per-class median rel:", ", ".join(f"{k}={np.median(v):.1e}" for k, v in sorted(classes.items())))
+    bad = [(n, rel, cos) for n, rel, cos, den in rows if den > 0 and (rel > REL_L2 or cos < COS_MIN)]
+    assert not bad, f"{label}: {len(bad)} parameters out of tolerance, first: {bad[:5]}"
+
+
+CASES = [
+    # label,        dim_feat, depth, heads, mlp, B, F
+    ("lite_d2_f9", 256, 2, 8, 2, 2, 9),          # head_dim 32, packed temporal attention (F <= 32)
+    ("lite_d2_f40", 256, 2, 8, 4, 3, 40),        # head_dim 32, one-sequence temporal tiles
+    ("base_d1_f243", 512, 1, 8, 4, 1, 243),      # head_dim 64, two query tiles per sequence (BASELINE length)
+]
+
+
+@pytest.mark.parametrize("label,dim_feat,depth,heads,mlp,B,F", CASES, ids=[c[0] for c in CASES])
+def test_native_backward_matches_fp64_autograd(cuda_device, label, dim_feat, depth, heads, mlp, B, F):
+    m = _module(cuda_device, dim_feat, depth, heads, mlp, seed=11)
+    x = torch.from_numpy(O.make_input(B, F, 17, 21)).to(cuda_device)
+    g = torch.Generator().manual_seed(5)
+    w_out = torch.randn(B, F, 17, 3, generator=g).to(cuda_device)
+    assert m._native_backward_ok(x, None)
+    out = m(x)
+    (out * w_out).sum().backward()
+    torch.cuda.synchronize(cuda_device)
+    grads_ref, y_ref = _reference_grads(m, x, w_out, False)
+    assert float((out.detach().double() - y_ref).abs().max()) < 1e-3 * float(y_ref.abs().max())
+    _compare(m, grads_ref, label)
+
+
+def test_native_backward_through_get_representation(cuda_device):
+    """train_action.py / train_mesh.py back-propagate through get_representation (DSTformer.py:360-361)."""
+    m = _module(cuda_device, 256, 2, 8, 2, seed=3)
+    B, F = 2, 12
+    x = torch.from_numpy(O.make_input(B, F, 17, 8)).to(cuda_device)
+    w = torch.randn(B, F, 17, 512, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    rep = m.get_representation(x)
+    (rep * w).sum().backward()
+    grads_ref, _ = _reference_grads(m, x, w, True)
+    # head.* receives no gradient on this path
+    assert float(m.head.weight.grad.abs().max()) == 0.0
+    _compare(m, grads_ref, "rep_path")
+
+
+def test_native_backward_equals_torch_fallback_and_accumulates(cuda_device, monkeypatch):
+    """The two backward implementations agree (bf16 tolerance), and .grad accumulates over two backward calls."""
+    m = _module(cuda_device, 256, 1, 8, 2, seed=9)
+    x = torch.from_numpy(O.make_input(2, 10, 17, 4)).to(cuda_device)
+    (m(x) ** 2).sum().backward()
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters()}
+    (m(x) ** 2).sum().backward()
+    for n, p in m.named_parameters():
+        assert torch.allclose(p.grad, 2 * g1[n], rtol=1e-3, atol=1e-5 * float(g1[n].abs().max()) + 1e-12), n
+    m.zero_grad(set_to_none=True)
+    monkeypatch.setenv("MB_TORCH_BACKWARD", "1")
+    assert not m._native_backward_ok(x, None)
+    (m(x) ** 2).sum().backward()
+    for n, p in m.named_parameters():
+        den = float(p.grad.norm())
+        if den > 0:
+            assert float((p.grad - g1[n]).norm()) / den < REL_L2, n
+
+
+def test_training_step_reduces_loss(cuda_device):
+    """Ten AdamW steps on a fixed batch through forward_train/backward/repack: the loss must fall (train.py:149-176)."""
+    m = _module(cuda_device, 256, 2, 8, 2, seed=2)
+    x = torch.from_numpy(O.make_input(4, 16, 17, 6)).to(cuda_device)
+    target = torch.from_numpy(O.make_input(4, 16, 17, 7)).to(cuda_device)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(10):
+        opt.zero_grad(set_to_none=True)
+        loss = ((m(x) - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0], losses
+
+
+def test_backward_error_paths(cuda_device):
+    import ctypes
+
+    from motionbert_b200 import _lib
+    m = _module(cuda_device, 256, 1, 8, 2)
+    x = torch.from_numpy(O.make_input(1, 4, 17, 1)).to(cuda_device)
+    out, rep, saved = m._launch_train(x, True)
+    lib = _lib.load()
+    st = m._state_for(x.device)
+    nb = ctypes.c_size_t()
+    assert lib.mb_saved_bytes(st.handle, 1, 4, ctypes.byref(nb)) == 0 and nb.value > 0
+    assert lib.mb_saved_bytes(st.handle, 1, 1000, ctypes.byref(nb)) < 0
+    # too-small saved region is rejected before any launch
+    rc = lib.mb_forward_train(st.handle, m._aligned_ptr(st.packed), x.data_ptr(), None, rep.data_ptr(),
+                              m._aligned_ptr(saved), 1024, m._aligned_ptr(saved), 1 << 30, 1, 4, 0, None)
+    assert rc < 0 and b"saved region" in lib.mb_last_error()

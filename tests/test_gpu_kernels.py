@@ -184,4 +184,5 @@ def test_attention_core_backward(cuda_device, B, F, J, C, H, temporal):
     assert torch.isfinite(got).all(), "non-finite / unwritten gradient"
     for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
         rel, mx = _rel(got[:, sl], exp[:, sl])
-        assert rel < 2e-2, f"{name}: rel {rel:.3e} max {mx:.3e}"
+        # F = 1: softmax of a single key is constant -> dq = dk = 0 exactly, only an absolute check makes sense
+        assert rel < 2e-2 or mx < 1e-5, f"{name}: rel {rel:.3e} max {mx:.3e}"
