@@ -188,6 +188,92 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def run_train(args, device, world, rank, local_rank, dist, D):
+    """SURVEY.md 8d config 3 (N=1) / config 4 (N>1): one pretrain step = forward (saved residual stream) -> MPJPE loss
+    -> native backward -> gradient all-reduce over the ranks (N>1) -> fused AdamW -> weight re-pack at the next forward.
+    Supplementary to the headline forward line (BASELINE's metric); printed with the same keys."""
+    model = build_model(args.model, device, args.math).train()
+    cfg = MODELS[args.model]
+    hidden = int(cfg["dim_feat"] * cfg["mlp_ratio"])
+    B, T = args.batch, args.frames
+    x_host = synthetic_clips(B, T, seed=1 + rank)
+    gt_host = synthetic_clips(B, T, seed=1001 + rank)
+    x_dev, gt_dev = x_host.to(device), gt_host.to(device)
+    params = [p for p in model.parameters()]
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.01, fused=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def step(x, gt):
+        opt.zero_grad(set_to_none=True)
+        pred = model(x)
+        loss = torch.linalg.vector_norm(pred - gt, dim=-1).mean()          # loss_mpjpe, lib/model/loss.py:7-13
+        loss.backward()
+        if world > 1:
+            D.allreduce_gradients(params, world)
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step(x_dev, gt_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, gt_dev)
+    ev1.record()
+    barrier()
+    ms_per_step = D.max_over_ranks(ev0.elapsed_time(ev1), device) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    clocks = sampler.summary()
+    value = world * B / (ms_per_step * 1e-3)
+    # end to end: pinned host clip + target -> H2D, step, loss read back to the host every step
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        last = float(step(x_host.to(device, non_blocking=True), gt_host.to(device, non_blocking=True)).item())
+    e1.record()
+    barrier()
+    e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), device) / args.steps
+    peaks = load_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    step_flop = 3.0 * flops_per_sequence(cfg["dim_feat"], hidden, T) * B          # fwd + 2x bwd (recompute not counted)
+    achieved = step_flop / (ms_per_step * 1e-3) / 1e12
+    n_param = sum(p.numel() for p in params)
+    line = {
+        "metric": f"sequences/sec DSTformer-{args.model} pretrain step fwd+bwd+AdamW (Bx{T}x17)",
+        "value": value, "unit": "sequences/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.math == "bf16" else "bf16x3 forward / bf16 backward", "data": "synthetic",
+        "config": {"workload": f"SURVEY 8d config {'3' if world == 1 else '4'}: DSTformer-{args.model} pretrain step, B={B} per GPU, "
+                               f"T={T}, MPJPE loss, native backward (bf16 single-pass), fused AdamW", "global_batch": world * B,
+                   "seq_len": T, "parallelism": f"dp{world}" + (" + one flat fp32 gradient all-reduce per step (NCCL)" if world > 1 else ""),
+                   "l2": "activations >> 126 MB L2, no flush needed", "grad_allreduce_elems": n_param if world > 1 else 0},
+        "clocks": clocks,
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(2 * x_host.numel() * 4), "d2h_bytes_per_step": 4, "last_loss": last,
+                "api": "DSTformer.forward -> loss.backward() -> optimizer.step() on pinned host clips"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "traffic": None, "note": "whole step: 3 x forward algorithmic FLOPs / step time (recompute, optimizer and "
+                                              "all-reduce time included in the denominator, not in the numerator)",
+                     "peak_source": peaks["_source"] + " bf16_tflops_sustained"},
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,12 +281,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="base", choices=["base", "lite"])
-    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward = BASELINE config 2 (the headline); train = config 3/4 pretrain step (fwd+bwd+AdamW)")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU per step (default 256 forward / 128 train)")
     ap.add_argument("--frames", type=int, default=243)
-    ap.add_argument("--math", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--math", default=None, choices=["bf16x3", "bf16"],
+                    help="default bf16x3 (fp32 parity) for forward, bf16 for train (config 3 is a bf16 step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.batch is None:
+        args.batch = 128 if args.mode == "train" else 256
+    if args.math is None:
+        args.math = "bf16" if args.mode == "train" else "bf16x3"
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -218,6 +311,9 @@ def main():
     dist = D.init("nccl", device) if world > 1 else None
 
     from motionbert_b200 import _lib
+    if args.mode == "train":
+        run_train(args, device, world, rank, local_rank, dist, D)
+        return
     model = build_model(args.model, device, args.math)
     cfg = MODELS[args.model]
     hidden = int(cfg["dim_feat"] * cfg["mlp_ratio"])

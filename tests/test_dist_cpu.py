@@ -66,3 +66,43 @@ def test_two_rank_gloo_sharded_forward_matches_single_process():
     assert all(r[4] == 11.0 for r in res)                                        # max over ranks
     assert all(r[5] == 3.0 for r in res)                                         # whole-job unit count
     assert [r[6] for r in res] == [(2, 0, 0), (2, 1, 1)]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist = D.init("gloo")
+    try:
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
+        ps[0].grad = torch.full((3, 5), float(rank + 1))
+        ps[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+        n = D.allreduce_gradients(ps)                     # ps[2] has no gradient (frozen / unused): skipped
+        q.put((rank, n, ps[0].grad.clone(), ps[1].grad.clone(), ps[2].grad))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_is_the_mean_over_ranks():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n, g0, g1, g2 in res:
+        assert n == 22 and g2 is None
+        assert torch.equal(g0, torch.full((3, 5), 1.5))
+        assert torch.equal(g1, torch.arange(7, dtype=torch.float32) * 1.5)
+
+
+def test_gradient_allreduce_is_a_noop_without_a_process_group():
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    assert D.allreduce_gradients([p]) == 0 and torch.equal(p.grad, torch.ones(4))
