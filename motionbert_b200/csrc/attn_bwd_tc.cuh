@@ -11,6 +11,10 @@
 //   attn_bwd_kv_kernel: rows = keys.  S^T = K Q^T and dP^T = V dO^T, P^T / dS^T rebuilt from the stored statistics
 //                       (column vectors now), dV = P^T dO and dK = dS^T Q with dO / Q as MN-major operands.
 // The spatial attention is the same problem with (B' = B*F, F' = J, J' = 1): the host passes those dimensions.
+// PACK = true (sequences of <= 32 rows: the 17-joint spatial attention, short temporal clips): FOUR sequences share
+// one 128-row tile, each in its own 32-row slab (four 32-row TMA boxes per operand); scores are 128 x 128 with only
+// the diagonal 32 x 32 blocks live, the off-diagonal blocks of P / dS are written as zeros so the dQ / dK / dV
+// contractions over all 128 rows pick up exactly the rows of the own sequence.
 #pragma once
 #include "attn_t_tc.cuh"
 
@@ -47,7 +51,7 @@ struct AttnBwdCfg {
 };
 
 // ------------------------------------------------------------------------------------------------- dQ kernel
-template <int HD>
+template <int HD, bool PACK = false>
 __global__ void __launch_bounds__(ABW_THREADS, 1)
 attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box (HD, 1, 128, 1, 1)
                   const __grid_constant__ CUtensorMap tmQKV_s,   // qkv 5-D, box (HD, 1, NK , 1, 1)
@@ -70,9 +74,12 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_prob = p.B * p.J * p.H;
-    const int num_qt = (p.F + ATT_BM - 1) / ATT_BM;
-    const uint32_t seq_bytes = static_cast<uint32_t>(p.NK) * Cfg::SWZ;
+    const int nseq = p.B * p.J;
+    const int num_prob = PACK ? ((nseq + 3) / 4) * p.H : nseq * p.H;
+    const int num_qt = PACK ? 1 : (p.F + ATT_BM - 1) / ATT_BM;
+    const int NKe = PACK ? ATT_BM : p.NK;                    // key columns of the score tile
+    const uint32_t seq_bytes = static_cast<uint32_t>(NKe) * Cfg::SWZ;
+    constexpr uint32_t SLAB = 32 * Cfg::SWZ;                 // one 32-row slab of a packed tile
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV_t); tma_prefetch_desc(&tmQKV_s); tma_prefetch_desc(&tmDO_t);
@@ -98,6 +105,26 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                 const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
                 mbar_wait(kv_empty, (ip & 1) ^ 1);
                 mbar_arrive_expect_tx(kv_full, 2 * seq_bytes);
+                if (PACK) {
+                    // four sequences, one 32-row box each (sequences past the end re-load the last one: finite data,
+                    // their rows are never stored)
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        int sq = (prob / p.H) * 4 + s4;
+                        if (sq >= nseq) sq = nseq - 1;
+                        tma_load_5d(smem + Cfg::OFF_C + s4 * SLAB, &tmQKV_s, kv_full, p.C + h * HD, sq % p.J, 0, sq / p.J, 0);
+                        tma_load_5d(smem + Cfg::OFF_D + s4 * SLAB, &tmQKV_s, kv_full, 2 * p.C + h * HD, sq % p.J, 0, sq / p.J, 0);
+                    }
+                    mbar_wait(t_empty, (t_it & 1) ^ 1);
+                    mbar_arrive_expect_tx(t_full, 2 * Cfg::TILE);
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        int sq = (prob / p.H) * 4 + s4;
+                        if (sq >= nseq) sq = nseq - 1;
+                        tma_load_5d(smem + Cfg::OFF_A + s4 * SLAB, &tmQKV_t, t_full, h * HD, sq % p.J, 0, sq / p.J, 0);
+                        tma_load_5d(smem + Cfg::OFF_B + s4 * SLAB, &tmDO_t, t_full, h * HD, sq % p.J, 0, sq / p.J, 0);
+                    }
+                    ++t_it;
+                    continue;
+                }
                 tma_load_5d(smem + Cfg::OFF_C, &tmQKV_s, kv_full, p.C + h * HD, j, 0, b, 0);       // K
                 tma_load_5d(smem + Cfg::OFF_D, &tmQKV_s, kv_full, 2 * p.C + h * HD, j, 0, b, 0);   // V
                 for (int qt = 0; qt < num_qt; ++qt, ++t_it) {
@@ -109,7 +136,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, p.NK, 0, 0);
+        const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, NKe, 0, 0);
         const uint32_t idesc_q = umma_idesc_bf16(ATT_BM, HD, 0, 1);     // dQ = dS K: B (=K) MN-major
         const uint32_t sQ = smem_u32(smem + Cfg::OFF_A), sDO = smem_u32(smem + Cfg::OFF_B);
         const uint32_t sK = smem_u32(smem + Cfg::OFF_C), sV = smem_u32(smem + Cfg::OFF_D);
@@ -144,7 +171,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                 mbar_wait(ds_full, ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const int nks = p.NK / 16;
+                    const int nks = NKe / 16;
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t a = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);      // packed bf16 dS
                         const uint32_t koff = static_cast<uint32_t>(ks) * 16 * Cfg::SWZ;
@@ -162,17 +189,26 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
         const int half = (warp - 2) >> 2;
         const int r_in_tile = quad * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        const int nch = (p.NK + 31) / 32;
-        const int ch_lo = half * 4 < nch ? half * 4 : nch;
-        const int ch_hi = (half * 4 + 4 < nch) ? half * 4 + 4 : nch;
+        const int nch = (NKe + 31) / 32;
+        // unpacked: the two threads of a row split the chunks; packed: only the diagonal chunk (= quad) is live and
+        // half 0 owns it, half 1 zero-fills the three off-diagonal chunks
+        const int ch_lo = PACK ? (half == 0 ? quad : 0) : (half * 4 < nch ? half * 4 : nch);
+        const int ch_hi = PACK ? (half == 0 ? quad + 1 : 0) : ((half * 4 + 4 < nch) ? half * 4 + 4 : nch);
         const float sl2 = p.scale_log2e;
         uint32_t t_it = 0;
         for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
-            const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
+            int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
             for (int qt = 0; qt < num_qt; ++qt, ++t_it) {
                 const uint32_t ph = t_it & 1;
-                const int tq = qt * ATT_BM + r_in_tile;
-                const bool ok = tq < p.F;
+                int tq = qt * ATT_BM + r_in_tile;
+                bool ok = tq < p.F;
+                if (PACK) {
+                    const int sq = (prob / p.H) * 4 + quad;          // my slab's sequence
+                    tq = lane;
+                    ok = lane < p.F && sq < nseq;
+                    j = ok ? sq % p.J : 0;
+                    b = ok ? sq / p.J : 0;
+                }
                 const size_t tok = (static_cast<size_t>(b) * p.F + (ok ? tq : 0)) * p.J + j;
                 // delta = dO . O of my row (both threads of the row compute it redundantly)
                 float delta = 0.f;
@@ -199,7 +235,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (ch * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        if ((PACK ? i : ch * 32 + i) < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
                 }
                 red[half * 128 + r_in_tile] = mx;
                 named_bar_sync(1, ABW_SIMT);
@@ -212,14 +248,15 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (ch * 32 + i < p.F) sum += ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs));
+                        if ((PACK ? i : ch * 32 + i) < p.F) sum += ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs));
                 }
                 red[256 + half * 128 + r_in_tile] = sum;
                 named_bar_sync(1, ABW_SIMT);
                 sum = red[256 + r_in_tile] + red[256 + 128 + r_in_tile];
                 const float lse2 = mxs + log2f(sum);                 // P = 2^(s*c*log2e - lse2)
                 if (ok && half == 0) {
-                    const size_t si = (static_cast<size_t>(prob)) * p.F + tq;
+                    const size_t si = PACK ? static_cast<size_t>(prob) * ATT_BM + r_in_tile
+                                           : static_cast<size_t>(prob) * p.F + tq;
                     p.lse2[si] = lse2;
                     p.delta[si] = delta;
                 }
@@ -233,11 +270,11 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float d0 = 0.f, d1 = 0.f;
-                        if (ch * 32 + 2 * i < p.F) {
+                        if ((PACK ? 2 * i : ch * 32 + 2 * i) < p.F) {
                             const float pv = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -lse2));
                             d0 = pv * (__uint_as_float(g[2 * i]) - delta) * p.scale;
                         }
-                        if (ch * 32 + 2 * i + 1 < p.F) {
+                        if ((PACK ? 2 * i + 1 : ch * 32 + 2 * i + 1) < p.F) {
                             const float pv = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -lse2));
                             d1 = pv * (__uint_as_float(g[2 * i + 1]) - delta) * p.scale;
                         }
@@ -245,6 +282,14 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                         pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
                     }
                     tmem_st16(tmem_S + lane_off + ch * 32, pk);
+                }
+                if (PACK && half == 1) {
+                    uint32_t z[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch != quad) tmem_st16(tmem_S + lane_off + ch * 32, z);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -283,7 +328,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
 }
 
 // ------------------------------------------------------------------------------------------------- dK / dV kernel
-template <int HD>
+template <int HD, bool PACK = false>
 __global__ void __launch_bounds__(ABW_THREADS, 1)
 attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box (HD, 1, 128, 1, 1)
                    const __grid_constant__ CUtensorMap tmQKV_s,   // qkv 5-D, box (HD, 1, NK , 1, 1)
@@ -307,9 +352,12 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_prob = p.B * p.J * p.H;
-    const int num_kt = (p.F + ATT_BM - 1) / ATT_BM;
-    const uint32_t seq_bytes = static_cast<uint32_t>(p.NK) * Cfg::SWZ;
+    const int nseq = p.B * p.J;
+    const int num_prob = PACK ? ((nseq + 3) / 4) * p.H : nseq * p.H;
+    const int num_kt = PACK ? 1 : (p.F + ATT_BM - 1) / ATT_BM;
+    const int NKe = PACK ? ATT_BM : p.NK;
+    const uint32_t seq_bytes = static_cast<uint32_t>(NKe) * Cfg::SWZ;
+    constexpr uint32_t SLAB = 32 * Cfg::SWZ;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV_t); tma_prefetch_desc(&tmQKV_s); tma_prefetch_desc(&tmDO_s);
@@ -335,6 +383,24 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
                 const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
                 mbar_wait(seq_empty, (ip & 1) ^ 1);
                 mbar_arrive_expect_tx(seq_full, 2 * seq_bytes);
+                if (PACK) {
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        int sq = (prob / p.H) * 4 + s4;
+                        if (sq >= nseq) sq = nseq - 1;
+                        tma_load_5d(smem + Cfg::OFF_C + s4 * SLAB, &tmQKV_s, seq_full, h * HD, sq % p.J, 0, sq / p.J, 0);
+                        tma_load_5d(smem + Cfg::OFF_D + s4 * SLAB, &tmDO_s, seq_full, h * HD, sq % p.J, 0, sq / p.J, 0);
+                    }
+                    mbar_wait(t_empty, (t_it & 1) ^ 1);
+                    mbar_arrive_expect_tx(t_full, 2 * Cfg::TILE);
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        int sq = (prob / p.H) * 4 + s4;
+                        if (sq >= nseq) sq = nseq - 1;
+                        tma_load_5d(smem + Cfg::OFF_A + s4 * SLAB, &tmQKV_t, t_full, p.C + h * HD, sq % p.J, 0, sq / p.J, 0);
+                        tma_load_5d(smem + Cfg::OFF_B + s4 * SLAB, &tmQKV_t, t_full, 2 * p.C + h * HD, sq % p.J, 0, sq / p.J, 0);
+                    }
+                    ++t_it;
+                    continue;
+                }
                 tma_load_5d(smem + Cfg::OFF_C, &tmQKV_s, seq_full, h * HD, j, 0, b, 0);     // Q (all queries)
                 tma_load_5d(smem + Cfg::OFF_D, &tmDO_s, seq_full, h * HD, j, 0, b, 0);      // dO (all queries)
                 for (int kt = 0; kt < num_kt; ++kt, ++t_it) {
@@ -346,7 +412,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, p.NK, 0, 0);
+        const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, NKe, 0, 0);
         const uint32_t idesc_g = umma_idesc_bf16(ATT_BM, HD, 0, 1);
         const uint32_t sK = smem_u32(smem + Cfg::OFF_A), sV = smem_u32(smem + Cfg::OFF_B);
         const uint32_t sQ = smem_u32(smem + Cfg::OFF_C), sDO = smem_u32(smem + Cfg::OFF_D);
@@ -381,7 +447,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
                 mbar_wait(ps_full, ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const int nks = p.NK / 16;
+                    const int nks = NKe / 16;
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t a_p = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);     // P^T  : first 16 columns of the chunk
                         const uint32_t a_ds = a_p + 16;                                  // dS^T : last 16 columns
@@ -402,17 +468,22 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
         const int half = (warp - 2) >> 2;
         const int r_in_tile = quad * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        const int nch = (p.NK + 31) / 32;
-        const int ch_lo = half * 4 < nch ? half * 4 : nch;
-        const int ch_hi = (half * 4 + 4 < nch) ? half * 4 + 4 : nch;
+        const int nch = (NKe + 31) / 32;
+        const int ch_lo = PACK ? (half == 0 ? quad : 0) : (half * 4 < nch ? half * 4 : nch);
+        const int ch_hi = PACK ? (half == 0 ? quad + 1 : 0) : ((half * 4 + 4 < nch) ? half * 4 + 4 : nch);
         const float sl2 = p.scale_log2e;
         const int sid = threadIdx.x - 64;             // 0..255
         uint32_t t_it = 0;
         for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
-            const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
+            int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
             // per-query statistics of this sequence -> smem (queries >= F get p = 0)
             named_bar_sync(1, ABW_SIMT);               // previous problem's readers are done
-            {
+            if (PACK) {
+                const bool qok = sid < ATT_BM && (sid & 31) < p.F && (prob / p.H) * 4 + (sid >> 5) < nseq;
+                const size_t si = static_cast<size_t>(prob) * ATT_BM;
+                v_lse[sid] = qok ? p.lse2[si + sid] : 3.0e38f;
+                v_delta[sid] = qok ? p.delta[si + sid] : 0.f;
+            } else {
                 const size_t si = static_cast<size_t>(prob) * p.F;
                 v_lse[sid] = sid < p.F ? p.lse2[si + sid] : 3.0e38f;
                 v_delta[sid] = sid < p.F ? p.delta[si + sid] : 0.f;
@@ -443,13 +514,31 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
                     tmem_st16(tmem_S + lane_off + ch * 32, pp);
                     tmem_st16(tmem_S + lane_off + ch * 32 + 16, pd);
                 }
+                if (PACK && half == 1) {
+                    uint32_t z[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        if (ch != quad) {
+                            tmem_st16(tmem_S + lane_off + ch * 32, z);
+                            tmem_st16(tmem_S + lane_off + ch * 32 + 16, z);
+                        }
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(ps_full);
                 mbar_wait(g_full, ph);
                 tc_fence_after();
-                const int tk = kt * ATT_BM + r_in_tile;
-                const bool ok = tk < p.F;
+                int tk = kt * ATT_BM + r_in_tile;
+                bool ok = tk < p.F;
+                if (PACK) {
+                    const int sq = (prob / p.H) * 4 + quad;
+                    tk = lane;
+                    ok = lane < p.F && sq < nseq;
+                    j = ok ? sq % p.J : 0;
+                    b = ok ? sq / p.J : 0;
+                }
                 const size_t tok = (static_cast<size_t>(b) * p.F + (ok ? tk : 0)) * p.J + j;
                 // half 0 drains dV, half 1 drains dK (HD columns each)
                 {

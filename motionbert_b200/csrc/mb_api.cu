@@ -159,10 +159,14 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, false>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, true>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_bwd_q_kernel<64>, AttnBwdCfg<64>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_bwd_q_kernel<32>, AttnBwdCfg<32>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_bwd_kv_kernel<64>, AttnBwdCfg<64>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_bwd_kv_kernel<32>, AttnBwdCfg<32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_q_kernel<64, false>, AttnBwdCfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_q_kernel<32, false>, AttnBwdCfg<32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_kv_kernel<64, false>, AttnBwdCfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_kv_kernel<32, false>, AttnBwdCfg<32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_q_kernel<64, true>, AttnBwdCfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_q_kernel<32, true>, AttnBwdCfg<32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_kv_kernel<64, true>, AttnBwdCfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_bwd_kv_kernel<32, true>, AttnBwdCfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<3>, WgradCfg<3>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<1>, WgradCfg<1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t2_kernel<64, 3>, Attn2Cfg<64, 3>::SMEM_BYTES));
@@ -1355,6 +1359,7 @@ static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H
     if (F < 1 || F > ATT_MAXK) return fail(MB_ERR_INVALID, "sequence length %d unsupported", F);
     const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
     const uint64_t C3 = 3ull * C, Cc = static_cast<uint64_t>(C);
+    const bool pack = F <= 32;             // four short sequences per 128-row tile (spatial attention, short clips)
     CUtensorMap q_t, q_s, do_t, do_s;
     int rc;
     {
@@ -1362,8 +1367,8 @@ static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H
         const uint64_t sq[4] = {C3, C3 * J, C3 * J * F, C3 * J * F * B};
         const uint64_t dd[5] = {Cc, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 1};
         const uint64_t sd[4] = {Cc, Cc * J, Cc * J * F, Cc * J * F * B};
-        const uint32_t bt[5] = {static_cast<uint32_t>(hd), 1, ATT_BM, 1, 1};
-        const uint32_t bs[5] = {static_cast<uint32_t>(hd), 1, NK, 1, 1};
+        const uint32_t bt[5] = {static_cast<uint32_t>(hd), 1, pack ? 32u : static_cast<uint32_t>(ATT_BM), 1, 1};
+        const uint32_t bs[5] = {static_cast<uint32_t>(hd), 1, pack ? 32u : NK, 1, 1};
         if ((rc = make_tmap(&q_t, qkv, 5, dq, sq, bt, hd * 2))) return rc;
         if ((rc = make_tmap(&q_s, qkv, 5, dq, sq, bs, hd * 2))) return rc;
         if ((rc = make_tmap(&do_t, dO, 5, dd, sd, bt, hd * 2))) return rc;
@@ -1375,20 +1380,29 @@ static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H
     bp.scale = scale;
     bp.scale_log2e = scale * 1.4426950408889634f;
     bp.O = O; bp.dO = dO; bp.lse2 = lse2; bp.delta = delta; bp.dqkv = dqkv;
-    const int prob = B * J * H;
+    const int prob = pack ? ((B * J + 3) / 4) * H : B * J * H;
     const int grid = prob < dev.sms ? prob : dev.sms;
-    if (hd == 64) {
-        attn_bwd_q_kernel<64><<<grid, ABW_THREADS, AttnBwdCfg<64>::SMEM_BYTES, st>>>(q_t, q_s, do_t, bp);
-        LAUNCH_CHECK("attn_bwd_q_kernel");
-        attn_bwd_kv_kernel<64><<<grid, ABW_THREADS, AttnBwdCfg<64>::SMEM_BYTES, st>>>(q_t, q_s, do_s, bp);
-        LAUNCH_CHECK("attn_bwd_kv_kernel");
-    } else {
-        attn_bwd_q_kernel<32><<<grid, ABW_THREADS, AttnBwdCfg<32>::SMEM_BYTES, st>>>(q_t, q_s, do_t, bp);
-        LAUNCH_CHECK("attn_bwd_q_kernel");
-        attn_bwd_kv_kernel<32><<<grid, ABW_THREADS, AttnBwdCfg<32>::SMEM_BYTES, st>>>(q_t, q_s, do_s, bp);
-        LAUNCH_CHECK("attn_bwd_kv_kernel");
-    }
+#define ABW_LAUNCH(HD_, PK_)                                                                                         \
+    do {                                                                                                             \
+        attn_bwd_q_kernel<HD_, PK_><<<grid, ABW_THREADS, AttnBwdCfg<HD_>::SMEM_BYTES, st>>>(q_t, q_s, do_t, bp);      \
+        LAUNCH_CHECK("attn_bwd_q_kernel");                                                                           \
+        attn_bwd_kv_kernel<HD_, PK_><<<grid, ABW_THREADS, AttnBwdCfg<HD_>::SMEM_BYTES, st>>>(q_t, q_s, do_s, bp);     \
+        LAUNCH_CHECK("attn_bwd_kv_kernel");                                                                          \
+    } while (0)
+    if (hd == 64 && pack) ABW_LAUNCH(64, true);
+    else if (hd == 64) ABW_LAUNCH(64, false);
+    else if (pack) ABW_LAUNCH(32, true);
+    else ABW_LAUNCH(32, false);
+#undef ABW_LAUNCH
     return MB_OK;
+}
+
+// floats needed by each of the lse2 / delta scratch vectors of launch_attn_bwd (packed tiles keep 32 slots per sequence)
+static size_t attn_bwd_stat_floats(size_t B, size_t F, size_t J, size_t H) {
+    const size_t nseq_t = B * J, nseq_s = B * F;
+    const size_t a = nseq_t * H * (F <= 32 ? 32 : F) + 4 * 32 * H;
+    const size_t b = nseq_s * H * 32 + 4 * 32 * H;
+    return a > b ? a : b;
 }
 
 extern "C" int mb_test_attention_backward_scratch_bytes(int B, int F, int J, int C, size_t* bytes) {
@@ -1398,7 +1412,7 @@ extern "C" int mb_test_attention_backward_scratch_bytes(int B, int F, int J, int
              + 2 * align_up(M * C * 2, 1024)        /* O planes */
              + align_up(M * C * 2, 1024)            /* dO */
              + align_up(M * 3 * C * 2, 1024)        /* dqkv */
-             + 2 * align_up(M * (C / 32) * 4, 1024);   /* lse2, delta (>= B*J*H*F floats) */
+             + 2 * align_up(attn_bwd_stat_floats(B, F, J, C / 32) * 4, 1024);   /* lse2, delta (C/32 >= heads) */
     return MB_OK;
 }
 
@@ -1431,7 +1445,7 @@ extern "C" int mb_test_attention_backward(int temporal, int B, int F, int J, int
     auto* dO_b = reinterpret_cast<__nv_bfloat16*>(b + 2 * qkv_plane + 2 * ao_plane);
     auto* dqkv_b = reinterpret_cast<__nv_bfloat16*>(b + 2 * qkv_plane + 3 * ao_plane);
     float* lse2 = reinterpret_cast<float*>(b + 3 * qkv_plane + 3 * ao_plane);
-    float* delta = lse2 + align_up(M * (C / 32) * 4, 1024) / 4;
+    float* delta = lse2 + align_up(attn_bwd_stat_floats(B, F, J, C / 32) * 4, 1024) / 4;
     {
         const size_t n = M * 3 * C;
         split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(qkv, P.qkv, nullptr, n);
@@ -1514,8 +1528,8 @@ static BwdLayout bwd_layout(const MbDesc& d, int B, int F) {
     w.d_o = take(M * C * 2);
     for (int i = 0; i < 3; ++i) { w.g_x[i] = take(M * C * 4); w.g_p[i] = take(M * C * 2); }
     w.dxhat = take(M * C * 4);
-    w.lse2 = take(M * d.num_heads * 4);
-    w.delta = take(M * d.num_heads * 4);
+    w.lse2 = take(attn_bwd_stat_floats(B, F, d.num_joints, d.num_heads) * 4);
+    w.delta = take(attn_bwd_stat_floats(B, F, d.num_joints, d.num_heads) * 4);
     w.dwp = take(w.max_n * C * 4);
     w.dc = take(w.max_n * 4);
     w.zero = take((w.max_n > C ? w.max_n : C) * 4);

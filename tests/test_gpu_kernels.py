@@ -171,7 +171,7 @@ def _attn_autograd(qkv, dO, B, F, J, C, H, temporal):
 
 @pytest.mark.parametrize("temporal", [1, 0], ids=["temporal", "spatial"])
 @pytest.mark.parametrize("B,F,J,C,H", [(2, 27, 17, 512, 8), (1, 243, 17, 512, 8), (2, 130, 17, 256, 8), (3, 16, 17, 512, 8),
-                                       (1, 1, 17, 256, 8)])
+                                       (1, 1, 17, 256, 8), (3, 9, 17, 256, 8), (1, 32, 5, 256, 4)])
 def test_attention_core_backward(cuda_device, B, F, J, C, H, temporal):
     """Groundwork for the native backward: flash-style tcgen05 attention backward (bf16 single pass) vs autograd."""
     g = torch.Generator().manual_seed(B * 31 + F)
