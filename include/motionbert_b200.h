@@ -137,6 +137,16 @@ int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, 
                 const void* saved, size_t saved_bytes, const float* d_out, const float* d_rep, float* const* grads,
                 void* workspace, size_t workspace_bytes, int B, int F, void* stream);
 
+/* ---- pretrain-step losses on the pose output, fused with their gradient ------------
+ * 3-D mode (conf == NULL):  losses[0] = loss_mpjpe (lib/model/loss.py:56-63), [1] = n_mpjpe (:80-89),
+ *   [2] = loss_velocity (:133-142), [3] = total = [0] + lambda_scale [1] + lambda_velocity [2]  (train.py:178-191);
+ * 2-D mode (conf != NULL, (B,T,J) detector confidences): losses[0] = losses[3] = loss_2d_weighted (:73-78).
+ * d_pred (optional) receives d total / d pred, computed analytically in the same launch.  All pointers are device
+ * pointers; pred / target are (B,T,J,3) fp32 contiguous; scratch = 32 bytes, 8-byte aligned. */
+int mb_pretrain_loss(const float* pred, const float* target, const float* conf, int B, int T, int J,
+                     float lambda_scale, float lambda_velocity, float* losses, float* d_pred, void* scratch,
+                     void* stream);
+
 /* Number of kernels one mb_forward call launches for this (B, F) (for bench.py's gpu_launches). */
 int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags);
 

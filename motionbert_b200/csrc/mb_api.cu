@@ -21,6 +21,7 @@
 #include "backward_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "loss_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "wgrad_tc.cuh"
 
@@ -1832,5 +1833,30 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
         g_x[cur], x_in, d.dim_in, B, F, J, C, grads[enc->index.at("joints_embed.weight")],
         grads[enc->index.at("joints_embed.bias")], grads[enc->index.at("pos_embed")], grads[enc->index.at("temp_embed")]);
     LAUNCH_CHECK("embed_bwd_kernel");
+    return MB_OK;
+}
+
+
+// ==================================================================================== pretrain losses (row f1)
+extern "C" int mb_pretrain_loss(const float* pred, const float* target, const float* conf, int B, int T, int J,
+                                float lambda_scale, float lambda_velocity, float* losses, float* d_pred, void* scratch,
+                                void* stream_) {
+    if (!pred || !target || !losses || !scratch) return fail(MB_ERR_NULL, "NULL argument");
+    if (B < 1 || T < 1 || J < 1 || J > 32) return fail(MB_ERR_INVALID, "bad shape B=%d T=%d J=%d (J <= 32)", B, T, J);
+    if (static_cast<size_t>(B) * T > 0x7fffffffULL / 64) return fail(MB_ERR_INVALID, "B*T too large");
+    if (reinterpret_cast<uintptr_t>(scratch) & 7) return fail(MB_ERR_ALIGN, "scratch must be 8-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), st));
+    PoseLossParams p;
+    p.pred = pred; p.target = target; p.conf = conf;
+    p.B = B; p.T = T; p.J = J;
+    p.lambda_scale = lambda_scale; p.lambda_velocity = lambda_velocity;
+    p.acc = static_cast<double*>(scratch);
+    p.d_pred = d_pred;
+    const int frames = B * T;
+    pose_loss_kernel<<<(frames + 7) / 8, 256, 0, st>>>(p);
+    LAUNCH_CHECK("pose_loss_kernel");
+    pose_loss_finalize_kernel<<<1, 32, 0, st>>>(p.acc, B, T, J, conf != nullptr, lambda_scale, lambda_velocity, losses);
+    LAUNCH_CHECK("pose_loss_finalize_kernel");
     return MB_OK;
 }
