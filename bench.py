@@ -192,6 +192,7 @@ def run_train(args, device, world, rank, local_rank, dist, D):
     """SURVEY.md 8d config 3 (N=1) / config 4 (N>1): one pretrain step = forward (saved residual stream) -> MPJPE loss
     -> native backward -> gradient all-reduce over the ranks (N>1) -> fused AdamW -> weight re-pack at the next forward.
     Supplementary to the headline forward line (BASELINE's metric); printed with the same keys."""
+    from motionbert_b200.loss import pretrain_loss_3d
     model = build_model(args.model, device, args.math).train()
     cfg = MODELS[args.model]
     hidden = int(cfg["dim_feat"] * cfg["mlp_ratio"])
@@ -210,7 +211,8 @@ def run_train(args, device, world, rank, local_rank, dist, D):
     def step(x, gt):
         opt.zero_grad(set_to_none=True)
         pred = model(x)
-        loss = torch.linalg.vector_norm(pred - gt, dim=-1).mean()          # loss_mpjpe, lib/model/loss.py:7-13
+        # loss_mpjpe + 0.5 n_mpjpe + 20 loss_velocity (train.py:178-191, MB_pretrain.yaml:39-44), fused with its gradient
+        loss, _parts = pretrain_loss_3d(pred, gt, 0.5, 20.0)
         loss.backward()
         if world > 1:
             D.allreduce_gradients(params, world)
@@ -255,7 +257,7 @@ def run_train(args, device, world, rank, local_rank, dist, D):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.math == "bf16" else "bf16x3 forward / bf16 backward", "data": "synthetic",
         "config": {"workload": f"SURVEY 8d config {'3' if world == 1 else '4'}: DSTformer-{args.model} pretrain step, B={B} per GPU, "
-                               f"T={T}, MPJPE loss, native backward (bf16 single-pass), fused AdamW", "global_batch": world * B,
+                               f"T={T}, fused pretrain loss (mpjpe + 0.5 n_mpjpe + 20 velocity), native backward (bf16 single-pass), fused AdamW", "global_batch": world * B,
                    "seq_len": T, "parallelism": f"dp{world}" + (" + one flat fp32 gradient all-reduce per step (NCCL)" if world > 1 else ""),
                    "l2": "activations >> 126 MB L2, no flush needed", "grad_allreduce_elems": n_param if world > 1 else 0},
         "clocks": clocks,
