@@ -114,7 +114,6 @@ class DSTformerFunction(torch.autograd.Function):
             g = grad.contiguous().float()
             grads = ctx.mod._launch_backward(x, rep, ctx.saved_region, None if ctx.return_rep else g,
                                              g if ctx.return_rep else None)
-            ctx.saved_region = None
             gp = [gr if ctx.needs_input_grad[4 + i] else None for i, gr in enumerate(grads)]
             return (None, None, None, None, *gp)
         x, *params = ctx.saved_tensors

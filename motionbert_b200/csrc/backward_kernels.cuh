@@ -53,11 +53,7 @@ __global__ void __launch_bounds__(256) gelu_plane_kernel(const __nv_bfloat16* __
 }
 
 // d/dx [x Phi(x)] = Phi(x) + x phi(x)
-__device__ __forceinline__ float gelu_grad(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.3989422804014327f * ex2_approx(-0.5f * x * x * 1.4426950408889634f);
-    return fmaf(x, pdf, cdf);
-}
+__device__ __forceinline__ float gelu_grad(float x) { return gelu_grad_fast(x); }
 // dh_pre = dh * gelu'(h_pre):  dh fp32 (dgrad output), h_pre bf16 -> dh_pre bf16 plane
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ dh, const __nv_bfloat16* __restrict__ hpre,
                                                         size_t n8, __nv_bfloat16* __restrict__ dhpre) {

@@ -25,7 +25,10 @@
 namespace mb {
 
 enum : int { EPI_LN_SPLIT = 0, EPI_LN_GELU_SPLIT = 1, EPI_RESID = 2, EPI_LN_TANH_F32 = 3, EPI_BIAS_F32 = 4,
-              EPI_BIAS_SPLIT = 5 /* y = acc + b[n] -> bf16 planes; 2-CTA kernel only (backward recompute / dgrad) */ };
+              EPI_BIAS_SPLIT = 5,      /* y = acc + b[n] -> bf16 plane                          (backward: qkv recompute, dgrad) */
+              EPI_BIAS_GELU_PAIR = 6,  /* plane 0 = y = acc + b[n], plane 1 = gelu(y)             (backward: fc1 recompute)         */
+              EPI_GELUBWD_SPLIT = 7    /* y = acc * gelu'(aux[m, n]) -> bf16 plane                (backward: fc2 dgrad -> d h_pre)  */
+};                                     /* 5..7 exist in the 2-CTA kernel only */
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
@@ -49,6 +52,7 @@ struct GemmParams {
     __nv_bfloat16* out_hi;    // split outputs [M,N]
     __nv_bfloat16* out_lo;    // may be null when PASSES == 1
     float* stats_out;         // RESID: [M][N/128][3]
+    const __nv_bfloat16* aux; // GELUBWD: pre-activation plane [M,N] (bf16)
 };
 
 template <int PASSES>
@@ -80,6 +84,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
     poly *= t;
     const float q = 0.5f * poly * ex2_approx(-z * z * 1.4426950408889634f);   // 0.5 * erfc(|z|)
     return x * (x >= 0.f ? 1.0f - q : q);
+}
+
+// d/dx [x Phi(x)] = Phi(x) + x phi(x), with Phi from the same erfc polynomial and phi from the SAME exponential
+// (exp(-z^2) with z = |x|/sqrt(2) is exp(-x^2/2)): one MUFU.RCP + one MUFU.EX2.
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float e = ex2_approx(-z * z * 1.4426950408889634f);   // exp(-x^2 / 2)
+    const float q = 0.5f * poly * e;                              // 0.5 * erfc(|z|)
+    return fmaf(x, 0.3989422804014327f * e, x >= 0.f ? 1.0f - q : q);
 }
 
 // Combine per-group partial statistics (Chan et al.) -> mean, rstd of a row.

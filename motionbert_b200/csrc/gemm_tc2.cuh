@@ -59,7 +59,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     constexpr int G2_STAGES = Cfg::STAGES;
     constexpr bool kResid = (EPI == EPI_RESID);
     constexpr bool kF32Out = (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32);
-    constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT);
+    constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT ||
+                                EPI == EPI_BIAS_GELU_PAIR || EPI == EPI_GELUBWD_SPLIT);
+    constexpr bool kTwoPlanes = (PASSES == 3) || (EPI == EPI_BIAS_GELU_PAIR);   // second bf16 plane: lo, or gelu(y)
     constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32);
 
     extern __shared__ uint8_t smem_raw[];
@@ -280,7 +282,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         st_sum += d;
                         st_sq = fmaf(d, d, st_sq);
                     }
-                } else if (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_SPLIT) {
+                } else if (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_SPLIT || EPI == EPI_BIAS_GELU_PAIR) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -289,6 +291,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
                         v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
                         v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+                    }
+                } else if (EPI == EPI_GELUBWD_SPLIT) {
+                    // d h_pre = d h * gelu'(h_pre): my row's 32 pre-activations (64 contiguous bytes) straight from global
+                    uint4 a[4];
+                    if (row_ok) {
+                        const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.N + col0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a[i] = __ldg(a4 + i);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a[i] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t w[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[8 * i + 2 * e] = __uint_as_float(r[8 * i + 2 * e]) * gelu_grad_fast(__uint_as_float(w[e] << 16));
+                            v[8 * i + 2 * e + 1] = __uint_as_float(r[8 * i + 2 * e + 1]) * gelu_grad_fast(__uint_as_float(w[e] & 0xffff0000u));
+                        }
                     }
                 } else {
                     const float4* c4 = reinterpret_cast<const float4*>(p.vec0 + col0);
@@ -326,12 +348,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 if (do_split) {                                                        // only the fp32 fusion kernel
                     uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                    for (int i = 0; i < 16; ++i) {
+                        if (EPI == EPI_BIAS_GELU_PAIR) {
+                            const __nv_bfloat162 y2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            const __nv_bfloat162 g2 = __floats2bfloat162_rn(gelu_erf(v[2 * i]), gelu_erf(v[2 * i + 1]));
+                            hi[i] = *reinterpret_cast<const uint32_t*>(&y2);
+                            lo[i] = *reinterpret_cast<const uint32_t*>(&g2);
+                        } else {
+                            split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         *reinterpret_cast<uint4*>(ss + lane * 64 + ((i ^ sw64) << 4)) =
                             make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                        if (PASSES == 3)
+                        if (kTwoPlanes)
                             *reinterpret_cast<uint4*>(ss + 2048 + lane * 64 + ((i ^ sw64) << 4)) =
                                 make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
                     }

@@ -160,6 +160,8 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, false>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, true>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_GELU_PAIR, false>, Gemm2Cfg<1, EPI_BIAS_GELU_PAIR>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_GELUBWD_SPLIT, true>, Gemm2Cfg<1, EPI_GELUBWD_SPLIT>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_q_kernel<64, false>, AttnBwdCfg<64>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_q_kernel<32, false>, AttnBwdCfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_kv_kernel<64, false>, AttnBwdCfg<64>::SMEM_BYTES));
@@ -1556,14 +1558,17 @@ static int make_plane_a_tmap(CUtensorMap* out, const __nv_bfloat16* base, uint64
 }
 
 // out[M, ncols] = A[M, kc] (bf16 plane) x W (K-major [ncols, kc] or, BMN, MN-major [kc, ncols]) + bias[ncols]
+//   EPI_BIAS_GELU_PAIR: second output plane gelu(out) at out_plane + pair_stride_el;  EPI_GELUBWD_SPLIT: aux = h_pre
 template <int EPI, bool BMN>
 static int bwd_gemm(const DevInfo& dev, const __nv_bfloat16* A, int M, int kc, int ncols, const CUtensorMap& tmB,
-                    const float* bias, float* out_f32, __nv_bfloat16* out_plane, cudaStream_t st) {
+                    const float* bias, float* out_f32, __nv_bfloat16* out_plane, cudaStream_t st,
+                    size_t pair_stride_el = 0, const __nv_bfloat16* aux = nullptr) {
     if (kc % 64 || ncols % 256) return fail(MB_ERR_INVALID, "internal: backward GEMM shape kc=%d ncols=%d", kc, ncols);
     CUtensorMap tmA, tmO;
     int rc;
     if ((rc = make_plane_a_tmap(&tmA, A, M, kc))) return rc;
     if (EPI == EPI_BIAS_F32) rc = make_f32_tile_tmap(&tmO, out_f32, M, ncols);
+    else if (EPI == EPI_BIAS_GELU_PAIR) rc = make_split_store_tmap(&tmO, out_plane, M, ncols, pair_stride_el, 3);
     else rc = make_split_store_tmap(&tmO, out_plane, M, ncols, static_cast<uint64_t>(M) * ncols, 1);
     if (rc) return rc;
     GemmParams p;
@@ -1572,6 +1577,7 @@ static int bwd_gemm(const DevInfo& dev, const __nv_bfloat16* A, int M, int kc, i
     p.vec0 = bias;
     p.out_f32 = out_f32;
     p.out_hi = out_plane;
+    p.aux = aux;
     p.J = 1;
     const int tiles = ((M + 255) / 256) * (ncols / 256);
     const int grid = 2 * (tiles < dev.sms / 2 ? tiles : dev.sms / 2);
@@ -1710,25 +1716,19 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
         LAUNCH_CHECK("ln_bwd_finalize_kernel");
         return MB_OK;
     };
-    const size_t n8_hid = M_ * hid / 8;
     // MLP sublayer  y = x + fc2(gelu(fc1(LN(x))))   (DSTformer.py:242,244,247,249), x in `slot`, dy in g[g_in] -> dx in g[g_out]
     auto mlp_backward = [&](const LinearPack* L, bool temporal, int slot, int g_in, const float* extra, int g_out) -> int {
         const LinearPack& L1 = L[temporal ? L_FC1_T : L_FC1_S];
         const LinearPack& L2 = L[temporal ? L_FC2_T : L_FC2_S];
         int r;
         if ((r = make_xhat(slot))) return r;
-        // recompute h_pre = xhat W1'^T + c1 and h = gelu(h_pre)
-        if ((r = bwd_gemm<EPI_BIAS_SPLIT, false>(di, xhat, M, C, hid, L1.tmap_k1, reinterpret_cast<const float*>(pk + L1.off_c),
-                                                 nullptr, wide[0], st))) return r;
-        gelu_plane_kernel<<<static_cast<unsigned>((n8_hid + 255) / 256), 256, 0, st>>>(wide[0], n8_hid, wide[1]);
-        LAUNCH_CHECK("gelu_plane_kernel");
-        // fc2: dW2 += dy^T h ; db2 += sum dy ; dh = dy W2
+        // recompute h_pre = xhat W1'^T + c1 and h = gelu(h_pre): one GEMM, two bf16 planes out of the same epilogue
+        if ((r = bwd_gemm<EPI_BIAS_GELU_PAIR, false>(di, xhat, M, C, hid, L1.tmap_k1, reinterpret_cast<const float*>(pk + L1.off_c),
+                                                     nullptr, wide[0], st, static_cast<size_t>(wide[1] - wide[0])))) return r;
+        // fc2: dW2 += dy^T h ; db2 += sum dy ; d h_pre = (dy W2) * gelu'(h_pre)  (GELU' applied in the dgrad epilogue)
         if ((r = bwd_wgrad(di, g_p[g_in], C, wide[1], hid, M, G(L2, 0), st))) return r;
         if ((r = colsum_f32(g_x[g_in], C, G(L2, 1)))) return r;
-        if ((r = bwd_gemm<EPI_BIAS_SPLIT, true>(di, g_p[g_in], M, C, hid, L2.tmap_mn, zero, nullptr, wide[2], st))) return r;
-        // dh_pre = dh * gelu'(h_pre)   (in place over dh)
-        gelu_bwd_plane_kernel<<<static_cast<unsigned>((n8_hid + 255) / 256), 256, 0, st>>>(wide[2], wide[0], n8_hid, wide[2]);
-        LAUNCH_CHECK("gelu_bwd_plane_kernel");
+        if ((r = bwd_gemm<EPI_GELUBWD_SPLIT, true>(di, g_p[g_in], M, C, hid, L2.tmap_mn, zero, nullptr, wide[2], st, 0, wide[0]))) return r;
         if ((r = ln_linear_backward(L1, wide[2]))) return r;
         return finalize(slot, g_in, extra, g_out);
     };

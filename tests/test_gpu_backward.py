@@ -177,3 +177,28 @@ def test_backward_error_paths(cuda_device):
     rc = lib.mb_forward_train(st.handle, m._aligned_ptr(st.packed), x.data_ptr(), None, rep.data_ptr(),
                               m._aligned_ptr(saved), 1024, m._aligned_ptr(saved), 1 << 30, 1, 4, 0, None)
     assert rc < 0 and b"saved region" in lib.mb_last_error()
+
+
+def test_frozen_parameters_and_retain_graph(cuda_device):
+    """partial_train (lib/utils/learning.py:69-77) freezes subsets of the backbone: frozen tensors must get no .grad,
+    the others the same gradient as before; backward(retain_graph=True) may be called twice on one forward."""
+    m = _module(cuda_device, 256, 1, 8, 2, seed=6)
+    x = torch.from_numpy(O.make_input(2, 8, 17, 4)).to(cuda_device)
+    (m(x) ** 2).sum().backward()
+    full = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    frozen = [n for n, _ in m.named_parameters() if "attn_t" in n or n == "pos_embed"]
+    for n, p in m.named_parameters():
+        p.requires_grad_(n not in frozen)
+    out = m(x)
+    loss = (out ** 2).sum()
+    loss.backward(retain_graph=True)
+    for n, p in m.named_parameters():
+        if n in frozen:
+            assert p.grad is None, n
+        else:
+            assert torch.allclose(p.grad, full[n], rtol=1e-3, atol=1e-5 * float(full[n].abs().max()) + 1e-12), n
+    loss.backward()                                   # second pass over the same saved activations: accumulates
+    n0 = "blocks_st.0.mlp_s.fc1.weight"
+    g = dict(m.named_parameters())[n0].grad
+    assert torch.allclose(g, 2 * full[n0], rtol=1e-3, atol=1e-5 * float(full[n0].abs().max()))
