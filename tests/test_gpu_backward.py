@@ -94,6 +94,8 @@ CASES = [
     ("lite_d2_f9", 256, 2, 8, 2, 2, 9),          # head_dim 32, packed temporal attention (F <= 32)
     ("lite_d2_f40", 256, 2, 8, 4, 3, 40),        # head_dim 32, one-sequence temporal tiles
     ("base_d1_f243", 512, 1, 8, 4, 1, 243),      # head_dim 64, two query tiles per sequence (BASELINE length)
+    ("base_full_f81", 512, 5, 8, 2, 2, 81),      # the shipped DSTformer-base (depth 5, mlp_ratio 2): 260 tensors
+    ("lite_full_f27", 256, 5, 8, 4, 2, 27),      # the shipped DSTformer-Lite (depth 5, mlp_ratio 4), packed temporal
 ]
 
 
