@@ -22,14 +22,23 @@ namespace mb {
 
 constexpr int G2_STAGES_RESID = 4;   // residual epilogue needs 12 KB staging per warp
 constexpr int G2_STAGES_OTHER = 5;   // split-only / fp32-only epilogues need 8 KB -> one more operand stage
-constexpr int G2_THREADS = 320;
+constexpr int G2_THREADS = 320;        // default: 8 epilogue warps
 constexpr int G2_EPI_WARPS = 8;
-constexpr int G2_EPI_THREADS_PAIR = 2 * G2_EPI_WARPS * 32;   // arrivals on the leader's tmem-empty barrier
+// Single-pass (bf16) GEMMs have a 3x shorter mainloop per tile and ncu showed their epilogue to be LATENCY-bound
+// (tensor pipe 32-48 % active, issue slots 24-46 %): the bf16-plane epilogues can therefore run with 16 epilogue
+// warps (EW = 16: each warp owns 32 rows x 64 columns, 4 warps per scheduler hide tcgen05.ld / MUFU / TMA-store
+// latency; no register double-buffering at the 112-register cap of 576 threads).
+constexpr int g2_threads(int ew) { return (2 + ew) * 32; }
 
-template <int PASSES, int EPI>
+template <int PASSES, int EPI, int EW = G2_EPI_WARPS>
 struct Gemm2Cfg {
     static constexpr int STAGES = (EPI == EPI_RESID) ? G2_STAGES_RESID : G2_STAGES_OTHER;
-    static constexpr int STAGING_PER_WARP = (EPI == EPI_RESID) ? 12288 : 8192;   // buf0 4 KB | buf1 4 KB | [split 4 KB]
+    // 8 warps: buf0 4 KB | buf1 4 KB | [split 4 KB].  16 warps (bf16-plane outputs only): one 2 KB plane tile per
+    // buffer, double-buffered (4 KB), or -- two output planes -- a single 4 KB buffer
+    static constexpr bool TWO_PLANES = (PASSES == 3) || (EPI == EPI_BIAS_GELU_PAIR);
+    static constexpr int NBUF = (EW == 16 && TWO_PLANES) ? 1 : 2;
+    static constexpr int BUF_BYTES = (EW == 16 && !TWO_PLANES) ? 2048 : 4096;
+    static constexpr int STAGING_PER_WARP = (EPI == EPI_RESID) ? 12288 : NBUF * BUF_BYTES;
     static constexpr int BK = (PASSES == 3) ? 32 : 64;
     static constexpr int SWZ = BK * 2;
     static constexpr uint32_t LAYOUT = (SWZ == 128) ? 2u : 4u;
@@ -40,28 +49,32 @@ struct Gemm2Cfg {
     static constexpr int B_BYTES = PLANES * B_PLANE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB
     static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_STAGING + G2_EPI_WARPS * STAGING_PER_WARP;
+    static constexpr int OFF_BAR = OFF_STAGING + EW * STAGING_PER_WARP;
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 };
 
 // B_MN = true is the data-gradient form  dX[M, Kf] = G[M, Nf] * W[Nf, Kf]  (backward groundwork, row a15): the
 // contraction runs over W's ROW index, so the very same packed W planes are consumed as an MN-major B operand
 // (64-column SWIZZLE_128B blocks, LBO = block stride) instead of packing a transposed copy of every weight.
-template <int PASSES, int EPI, bool B_MN = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+template <int PASSES, int EPI, bool B_MN = false, int EW = G2_EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EW), 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane), box (BK, 128, PLANES)
              const __grid_constant__ CUtensorMap tmB,   // bf16 3D (K, N, plane), box (BK, 128, PLANES); B_MN: (Kf, Nf, plane), box (64, BK, 1)
              const __grid_constant__ CUtensorMap tmR,   // fp32 2D (N, M) residual,    box (32, 32)         [RESID]
              const __grid_constant__ CUtensorMap tmX,   // fp32 2D (N, M) output,      box (32, 32)         [RESID/F32]
              const __grid_constant__ CUtensorMap tmS,   // bf16 3D (N, M, plane) out,  box (32, 32, PLANES) [RESID/SPLIT]
              const GemmParams p) {
-    using Cfg = Gemm2Cfg<PASSES, EPI>;
+    using Cfg = Gemm2Cfg<PASSES, EPI, EW>;
     constexpr int G2_STAGES = Cfg::STAGES;
+    static_assert(EW == 8 || (EW == 16 && PASSES == 1 && (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT ||
+                                                          EPI == EPI_BIAS_GELU_PAIR || EPI == EPI_GELUBWD_SPLIT)),
+                  "16 epilogue warps: single-pass bf16-plane epilogues only");
     constexpr bool kResid = (EPI == EPI_RESID);
     constexpr bool kF32Out = (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32);
     constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT ||
                                 EPI == EPI_BIAS_GELU_PAIR || EPI == EPI_GELUBWD_SPLIT);
-    constexpr bool kTwoPlanes = (PASSES == 3) || (EPI == EPI_BIAS_GELU_PAIR);   // second bf16 plane: lo, or gelu(y)
+    constexpr bool kTwoPlanes = Cfg::TWO_PLANES;                                  // second bf16 plane: lo, or gelu(y)
+    constexpr bool kDoubleLd = !kResid && EW == 8;                               // register double-buffered tcgen05.ld
     constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32);
 
     extern __shared__ uint8_t smem_raw[];
@@ -70,9 +83,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     uint64_t* full_bar = bars;                             // [STAGES] leader's is the one in use
     uint64_t* empty_bar = bars + G2_STAGES;                // [STAGES] per CTA, multicast-committed by the leader
     uint64_t* tfull_bar = bars + 2 * G2_STAGES;            // [2]      per CTA, multicast-committed by the leader
-    uint64_t* tempty_bar = bars + 2 * G2_STAGES + 2;       // [2]      leader's: 512 epilogue threads of the pair
+    uint64_t* tempty_bar = bars + 2 * G2_STAGES + 2;       // [2]      leader's: all epilogue threads of the pair
     uint64_t* rbar = bars + 2 * G2_STAGES + 4;             // [8 warps][2] residual-tile landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + 2 * G2_EPI_WARPS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + 2 * EW);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -97,9 +110,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], G2_EPI_THREADS_PAIR);
+            mbar_init(&tempty_bar[i], 2 * EW * 32);
         }
-        for (int i = 0; i < 2 * G2_EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
+        for (int i = 0; i < 2 * EW; ++i) mbar_init(&rbar[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
@@ -188,10 +201,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         // ------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
         const int ew = warp - 2;
         const int quad = warp & 3;
-        const int half = ew >> 2;
-        constexpr int NCH = 4;
+        const int half = ew >> 2;                      // column group of this warp: 128 columns (EW = 8) / 64 (EW = 16)
+        constexpr int NCH = 32 / EW;                   // 32-column chunks per warp per tile: 4 / 2
+        constexpr int COLS_PER_WARP = NCH * 32;
         uint8_t* stg = smem + Cfg::OFF_STAGING + ew * Cfg::STAGING_PER_WARP;
-        uint8_t* buf[2] = {stg, stg + 4096};
+        uint8_t* buf[2] = {stg, stg + (Cfg::NBUF == 2 ? Cfg::BUF_BYTES : 0)};
         uint8_t* bufS = stg + 8192;   // only exists (and is only used) for EPI_RESID
         uint64_t* my_rbar = rbar + 2 * ew;
         const int ngrp_out = p.N / STATS_GROUP;
@@ -200,7 +214,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 
         auto chunk_coords = [&](int tile, int ch, int& col0, int& rowb) {
             const int m_pair = tile / num_n, n_idx = tile % num_n;
-            col0 = n_idx * 256 + half * 128 + ch * 32;
+            col0 = n_idx * 256 + half * COLS_PER_WARP + ch * 32;
             rowb = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32;
         };
         uint32_t ci = 0;   // chunks processed by this warp (buffer parity / rbar phase)
@@ -229,8 +243,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * 256 + half * 128 + (static_cast<uint32_t>(quad * 32) << 16);
-            uint32_t racc[kResid ? 1 : 2][32];
+            const uint32_t t_row = tmem_base + acc * 256 + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+            uint32_t racc[kDoubleLd ? 2 : 1][32];
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch, ++ci) {
                 const int b = ci & 1;
@@ -249,13 +263,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                             tma_load_2d(buf[b ^ 1], &tmR, &my_rbar[b ^ 1], c1, r1);
                         }
                     }
-                } else {
+                } else if (Cfg::NBUF == 2) {
                     if (lane == 0) tma_store_wait_read<1>();           // group ci-2 no longer reads buf[b]
+                } else {
+                    if (lane == 0) tma_store_wait_read<0>();           // single staging buffer: previous store has read it
                 }
                 // non-residual epilogues double-buffer the accumulator chunk: tcgen05.ld of chunk ch+1 is in flight while
                 // chunk ch is processed (the residual variant has no registers to spare at 10 warps / 168 registers)
-                uint32_t (&r)[32] = racc[kResid ? 0 : (ch & 1)];
-                if (kResid) {
+                uint32_t (&r)[32] = racc[kDoubleLd ? (ch & 1) : 0];
+                if (!kDoubleLd) {
                     tmem_ld32(t_row + ch * 32, r);
                     tmem_ld_wait();
                 } else {

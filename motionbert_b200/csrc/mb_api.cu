@@ -158,10 +158,13 @@ static int device_init(int* dev_out, DevInfo* info_out) {
 #undef SET_GEMM2
         CUDA_TRY(set_smem(gemm2_kernel<3, EPI_BIAS_F32, true>, Gemm2Cfg<3, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
-        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, false>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
-        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, true>, Gemm2Cfg<1, EPI_BIAS_SPLIT>::SMEM_BYTES));
-        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_GELU_PAIR, false>, Gemm2Cfg<1, EPI_BIAS_GELU_PAIR>::SMEM_BYTES));
-        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_GELUBWD_SPLIT, true>, Gemm2Cfg<1, EPI_GELUBWD_SPLIT>::SMEM_BYTES));
+        // single-pass bf16-plane epilogues run with 16 epilogue warps (gemm_tc2.cuh)
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, false, 16>, Gemm2Cfg<1, EPI_BIAS_SPLIT, 16>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_SPLIT, true, 16>, Gemm2Cfg<1, EPI_BIAS_SPLIT, 16>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_GELU_PAIR, false, 16>, Gemm2Cfg<1, EPI_BIAS_GELU_PAIR, 16>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_GELUBWD_SPLIT, true, 16>, Gemm2Cfg<1, EPI_GELUBWD_SPLIT, 16>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_LN_SPLIT, false, 16>, Gemm2Cfg<1, EPI_LN_SPLIT, 16>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_LN_GELU_SPLIT, false, 16>, Gemm2Cfg<1, EPI_LN_GELU_SPLIT, 16>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_q_kernel<64, false>, AttnBwdCfg<64>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_q_kernel<32, false>, AttnBwdCfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_bwd_kv_kernel<64, false>, AttnBwdCfg<64>::SMEM_BYTES));
@@ -640,10 +643,11 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
         ((EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) && !em.out_s) ||
         ((EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32) && !em.out_x))
         return fail(MB_ERR_INVALID, "internal: missing epilogue tensor map");
+    constexpr int EW1 = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) ? 16 : 8;   // single-pass epilogue warps
     if (passes == 3)
         gemm2_kernel<3, EPI><<<grid, G2_THREADS, Gemm2Cfg<3, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else
-        gemm2_kernel<1, EPI><<<grid, G2_THREADS, Gemm2Cfg<1, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
+        gemm2_kernel<1, EPI, false, EW1><<<grid, g2_threads(EW1), Gemm2Cfg<1, EPI, EW1>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     LAUNCH_CHECK("gemm2_kernel");
     return MB_OK;
 }
@@ -1261,7 +1265,8 @@ extern "C" int mb_test_wgrad(int math, int M, int N, int K, const float* G, cons
     }
     CUtensorMap tmG, tmX;
     {
-        const uint32_t box[3] = {64, WG_BT, 1};
+        const int WG_BT = passes == 3 ? WgBt<3>::value : WgBt<1>::value;
+        const uint32_t box[3] = {64, static_cast<uint32_t>(WG_BT), 1};
         const uint64_t dG[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 2};
         const uint64_t sG[2] = {static_cast<uint64_t>(N), g_plane / 2};
         if ((rc = make_tmap(&tmG, g_hi, 3, dG, sG, box, 128))) return rc;
@@ -1275,6 +1280,7 @@ extern "C" int mb_test_wgrad(int math, int M, int N, int K, const float* G, cons
     const int tiles = (N / 128) * (K / 256);
     int splits = info.sms / tiles;
     if (splits < 1) splits = 1;
+    const int WG_BT = passes == 3 ? WgBt<3>::value : WgBt<1>::value;
     const int max_splits = (M + WG_BT - 1) / WG_BT;
     if (splits > max_splits) splits = max_splits;
     wp.tokens_per_split = static_cast<int>(align_up((static_cast<size_t>(M) + splits - 1) / splits, WG_BT));
@@ -1581,7 +1587,8 @@ static int bwd_gemm(const DevInfo& dev, const __nv_bfloat16* A, int M, int kc, i
     p.J = 1;
     const int tiles = ((M + 255) / 256) * (ncols / 256);
     const int grid = 2 * (tiles < dev.sms / 2 ? tiles : dev.sms / 2);
-    gemm2_kernel<1, EPI, BMN><<<grid, G2_THREADS, Gemm2Cfg<1, EPI>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmO, tmO, p);
+    constexpr int EW = (EPI == EPI_BIAS_F32) ? 8 : 16;
+    gemm2_kernel<1, EPI, BMN, EW><<<grid, g2_threads(EW), Gemm2Cfg<1, EPI, EW>::SMEM_BYTES, st>>>(tmA, tmB, tmA, tmO, tmO, p);
     LAUNCH_CHECK("gemm2_kernel<backward>");
     return MB_OK;
 }
@@ -1592,6 +1599,7 @@ static int bwd_wgrad(const DevInfo& dev, const __nv_bfloat16* G, int N, const __
     if (N % 128 || K % 256) return fail(MB_ERR_INVALID, "internal: wgrad shape N=%d K=%d", N, K);
     CUtensorMap tmG, tmX;
     int rc;
+    constexpr int WG_BT = WgBt<1>::value;
     const uint32_t box[3] = {64, WG_BT, 1};
     const uint64_t dG[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 1};
     const uint64_t sG[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M) * N};

@@ -15,33 +15,39 @@
 namespace mb {
 
 constexpr int WG_THREADS = 192;   // w0 TMA, w1 MMA, w2..w5 epilogue (TMEM lane quadrant = warp % 4)
-constexpr int WG_BT = 32;         // tokens per pipeline stage (2 K-steps of 16)
 constexpr int WG_STAGES = 4;
+// tokens per pipeline stage: 64 in single-pass mode (48 KB per stage, 192 KB in flight -- with 32-token stages the
+// 4-deep ring held only ~1000 MMA-cycles of work, less than one TMA round trip: ncu showed the tensor pipe 49 % active),
+// 32 in BF16x3 mode (two planes per operand)
+template <int PASSES>
+struct WgBt { static constexpr int value = (PASSES == 3) ? 32 : 64; };
 
 struct WgradParams {
     int M, N, K;
-    int tokens_per_split;   // multiple of WG_BT
+    int tokens_per_split;   // multiple of the stage size WgBt<PASSES>::value
     float* dW;              // [N, K] fp32, accumulated with atomics
 };
 
 template <int PASSES>
 struct WgradCfg {
     static constexpr int PLANES = (PASSES == 3) ? 2 : 1;
-    static constexpr int BLK = WG_BT * 128;                    // one 64-element MN block: [32 token rows][128 B] = 4 KB
+    static constexpr int BT = WgBt<PASSES>::value;
+    static constexpr int BLK = BT * 128;                       // one 64-element MN block: [BT token rows][128 B]
     static constexpr int A_PLANE = 2 * BLK;                    // 128 n  = 2 blocks
     static constexpr int B_PLANE = 4 * BLK;                    // 256 k  = 4 blocks
     static constexpr int A_BYTES = PLANES * A_PLANE;
     static constexpr int B_BYTES = PLANES * B_PLANE;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB (3 passes) / 24 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 48 KB in both modes
     static constexpr int SMEM_BYTES = WG_STAGES * STAGE_BYTES + 256 + 1024;
 };
 
 template <int PASSES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmG,   // bf16 3D (N, M, plane), box (64, WG_BT, 1)
-             const __grid_constant__ CUtensorMap tmX,   // bf16 3D (K, M, plane), box (64, WG_BT, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG,   // bf16 3D (N, M, plane), box (64, BT, 1)
+             const __grid_constant__ CUtensorMap tmX,   // bf16 3D (K, M, plane), box (64, BT, 1)
              const WgradParams p) {
     using Cfg = WgradCfg<PASSES>;
+    constexpr int WG_BT = Cfg::BT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * Cfg::STAGE_BYTES);
