@@ -4,8 +4,8 @@ Forward = the sm_100a CUDA library (`mb_forward`, or `mb_forward_train` when a g
 Backward = `mb_backward`: hand-written tcgen05 data-/weight-gradient GEMMs,
 attention-core backward and CUDA-core LayerNorm / GELU / fusion / embed kernels, bf16 single-pass arithmetic.
 `recompute_forward` below is a differentiable torch-op restatement kept for (a) the gradient-parity tests and
-(b) the configurations the native backward does not cover (DropPath rate > 0, input gradients): there the
-backward recomputes the chain with torch CUDA ops under autograd.  No forward / inference call uses it.
+(b) the rare configurations the native backward does not cover (no fusion head, dim_out > 8): there the backward
+recomputes the chain with torch CUDA ops under autograd.  No forward / inference call uses it.
 """
 from __future__ import annotations
 
@@ -87,8 +87,9 @@ def recompute_forward(mod, x, return_rep, dp_scale, P):
 
 class DSTformerFunction(torch.autograd.Function):
     """forward = mb_forward_train (or mb_forward), backward = mb_backward (hand-written sm_100a kernels).
-    Configurations the native backward does not cover (DropPath rate > 0, gradient w.r.t. the input, missing
-    fusion head) fall back to back-propagating through `recompute_forward` with torch CUDA ops."""
+    DropPath (per-frame scale vector) and the gradient w.r.t. the pose input are handled natively; configurations
+    the native backward does not cover (missing fusion head, dim_out > 8, non-fp32 parameters) fall back to
+    back-propagating through `recompute_forward` with torch CUDA ops."""
 
     @staticmethod
     def forward(ctx, mod, x, return_rep, dp_scale, *params):
@@ -98,7 +99,7 @@ class DSTformerFunction(torch.autograd.Function):
         ctx.native = mod._native_backward_ok(x, dp_scale)
         with torch.no_grad():
             if ctx.native:
-                out, rep, saved = mod._launch_train(x, not return_rep)
+                out, rep, saved = mod._launch_train(x, not return_rep, dp_scale)
                 ctx.saved_region = saved
                 ctx.save_for_backward(x, rep)
                 ctx.pack_versions = tuple(p._version for p in params)
@@ -112,10 +113,10 @@ class DSTformerFunction(torch.autograd.Function):
         if ctx.native:
             x, rep = ctx.saved_tensors
             g = grad.contiguous().float()
-            grads = ctx.mod._launch_backward(x, rep, ctx.saved_region, None if ctx.return_rep else g,
-                                             g if ctx.return_rep else None)
+            grads, d_x = ctx.mod._launch_backward(x, rep, ctx.saved_region, None if ctx.return_rep else g,
+                                                  g if ctx.return_rep else None, ctx.dp_scale, ctx.needs_input_grad[1])
             gp = [gr if ctx.needs_input_grad[4 + i] else None for i, gr in enumerate(grads)]
-            return (None, None, None, None, *gp)
+            return (None, d_x, None, None, *gp)
         x, *params = ctx.saved_tensors
         with torch.enable_grad():
             xs = x.detach().requires_grad_(ctx.needs_input_grad[1])

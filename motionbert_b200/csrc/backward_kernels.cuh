@@ -188,6 +188,48 @@ __global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __res
     }
 }
 
+// DropPath backward (lib/model/drop.py:17-32): the branch of a residual sublayer sees scale[frame] * dy
+template <int NV>
+__global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict__ g, const float* __restrict__ scale, int J,
+                                                          int M, int C, float* __restrict__ out,
+                                                          __nv_bfloat16* __restrict__ out_plane) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = lane_id();
+    const float sc = scale[row / J];
+    const size_t base = static_cast<size_t>(row) * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = 128 * i + 4 * lane;
+        float4 v = *reinterpret_cast<const float4*>(g + base + c);
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        *reinterpret_cast<float4*>(out + base + c) = v;
+        *reinterpret_cast<uint2*>(out_plane + base + c) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    }
+}
+
+// gradient w.r.t. the pose input: d x_in[m, k] = sum_c d x0[m, c] We[c, k]   (DSTformer.py:333)
+__global__ void __launch_bounds__(256) embed_dx_kernel(const float* __restrict__ dx0, const float* __restrict__ We, int M,
+                                                        int C, int dim_in, float* __restrict__ dxin) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = lane_id();
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float g = dx0[static_cast<size_t>(row) * C + c];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < dim_in) acc[k] = fmaf(g, We[static_cast<size_t>(c) * dim_in + k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float t = warp_sum(acc[k]);
+        if (lane == 0 && k < dim_in) dxin[static_cast<size_t>(row) * dim_in + k] = t;
+    }
+}
+
 // S/T fusion backward (DSTformer.py:343-349):  x = a0 x_st + a1 x_ts,  a = softmax([x_st, x_ts] Wa^T + ba)
 // One warp walks FUSE_ROWS consecutive token rows and keeps its share of dWa (2 logits x 2C columns) in registers;
 // the 8 warps of a CTA then merge through shared-memory atomics and issue ONE global atomic per dWa element per CTA.

@@ -1508,19 +1508,19 @@ extern "C" int mb_saved_bytes(const MbEncoder* enc, int B, int F, size_t* bytes)
 }
 
 extern "C" int mb_forward_train(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
-                                void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, int B, int F,
-                                uint32_t flags, void* stream_) {
+                                const float* drop_path_scale, void* saved, size_t saved_bytes, void* workspace,
+                                size_t workspace_bytes, int B, int F, uint32_t flags, void* stream_) {
     if (!enc || !saved || !rep) return fail(MB_ERR_NULL, "NULL argument (training forward needs saved and rep)");
     if (reinterpret_cast<uintptr_t>(saved) & 1023) return fail(MB_ERR_ALIGN, "saved region must be 1024-byte aligned");
     if (B < 1 || F < 1 || F > enc->d.maxlen) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d", B, F);
     const SavedLayout sl = saved_layout(enc->d, B, F);
     if (saved_bytes < sl.total) return fail(MB_ERR_WORKSPACE, "saved region %zu < required %zu", saved_bytes, sl.total);
-    return forward_impl(enc, packed, x, out, rep, nullptr, workspace, workspace_bytes, B, F, flags, stream_,
+    return forward_impl(enc, packed, x, out, rep, drop_path_scale, workspace, workspace_bytes, B, F, flags, stream_,
                         static_cast<uint8_t*>(saved));
 }
 
 struct BwdLayout {
-    size_t xhat, wide[3], o, d_o, g_x[3], g_p[3], dxhat, lse2, delta, dwp, dc, zero, drep, dz, total;
+    size_t xhat, wide[3], o, d_o, g_x[4], g_p[4], dxhat, lse2, delta, dwp, dc, zero, drep, dz, total;
     size_t wide_cols, max_n;
 };
 static BwdLayout bwd_layout(const MbDesc& d, int B, int F) {
@@ -1535,7 +1535,7 @@ static BwdLayout bwd_layout(const MbDesc& d, int B, int F) {
     for (int i = 0; i < 3; ++i) w.wide[i] = take(M * w.wide_cols * 2);
     w.o = take(M * C * 2);
     w.d_o = take(M * C * 2);
-    for (int i = 0; i < 3; ++i) { w.g_x[i] = take(M * C * 4); w.g_p[i] = take(M * C * 2); }
+    for (int i = 0; i < 4; ++i) { w.g_x[i] = take(M * C * 4); w.g_p[i] = take(M * C * 2); }   // [3]: DropPath-scaled copy
     w.dxhat = take(M * C * 4);
     w.lse2 = take(attn_bwd_stat_floats(B, F, d.num_joints, d.num_heads) * 4);
     w.delta = take(attn_bwd_stat_floats(B, F, d.num_joints, d.num_heads) * 4);
@@ -1621,9 +1621,9 @@ static int bwd_wgrad(const DevInfo& dev, const __nv_bfloat16* G, int N, const __
 }
 
 extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x_in,
-                           const float* rep, const void* saved_, size_t saved_bytes, const float* d_out,
-                           const float* d_rep, float* const* grads, void* workspace, size_t workspace_bytes, int B,
-                           int F, void* stream_) {
+                           const float* rep, const void* saved_, size_t saved_bytes, const float* drop_path_scale,
+                           const float* d_out, const float* d_rep, float* const* grads, float* d_x, void* workspace,
+                           size_t workspace_bytes, int B, int F, void* stream_) {
     if (!enc || !packed || !params || !x_in || !rep || !saved_ || !grads || !workspace)
         return fail(MB_ERR_NULL, "NULL argument");
     if (!d_out && !d_rep) return fail(MB_ERR_NULL, "both d_out and d_rep are NULL");
@@ -1665,9 +1665,9 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
     for (int i = 0; i < 3; ++i) wide[i] = reinterpret_cast<__nv_bfloat16*>(ws + wl.wide[i]);
     auto* o_pl = reinterpret_cast<__nv_bfloat16*>(ws + wl.o);
     auto* do_pl = reinterpret_cast<__nv_bfloat16*>(ws + wl.d_o);
-    float* g_x[3];
-    __nv_bfloat16* g_p[3];
-    for (int i = 0; i < 3; ++i) {
+    float* g_x[4];
+    __nv_bfloat16* g_p[4];
+    for (int i = 0; i < 4; ++i) {
         g_x[i] = reinterpret_cast<float*>(ws + wl.g_x[i]);
         g_p[i] = reinterpret_cast<__nv_bfloat16*>(ws + wl.g_p[i]);
     }
@@ -1725,18 +1725,28 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
         return MB_OK;
     };
     // MLP sublayer  y = x + fc2(gelu(fc1(LN(x))))   (DSTformer.py:242,244,247,249), x in `slot`, dy in g[g_in] -> dx in g[g_out]
-    auto mlp_backward = [&](const LinearPack* L, bool temporal, int slot, int g_in, const float* extra, int g_out) -> int {
+    // DropPath: the branch sees scale[frame] * dy (buffer 3), the residual path the unscaled dy
+    auto branch_grad = [&](int sub, int g_in, int* g_br) -> int {
+        *g_br = g_in;
+        if (!drop_path_scale) return MB_OK;
+        ROWK(scale_rows_kernel, g_x[g_in], drop_path_scale + static_cast<size_t>(sub) * B * F, J, M, C, g_x[3], g_p[3]);
+        LAUNCH_CHECK("scale_rows_kernel");
+        *g_br = 3;
+        return MB_OK;
+    };
+    auto mlp_backward = [&](const LinearPack* L, bool temporal, int slot, int sub, int g_in, const float* extra, int g_out) -> int {
         const LinearPack& L1 = L[temporal ? L_FC1_T : L_FC1_S];
         const LinearPack& L2 = L[temporal ? L_FC2_T : L_FC2_S];
-        int r;
+        int r, gb;
+        if ((r = branch_grad(sub, g_in, &gb))) return r;
         if ((r = make_xhat(slot))) return r;
         // recompute h_pre = xhat W1'^T + c1 and h = gelu(h_pre): one GEMM, two bf16 planes out of the same epilogue
         if ((r = bwd_gemm<EPI_BIAS_GELU_PAIR, false>(di, xhat, M, C, hid, L1.tmap_k1, reinterpret_cast<const float*>(pk + L1.off_c),
                                                      nullptr, wide[0], st, static_cast<size_t>(wide[1] - wide[0])))) return r;
         // fc2: dW2 += dy^T h ; db2 += sum dy ; d h_pre = (dy W2) * gelu'(h_pre)  (GELU' applied in the dgrad epilogue)
-        if ((r = bwd_wgrad(di, g_p[g_in], C, wide[1], hid, M, G(L2, 0), st))) return r;
-        if ((r = colsum_f32(g_x[g_in], C, G(L2, 1)))) return r;
-        if ((r = bwd_gemm<EPI_GELUBWD_SPLIT, true>(di, g_p[g_in], M, C, hid, L2.tmap_mn, zero, nullptr, wide[2], st, 0, wide[0]))) return r;
+        if ((r = bwd_wgrad(di, g_p[gb], C, wide[1], hid, M, G(L2, 0), st))) return r;
+        if ((r = colsum_f32(g_x[gb], C, G(L2, 1)))) return r;
+        if ((r = bwd_gemm<EPI_GELUBWD_SPLIT, true>(di, g_p[gb], M, C, hid, L2.tmap_mn, zero, nullptr, wide[2], st, 0, wide[0]))) return r;
         if ((r = ln_linear_backward(L1, wide[2]))) return r;
         return finalize(slot, g_in, extra, g_out);
     };
@@ -1768,19 +1778,20 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
     one_pass.device = enc->device;
     one_pass.dev = enc->dev;
     // attention sublayer  y = x + proj(attn(qkv(LN(x))))   (DSTformer.py:241,243,246,248)
-    auto attn_backward = [&](const LinearPack* L, bool temporal, int slot, int g_in, const float* extra, int g_out) -> int {
+    auto attn_backward = [&](const LinearPack* L, bool temporal, int slot, int sub, int g_in, const float* extra, int g_out) -> int {
         const LinearPack& Lq = L[temporal ? L_QKV_T : L_QKV_S];
         const LinearPack& Lp = L[temporal ? L_PROJ_T : L_PROJ_S];
-        int r;
+        int r, gb;
+        if ((r = branch_grad(sub, g_in, &gb))) return r;
         if ((r = make_xhat(slot))) return r;
         // recompute qkv = xhat Wq'^T + cq and the attention output O
         if ((r = bwd_gemm<EPI_BIAS_SPLIT, false>(di, xhat, M, C, 3 * C, Lq.tmap_k1, reinterpret_cast<const float*>(pk + Lq.off_c),
                                                  nullptr, wide[0], st))) return r;
         if ((r = launch_attn(&one_pass, 0u, temporal, AP, B, F, M_ * 3 * C, M_ * C, st))) return r;
         // proj: dWp += dy^T O ; dbp += sum dy ; dO = dy Wp
-        if ((r = bwd_wgrad(di, g_p[g_in], C, o_pl, C, M, G(Lp, 0), st))) return r;
-        if ((r = colsum_f32(g_x[g_in], C, G(Lp, 1)))) return r;
-        if ((r = bwd_gemm<EPI_BIAS_SPLIT, true>(di, g_p[g_in], M, C, C, Lp.tmap_mn, zero, nullptr, do_pl, st))) return r;
+        if ((r = bwd_wgrad(di, g_p[gb], C, o_pl, C, M, G(Lp, 0), st))) return r;
+        if ((r = colsum_f32(g_x[gb], C, G(Lp, 1)))) return r;
+        if ((r = bwd_gemm<EPI_BIAS_SPLIT, true>(di, g_p[gb], M, C, C, Lp.tmap_mn, zero, nullptr, do_pl, st))) return r;
         // attention core: (qkv, O, dO) -> dqkv
         if (temporal) r = launch_attn_bwd(di, B, F, J, C, H, scale, wide[0], o_pl, do_pl, lse2, delta, wide[1], st);
         else r = launch_attn_bwd(di, B * F, J, 1, C, H, scale, wide[0], o_pl, do_pl, lse2, delta, wide[1], st);
@@ -1824,16 +1835,17 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
             }
             LAUNCH_CHECK("fuse_bwd_kernel");
         }
-        // blocks_st[i] backward: T-mlp(in slot 3), T-attn(2), S-mlp(1), S-attn(0); gradient ping-pongs a <-> cur
-        if ((rc = mlp_backward(Lst, true, sb + 3, a, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lst, true, sb + 2, cur, nullptr, a))) return rc;
-        if ((rc = mlp_backward(Lst, false, sb + 1, a, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lst, false, sb + 0, cur, nullptr, a))) return rc;      // d X0 via the st stream in g[a]
-        // blocks_ts[i] backward: S-mlp(in slot 7), S-attn(6), T-mlp(5), T-attn(0); ping-pong b <-> cur, sum with g[a]
-        if ((rc = mlp_backward(Lts, false, sb + 7, b, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lts, false, sb + 6, cur, nullptr, b))) return rc;
-        if ((rc = mlp_backward(Lts, true, sb + 5, b, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lts, true, sb + 0, cur, g_x[a], b))) return rc;       // total d X0 in g[b]
+        // blocks_st[i] backward: T-mlp(in slot 3), T-attn(2), S-mlp(1), S-attn(0); gradient ping-pongs a <-> cur.
+        // DropPath sublayer indices follow the forward: blocks_st[i] = 8i + {0 S-attn, 1 S-mlp, 2 T-attn, 3 T-mlp}
+        if ((rc = mlp_backward(Lst, true, sb + 3, 8 * i + 3, a, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lst, true, sb + 2, 8 * i + 2, cur, nullptr, a))) return rc;
+        if ((rc = mlp_backward(Lst, false, sb + 1, 8 * i + 1, a, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lst, false, sb + 0, 8 * i + 0, cur, nullptr, a))) return rc;      // d X0 via the st stream in g[a]
+        // blocks_ts[i] = 8i + {4 T-attn, 5 T-mlp, 6 S-attn, 7 S-mlp}: S-mlp(in slot 7), S-attn(6), T-mlp(5), T-attn(0)
+        if ((rc = mlp_backward(Lts, false, sb + 7, 8 * i + 7, b, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lts, false, sb + 6, 8 * i + 6, cur, nullptr, b))) return rc;
+        if ((rc = mlp_backward(Lts, true, sb + 5, 8 * i + 5, b, nullptr, cur))) return rc;
+        if ((rc = attn_backward(Lts, true, sb + 0, 8 * i + 4, cur, g_x[a], b))) return rc;       // total d X0 in g[b]
         cur = b;
     }
     // ---- embed (DSTformer.py:333-337)
@@ -1841,6 +1853,10 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
         g_x[cur], x_in, d.dim_in, B, F, J, C, grads[enc->index.at("joints_embed.weight")],
         grads[enc->index.at("joints_embed.bias")], grads[enc->index.at("pos_embed")], grads[enc->index.at("temp_embed")]);
     LAUNCH_CHECK("embed_bwd_kernel");
+    if (d_x) {
+        embed_dx_kernel<<<rows_grid, 256, 0, st>>>(g_x[cur], params[enc->index.at("joints_embed.weight")], M, C, d.dim_in, d_x);
+        LAUNCH_CHECK("embed_dx_kernel");
+    }
     return MB_OK;
 }
 

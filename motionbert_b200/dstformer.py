@@ -298,15 +298,15 @@ class DSTformer(nn.Module):
 
     # ------------------------------------------------------------------ training (mb_forward_train / mb_backward)
     def _native_backward_ok(self, x: torch.Tensor, dp_scale) -> bool:
-        """The hand-written backward covers the configuration every reference training script uses: DropPath rate 0,
-        fusion head present, no gradient w.r.t. the pose input, fp32 contiguous parameters."""
-        if dp_scale is not None or x.requires_grad or os.environ.get("MB_TORCH_BACKWARD") == "1":
+        """The hand-written backward needs the fusion head, fp32 contiguous parameters on x's device and dim_out <= 8
+        (every configuration the reference's training scripts build); otherwise the torch-op fallback is used."""
+        if os.environ.get("MB_TORCH_BACKWARD") == "1":
             return False
         params = self._ordered_params()
         return all(p is not None and p.dtype == torch.float32 and p.is_contiguous() and p.device == x.device
                    for p in params) and self.dim_out <= 8
 
-    def _launch_train(self, x: torch.Tensor, want_out: bool):
+    def _launch_train(self, x: torch.Tensor, want_out: bool, dp_scale=None):
         """mb_forward_train on the current stream: returns (out, rep, saved) with `saved` the activation region."""
         device = x.device
         B, F, J, _ = x.shape
@@ -330,12 +330,13 @@ class DSTformer(nn.Module):
             rep = torch.empty(B, F, J, self.dim_rep, dtype=torch.float32, device=device)
             _lib.check(lib.mb_forward_train(
                 st.handle, self._aligned_ptr(st.packed), x.data_ptr(), out.data_ptr() if out is not None else None,
-                rep.data_ptr(), self._aligned_ptr(saved), saved.numel() - 1024, self._aligned_ptr(ws),
-                ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr), "mb_forward_train")
+                rep.data_ptr(), dp_scale.data_ptr() if dp_scale is not None else None, self._aligned_ptr(saved),
+                saved.numel() - 1024, self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr),
+                "mb_forward_train")
         return out, rep, saved
 
-    def _launch_backward(self, x, rep, saved, d_out, d_rep):
-        """mb_backward on the current stream: returns the parameter gradients in `_ordered_params()` order."""
+    def _launch_backward(self, x, rep, saved, d_out, d_rep, dp_scale=None, want_dx=False):
+        """mb_backward on the current stream: returns (parameter gradients in `_ordered_params()` order, d_x or None)."""
         device = x.device
         B, F, J, _ = x.shape
         lib = _lib.load()
@@ -358,12 +359,14 @@ class DSTformer(nn.Module):
                 off += n
             pp = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
             gp = (ctypes.c_void_p * len(params))(*[g.data_ptr() for g in grads])
+            d_x = torch.empty_like(x) if want_dx else None
             _lib.check(lib.mb_backward(
                 st.handle, self._aligned_ptr(st.packed), pp, x.data_ptr(), rep.data_ptr(), self._aligned_ptr(saved),
-                saved.numel() - 1024, d_out.data_ptr() if d_out is not None else None,
-                d_rep.data_ptr() if d_rep is not None else None, gp, self._aligned_ptr(bws), bws.numel() - 1024,
+                saved.numel() - 1024, dp_scale.data_ptr() if dp_scale is not None else None,
+                d_out.data_ptr() if d_out is not None else None, d_rep.data_ptr() if d_rep is not None else None, gp,
+                d_x.data_ptr() if d_x is not None else None, self._aligned_ptr(bws), bws.numel() - 1024,
                 B, F, stream_ptr), "mb_backward")
-        return grads
+        return grads, d_x
 
     def make_graphed(self, B: int, F: int, return_rep: bool = False):
         """CUDA-graph the inference forward for a fixed (B, F): returns `run(x) -> out` that copies x into a static

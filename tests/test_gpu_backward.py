@@ -38,9 +38,9 @@ def _module(dev, dim_feat, depth, heads, mlp_ratio, dim_rep=512, maxlen=243, see
     return m.to(dev).train()
 
 
-def _reference_grads(m, x, w_out, return_rep):
+def _reference_grads(m, x, w_out, return_rep, dp=None):
     ps = [p.detach().double().requires_grad_(True) for p in m._ordered_params()]
-    y = recompute_forward(m, x.double(), return_rep, None, ps)
+    y = recompute_forward(m, x.double(), return_rep, dp.double() if dp is not None else None, ps)
     loss = (y * w_out.double()).sum()
     grads = torch.autograd.grad(loss, ps, allow_unused=True)       # head.* is unused on the representation path
     return [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, ps)], y.detach()
@@ -176,7 +176,7 @@ def test_backward_error_paths(cuda_device):
     assert lib.mb_saved_bytes(st.handle, 1, 4, ctypes.byref(nb)) == 0 and nb.value > 0
     assert lib.mb_saved_bytes(st.handle, 1, 1000, ctypes.byref(nb)) < 0
     # too-small saved region is rejected before any launch
-    rc = lib.mb_forward_train(st.handle, m._aligned_ptr(st.packed), x.data_ptr(), None, rep.data_ptr(),
+    rc = lib.mb_forward_train(st.handle, m._aligned_ptr(st.packed), x.data_ptr(), None, rep.data_ptr(), None,
                               m._aligned_ptr(saved), 1024, m._aligned_ptr(saved), 1 << 30, 1, 4, 0, None)
     assert rc < 0 and b"saved region" in lib.mb_last_error()
 
@@ -204,3 +204,31 @@ def test_frozen_parameters_and_retain_graph(cuda_device):
     n0 = "blocks_st.0.mlp_s.fc1.weight"
     g = dict(m.named_parameters())[n0].grad
     assert torch.allclose(g, 2 * full[n0], rtol=1e-3, atol=1e-5 * float(full[n0].abs().max()))
+
+
+def test_native_backward_with_drop_path_and_input_gradient(cuda_device):
+    """DropPath (lib/model/drop.py:17-32: per-frame keep mask / keep_prob on every residual branch) and the gradient
+    w.r.t. the pose input, both through the native backward, against fp64 autograd with the SAME mask."""
+    from motionbert_b200._autograd import DSTformerFunction
+    m = _module(cuda_device, 256, 2, 8, 2, seed=8)
+    B, F = 3, 10
+    x = torch.from_numpy(O.make_input(B, F, 17, 2)).to(cuda_device).requires_grad_(True)
+    w = torch.randn(B, F, 17, 3, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    g = torch.Generator().manual_seed(4)
+    keep = 0.7
+    dp = ((keep + torch.rand(16, B * F, generator=g)).floor() / keep).to(cuda_device).contiguous()
+    assert float(dp.min()) == 0.0 and float(dp.max()) > 1.0
+    params = m._ordered_params()
+    assert m._native_backward_ok(x, dp)
+    out = DSTformerFunction.apply(m, x, False, dp, *params)
+    (out * w).sum().backward()
+    ps = [p.detach().double().requires_grad_(True) for p in params]
+    xr = x.detach().double().requires_grad_(True)
+    y = recompute_forward(m, xr, False, dp.double(), ps)
+    assert float((out.detach().double() - y.detach()).abs().max()) < 1e-3 * float(y.abs().max())
+    ref = torch.autograd.grad((y * w.double()).sum(), [xr] + ps)
+    gx_ref = ref[0]
+    rel_x = float((x.grad.double() - gx_ref).norm() / gx_ref.norm())
+    print(f"input-gradient rel L2 error {rel_x:.3e}")
+    assert rel_x < REL_L2
+    _compare(m, list(ref[1:]), "drop_path")
