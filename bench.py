@@ -251,6 +251,11 @@ def run_train(args, device, world, rank, local_rank, dist, D):
     step_flop = 3.0 * flops_per_sequence(cfg["dim_feat"], hidden, T) * B          # fwd + 2x bwd (recompute not counted)
     achieved = step_flop / (ms_per_step * 1e-3) / 1e12
     n_param = sum(p.numel() for p in params)
+    from motionbert_b200 import _lib
+    lib = _lib.load()
+    hnd = model._state_for(device).handle
+    # kernels of this library per step: forward + backward + fused loss (2); the per-step weight re-pack is not counted
+    launches_per_step = _lib.check(lib.mb_forward_launch_count(hnd, 1, 0)) + _lib.check(lib.mb_backward_launch_count(hnd, 0, 0)) + 2
     line = {
         "metric": f"sequences/sec DSTformer-{args.model} pretrain step fwd+bwd+AdamW (Bx{T}x17)",
         "value": value, "unit": "sequences/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -264,6 +269,7 @@ def run_train(args, device, world, rank, local_rank, dist, D):
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(2 * x_host.numel() * 4), "d2h_bytes_per_step": 4, "last_loss": last,
                 "api": "DSTformer.forward -> loss.backward() -> optimizer.step() on pinned host clips"},
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": None, "note": "whole step: 3 x forward algorithmic FLOPs / step time (recompute, optimizer and "
                                               "all-reduce time included in the denominator, not in the numerator)",

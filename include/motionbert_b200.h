@@ -135,6 +135,7 @@ int mb_forward_train(MbEncoder* enc, const void* packed, const float* x, float* 
                      const float* drop_path_scale, void* saved, size_t saved_bytes, void* workspace,
                      size_t workspace_bytes, int B, int F, uint32_t flags, void* stream);
 int mb_backward_workspace_bytes(const MbEncoder* enc, int B, int F, size_t* bytes);
+int mb_backward_launch_count(const MbEncoder* enc, int has_drop_path, int want_dx);   /* kernels per mb_backward call */
 int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x, const float* rep,
                 const void* saved, size_t saved_bytes, const float* drop_path_scale, const float* d_out,
                 const float* d_rep, float* const* grads, float* d_x, void* workspace, size_t workspace_bytes, int B,

@@ -1620,6 +1620,13 @@ static int bwd_wgrad(const DevInfo& dev, const __nv_bfloat16* G, int N, const __
     return MB_OK;
 }
 
+// kernels one mb_backward call launches (memsets not counted): tail 8, per depth 1 fusion + 4 MLP sublayers x 10
+// + 4 attention sublayers x 13 (+ 8 DropPath row scalings), embed 1 (+ 1 for d_x)
+extern "C" int mb_backward_launch_count(const MbEncoder* enc, int has_drop_path, int want_dx) {
+    if (!enc) return fail(MB_ERR_NULL, "enc is NULL");
+    return 8 + enc->d.depth * (1 + 4 * 10 + 4 * 13 + (has_drop_path ? 8 : 0)) + 1 + (want_dx ? 1 : 0);
+}
+
 extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x_in,
                            const float* rep, const void* saved_, size_t saved_bytes, const float* drop_path_scale,
                            const float* d_out, const float* d_rep, float* const* grads, float* d_x, void* workspace,
