@@ -20,8 +20,13 @@
 
 namespace mb {
 
-constexpr int ABW_THREADS = 320;       // w0 TMA, w1 MMA, w2..w9 SIMT (2 threads per row, each half of the columns)
-constexpr int ABW_SIMT = 256;
+// dQ kernel: w0 TMA, w1 MMA, w2..w17 SIMT = FOUR threads per row (TMEM lane quadrant = warp % 4, column quarter =
+// (warp - 2) / 4): 11 % faster than two per row (ncu: 549 -> 486 us at B=32).  dK/dV kernel: two threads per row
+// (w2..w9) -- with four it needs 16-column steps at the 96-register cap and came out 12 % slower.
+constexpr int ABW_THREADS = 576;
+constexpr int ABW_SIMT = 512;
+constexpr int ABW_KV_THREADS = 320;
+constexpr int ABW_KV_SIMT = 256;
 
 struct AttnBwdParams {
     int B, F, J, C, H;
@@ -45,9 +50,10 @@ struct AttnBwdCfg {
     static constexpr int OFF_B = TILE;                        // q kernel: dO tile  | kv kernel: V tile
     static constexpr int OFF_C = 2 * TILE;                    // q kernel: K (seq)  | kv kernel: Q (seq)
     static constexpr int OFF_D = 2 * TILE + SEQ;              // q kernel: V (seq)  | kv kernel: dO (seq)
-    static constexpr int OFF_BAR = 2 * TILE + 2 * SEQ;
-    static constexpr int OFF_VEC = OFF_BAR + 128;             // floats: red[2][128] | lse2[256], delta[256]
-    static constexpr int SMEM_BYTES = OFF_VEC + 2 * 256 * 4 + 1024;
+    static constexpr int OFF_E = 2 * TILE + 2 * SEQ;          // q kernel: O tile (row-wise delta = dO . O, read by the SIMT threads)
+    static constexpr int OFF_BAR = 3 * TILE + 2 * SEQ;
+    static constexpr int OFF_VEC = OFF_BAR + 128;             // floats: q kernel max/sum/delta [3][4][128] | kv kernel lse2[256], delta[256]
+    static constexpr int SMEM_BYTES = OFF_VEC + 3 * 4 * 128 * 4 + 1024;
 };
 
 // ------------------------------------------------------------------------------------------------- dQ kernel
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(ABW_THREADS, 1)
 attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box (HD, 1, 128, 1, 1)
                   const __grid_constant__ CUtensorMap tmQKV_s,   // qkv 5-D, box (HD, 1, NK , 1, 1)
                   const __grid_constant__ CUtensorMap tmDO_t,    // dO  5-D, box (HD, 1, 128, 1, 1)
+                  const __grid_constant__ CUtensorMap tmO_t,     // O   5-D, box (HD, 1, 128, 1, 1)
                   const AttnBwdParams p) {
     using Cfg = AttnBwdCfg<HD>;
     extern __shared__ uint8_t smem_raw[];
@@ -82,9 +89,9 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
     constexpr uint32_t SLAB = 32 * Cfg::SWZ;                 // one 32-row slab of a packed tile
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQKV_t); tma_prefetch_desc(&tmQKV_s); tma_prefetch_desc(&tmDO_t);
+        tma_prefetch_desc(&tmQKV_t); tma_prefetch_desc(&tmQKV_s); tma_prefetch_desc(&tmDO_t); tma_prefetch_desc(&tmO_t);
         mbar_init(kv_full, 1);  mbar_init(kv_empty, 1);
-        mbar_init(t_full, 1);   mbar_init(t_empty, 1);
+        mbar_init(t_full, 1);   mbar_init(t_empty, 1 + ABW_SIMT);   // MMA commit + the SIMT readers of the dO / O tiles
         mbar_init(sd_full, 1);  mbar_init(ds_full, ABW_SIMT);
         mbar_init(dq_full, 1);  mbar_init(dq_empty, ABW_SIMT);
         fence_barrier_init();
@@ -115,12 +122,13 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                         tma_load_5d(smem + Cfg::OFF_D + s4 * SLAB, &tmQKV_s, kv_full, 2 * p.C + h * HD, sq % p.J, 0, sq / p.J, 0);
                     }
                     mbar_wait(t_empty, (t_it & 1) ^ 1);
-                    mbar_arrive_expect_tx(t_full, 2 * Cfg::TILE);
+                    mbar_arrive_expect_tx(t_full, 3 * Cfg::TILE);
                     for (int s4 = 0; s4 < 4; ++s4) {
                         int sq = (prob / p.H) * 4 + s4;
                         if (sq >= nseq) sq = nseq - 1;
                         tma_load_5d(smem + Cfg::OFF_A + s4 * SLAB, &tmQKV_t, t_full, h * HD, sq % p.J, 0, sq / p.J, 0);
                         tma_load_5d(smem + Cfg::OFF_B + s4 * SLAB, &tmDO_t, t_full, h * HD, sq % p.J, 0, sq / p.J, 0);
+                        tma_load_5d(smem + Cfg::OFF_E + s4 * SLAB, &tmO_t, t_full, h * HD, sq % p.J, 0, sq / p.J, 0);
                     }
                     ++t_it;
                     continue;
@@ -129,9 +137,10 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                 tma_load_5d(smem + Cfg::OFF_D, &tmQKV_s, kv_full, 2 * p.C + h * HD, j, 0, b, 0);   // V
                 for (int qt = 0; qt < num_qt; ++qt, ++t_it) {
                     mbar_wait(t_empty, (t_it & 1) ^ 1);
-                    mbar_arrive_expect_tx(t_full, 2 * Cfg::TILE);
+                    mbar_arrive_expect_tx(t_full, 3 * Cfg::TILE);
                     tma_load_5d(smem + Cfg::OFF_A, &tmQKV_t, t_full, h * HD, j, qt * ATT_BM, b, 0);   // Q tile
                     tma_load_5d(smem + Cfg::OFF_B, &tmDO_t, t_full, h * HD, j, qt * ATT_BM, b, 0);    // dO tile
+                    tma_load_5d(smem + Cfg::OFF_E, &tmO_t, t_full, h * HD, j, qt * ATT_BM, b, 0);     // O tile
                 }
             }
         }
@@ -186,15 +195,18 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
         }
     } else {
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;                 // 0..3: the four threads of a row split its key columns
         const int r_in_tile = quad * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
         const int nch = (NKe + 31) / 32;
-        // unpacked: the two threads of a row split the chunks; packed: only the diagonal chunk (= quad) is live and
-        // half 0 owns it, half 1 zero-fills the three off-diagonal chunks
-        const int ch_lo = PACK ? (half == 0 ? quad : 0) : (half * 4 < nch ? half * 4 : nch);
-        const int ch_hi = PACK ? (half == 0 ? quad + 1 : 0) : ((half * 4 + 4 < nch) ? half * 4 + 4 : nch);
+        // unpacked: part p owns the 32-column chunks [2p, 2p+2); packed: only the diagonal chunk (= quad) is live, part 0
+        // owns it and parts 1..3 zero-fill one off-diagonal chunk each
+        const int ch_lo = PACK ? (part == 0 ? quad : 0) : (part * 2 < nch ? part * 2 : nch);
+        const int ch_hi = PACK ? (part == 0 ? quad + 1 : 0) : (part * 2 + 2 < nch ? part * 2 + 2 : nch);
         const float sl2 = p.scale_log2e;
+        float* red_max = red;                             // [4][128]
+        float* red_sum = red + 512;
+        float* red_del = red + 1024;
         uint32_t t_it = 0;
         for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
             int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
@@ -210,22 +222,32 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                     b = ok ? sq / p.J : 0;
                 }
                 const size_t tok = (static_cast<size_t>(b) * p.F + (ok ? tq : 0)) * p.J + j;
-                // delta = dO . O of my row (both threads of the row compute it redundantly)
-                float delta = 0.f;
-                if (ok) {
-                    const uint4* o4 = reinterpret_cast<const uint4*>(p.O + tok * p.C + h * HD);
-                    const uint4* g4 = reinterpret_cast<const uint4*>(p.dO + tok * p.C + h * HD);
+                // delta = dO . O of my row, from the TMA-staged (swizzled) tiles: each of the four threads takes HD/4 columns.
+                // (Reading the rows from global memory here -- 128 scattered 128-byte rows per warp instruction -- was the
+                // top stall of this kernel.)
+                float dpart = 0.f;
+                mbar_wait(t_full, ph);
+                {
+                    constexpr int NCHK = HD / 32;                    // 16-byte chunks per thread: 2 (HD = 64) or 1
+                    const uint32_t sw = (Cfg::SWZ == 128) ? static_cast<uint32_t>(r_in_tile & 7)
+                                                          : static_cast<uint32_t>((r_in_tile >> 1) & 3);
+                    const uint8_t* so = smem + Cfg::OFF_E + r_in_tile * Cfg::SWZ;
+                    const uint8_t* sg = smem + Cfg::OFF_B + r_in_tile * Cfg::SWZ;
 #pragma unroll
-                    for (int i = 0; i < HD / 8; ++i) {
-                        const uint4 a = o4[i], g = g4[i];
+                    for (int i = 0; i < NCHK; ++i) {
+                        const uint32_t chunk = (static_cast<uint32_t>(part * NCHK + i) ^ sw) << 4;
+                        const uint4 a = *reinterpret_cast<const uint4*>(so + chunk);
+                        const uint4 g = *reinterpret_cast<const uint4*>(sg + chunk);
                         const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            delta = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), delta);
-                            delta = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(gw[e] & 0xffff0000u), delta);
+                            dpart = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), dpart);
+                            dpart = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(gw[e] & 0xffff0000u), dpart);
                         }
                     }
                 }
+                mbar_arrive(t_empty);                                // my reads of the dO / O tiles are done
+                red_del[part * 128 + r_in_tile] = dpart;
                 mbar_wait(sd_full, ph);
                 tc_fence_after();
                 float mx = -INFINITY;
@@ -237,9 +259,10 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                     for (int i = 0; i < 32; ++i)
                         if ((PACK ? i : ch * 32 + i) < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
                 }
-                red[half * 128 + r_in_tile] = mx;
+                red_max[part * 128 + r_in_tile] = mx;
                 named_bar_sync(1, ABW_SIMT);
-                mx = fmaxf(red[r_in_tile], red[128 + r_in_tile]);
+                mx = fmaxf(fmaxf(red_max[r_in_tile], red_max[128 + r_in_tile]), fmaxf(red_max[256 + r_in_tile], red_max[384 + r_in_tile]));
+                const float delta = (red_del[r_in_tile] + red_del[128 + r_in_tile]) + (red_del[256 + r_in_tile] + red_del[384 + r_in_tile]);
                 const float mxs = mx * sl2;
                 float sum = 0.f;
                 for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -250,68 +273,70 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                     for (int i = 0; i < 32; ++i)
                         if ((PACK ? i : ch * 32 + i) < p.F) sum += ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs));
                 }
-                red[256 + half * 128 + r_in_tile] = sum;
+                red_sum[part * 128 + r_in_tile] = sum;
                 named_bar_sync(1, ABW_SIMT);
-                sum = red[256 + r_in_tile] + red[256 + 128 + r_in_tile];
+                sum = (red_sum[r_in_tile] + red_sum[128 + r_in_tile]) + (red_sum[256 + r_in_tile] + red_sum[384 + r_in_tile]);
                 const float lse2 = mxs + log2f(sum);                 // P = 2^(s*c*log2e - lse2)
-                if (ok && half == 0) {
+                if (ok && part == 0) {
                     const size_t si = PACK ? static_cast<size_t>(prob) * ATT_BM + r_in_tile
                                            : static_cast<size_t>(prob) * p.F + tq;
                     p.lse2[si] = lse2;
                     p.delta[si] = delta;
                 }
-                // dS = P (dP - delta) * scale  -> packed bf16 over S
+                // dS = P (dP - delta) * scale  -> packed bf16 over S, 16 source columns at a time (register budget: 96)
                 for (int ch = ch_lo; ch < ch_hi; ++ch) {
-                    uint32_t s[32], g[32];
-                    tmem_ld32(tmem_S + lane_off + ch * 32, s);
-                    tmem_ld32(tmem_dP + lane_off + ch * 32, g);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float d0 = 0.f, d1 = 0.f;
-                        if ((PACK ? 2 * i : ch * 32 + 2 * i) < p.F) {
-                            const float pv = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -lse2));
-                            d0 = pv * (__uint_as_float(g[2 * i]) - delta) * p.scale;
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t sv[16], gv[16];
+                        tmem_ld16(tmem_S + lane_off + ch * 32 + hh * 16, sv);
+                        tmem_ld16(tmem_dP + lane_off + ch * 32 + hh * 16, gv);
+                        tmem_ld_wait();
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int c = hh * 16 + 2 * i;
+                            float d0 = 0.f, d1 = 0.f;
+                            if ((PACK ? c : ch * 32 + c) < p.F) {
+                                const float pv = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -lse2));
+                                d0 = pv * (__uint_as_float(gv[2 * i]) - delta) * p.scale;
+                            }
+                            if ((PACK ? c + 1 : ch * 32 + c + 1) < p.F) {
+                                const float pv = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -lse2));
+                                d1 = pv * (__uint_as_float(gv[2 * i + 1]) - delta) * p.scale;
+                            }
+                            const __nv_bfloat162 t2 = __floats2bfloat162_rn(d0, d1);
+                            pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
                         }
-                        if ((PACK ? 2 * i + 1 : ch * 32 + 2 * i + 1) < p.F) {
-                            const float pv = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -lse2));
-                            d1 = pv * (__uint_as_float(g[2 * i + 1]) - delta) * p.scale;
-                        }
-                        const __nv_bfloat162 t2 = __floats2bfloat162_rn(d0, d1);
-                        pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
+                        tmem_st8(tmem_S + lane_off + ch * 32 + hh * 8, pk);
                     }
-                    tmem_st16(tmem_S + lane_off + ch * 32, pk);
                 }
-                if (PACK && half == 1) {
+                if (PACK && part != 0) {
                     uint32_t z[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) z[i] = 0u;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch)
-                        if (ch != quad) tmem_st16(tmem_S + lane_off + ch * 32, z);
+                    tmem_st16(tmem_S + lane_off + ((quad + part) & 3) * 32, z);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(ds_full);
-                // dQ tile
+                // dQ tile: 16 columns per thread
                 mbar_wait(dq_full, ph);
                 tc_fence_after();
-                if (HD == 64 || half == 0) {
-                    const int c0 = (HD == 64) ? half * 32 : 0;
-                    uint32_t r[32];
-                    tmem_ld32(tmem_dP + lane_off + c0, r);
+                if (HD == 64 || part < 2) {
+                    const int c0 = part * 16;
+                    uint32_t r[16];
+                    tmem_ld16(tmem_dP + lane_off + c0, r);
                     tmem_ld_wait();
                     if (ok) {
-                        uint32_t pk[16];
+                        uint32_t pk[8];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
+                        for (int i = 0; i < 8; ++i) {
                             const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
                             pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
                         }
                         uint4* d4 = reinterpret_cast<uint4*>(p.dqkv + tok * (3 * p.C) + h * HD + c0);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                 }
                 tc_fence_before();
@@ -329,7 +354,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
 
 // ------------------------------------------------------------------------------------------------- dK / dV kernel
 template <int HD, bool PACK = false>
-__global__ void __launch_bounds__(ABW_THREADS, 1)
+__global__ void __launch_bounds__(ABW_KV_THREADS, 1)
 attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box (HD, 1, 128, 1, 1)
                    const __grid_constant__ CUtensorMap tmQKV_s,   // qkv 5-D, box (HD, 1, NK , 1, 1)
                    const __grid_constant__ CUtensorMap tmDO_s,    // dO  5-D, box (HD, 1, NK , 1, 1)
@@ -363,8 +388,8 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
         tma_prefetch_desc(&tmQKV_t); tma_prefetch_desc(&tmQKV_s); tma_prefetch_desc(&tmDO_s);
         mbar_init(seq_full, 1); mbar_init(seq_empty, 1);
         mbar_init(t_full, 1);   mbar_init(t_empty, 1);
-        mbar_init(sd_full, 1);  mbar_init(ps_full, ABW_SIMT);
-        mbar_init(g_full, 1);   mbar_init(g_empty, ABW_SIMT);
+        mbar_init(sd_full, 1);  mbar_init(ps_full, ABW_KV_SIMT);
+        mbar_init(g_full, 1);   mbar_init(g_empty, ABW_KV_SIMT);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -477,7 +502,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
         for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
             int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
             // per-query statistics of this sequence -> smem (queries >= F get p = 0)
-            named_bar_sync(1, ABW_SIMT);               // previous problem's readers are done
+            named_bar_sync(1, ABW_KV_SIMT);               // previous problem's readers are done
             if (PACK) {
                 const bool qok = sid < ATT_BM && (sid & 31) < p.F && (prob / p.H) * 4 + (sid >> 5) < nseq;
                 const size_t si = static_cast<size_t>(prob) * ATT_BM;
@@ -488,7 +513,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
                 v_lse[sid] = sid < p.F ? p.lse2[si + sid] : 3.0e38f;
                 v_delta[sid] = sid < p.F ? p.delta[si + sid] : 0.f;
             }
-            named_bar_sync(1, ABW_SIMT);
+            named_bar_sync(1, ABW_KV_SIMT);
             for (int kt = 0; kt < num_kt; ++kt, ++t_it) {
                 const uint32_t ph = t_it & 1;
                 mbar_wait(sd_full, ph);

@@ -1369,7 +1369,7 @@ static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H
     const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
     const uint64_t C3 = 3ull * C, Cc = static_cast<uint64_t>(C);
     const bool pack = F <= 32;             // four short sequences per 128-row tile (spatial attention, short clips)
-    CUtensorMap q_t, q_s, do_t, do_s;
+    CUtensorMap q_t, q_s, do_t, do_s, o_t;
     int rc;
     {
         const uint64_t dq[5] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 1};
@@ -1382,6 +1382,7 @@ static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H
         if ((rc = make_tmap(&q_s, qkv, 5, dq, sq, bs, hd * 2))) return rc;
         if ((rc = make_tmap(&do_t, dO, 5, dd, sd, bt, hd * 2))) return rc;
         if ((rc = make_tmap(&do_s, dO, 5, dd, sd, bs, hd * 2))) return rc;
+        if ((rc = make_tmap(&o_t, O, 5, dd, sd, bt, hd * 2))) return rc;
     }
     AttnBwdParams bp;
     bp.B = B; bp.F = F; bp.J = J; bp.C = C; bp.H = H;
@@ -1393,9 +1394,9 @@ static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H
     const int grid = prob < dev.sms ? prob : dev.sms;
 #define ABW_LAUNCH(HD_, PK_)                                                                                         \
     do {                                                                                                             \
-        attn_bwd_q_kernel<HD_, PK_><<<grid, ABW_THREADS, AttnBwdCfg<HD_>::SMEM_BYTES, st>>>(q_t, q_s, do_t, bp);      \
+        attn_bwd_q_kernel<HD_, PK_><<<grid, ABW_THREADS, AttnBwdCfg<HD_>::SMEM_BYTES, st>>>(q_t, q_s, do_t, o_t, bp);      \
         LAUNCH_CHECK("attn_bwd_q_kernel");                                                                           \
-        attn_bwd_kv_kernel<HD_, PK_><<<grid, ABW_THREADS, AttnBwdCfg<HD_>::SMEM_BYTES, st>>>(q_t, q_s, do_s, bp);     \
+        attn_bwd_kv_kernel<HD_, PK_><<<grid, ABW_KV_THREADS, AttnBwdCfg<HD_>::SMEM_BYTES, st>>>(q_t, q_s, do_s, bp);     \
         LAUNCH_CHECK("attn_bwd_kv_kernel");                                                                          \
     } while (0)
     if (hd == 64 && pack) ABW_LAUNCH(64, true);
