@@ -20,3 +20,5 @@ print("bench:", round(j["value"], 1), j["unit"], round(j["ms_per_step"], 1), "ms
 print({k: round(v, 1) for k, v in r["class_ms_per_step"].items()})
 PY
 tail -2 gpurun_out/final_bench.err
+timeout 900 python bench.py --mode train --steps 5 --warmup 3 > gpurun_out/final_bench_train.json 2> gpurun_out/final_bench_train.err
+cut -c1-330 gpurun_out/final_bench_train.json; tail -2 gpurun_out/final_bench_train.err
