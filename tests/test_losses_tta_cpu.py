@@ -59,3 +59,17 @@ def test_flip_tta_is_one_call_of_2b_sequences():
     assert calls == [(6, 4, 17, 3)]
     exp = (model(x) + tta.flip_data(model(tta.flip_data(x)))) * 0.5
     assert torch.allclose(y, exp)
+
+
+def test_fused_loss_has_no_cpu_fallback_and_checks_shapes():
+    from motionbert_b200 import loss as ML
+    p, g, conf = (torch.from_numpy(a) for a in LO.make_case(2, 3, 17, 1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ML.pretrain_loss_3d(p, g)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ML.loss_2d_weighted(p, g, conf)
+
+
+def test_forward_flip_tta_rejects_representation_output():
+    with pytest.raises(ValueError):
+        tta.forward_flip_tta(lambda x: x, torch.zeros(1, 2, 17, 3), return_rep=True)
