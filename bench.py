@@ -201,6 +201,8 @@ def run_train(args, device, world, rank, local_rank, dist, D):
     gt_host = synthetic_clips(B, T, seed=1001 + rank)
     x_dev, gt_dev = x_host.to(device), gt_host.to(device)
     params = [p for p in model.parameters()]
+    if world > 1:
+        model.enable_gradient_allreduce()
     opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.01, fused=True)
 
     def barrier():
@@ -213,9 +215,7 @@ def run_train(args, device, world, rank, local_rank, dist, D):
         pred = model(x)
         # loss_mpjpe + 0.5 n_mpjpe + 20 loss_velocity (train.py:178-191, MB_pretrain.yaml:39-44), fused with its gradient
         loss, _parts = pretrain_loss_3d(pred, gt, 0.5, 20.0)
-        loss.backward()
-        if world > 1:
-            D.allreduce_gradients(params, world)
+        loss.backward()       # world > 1: gradients are averaged over the ranks inside the backward (phase by phase)
         opt.step()
         return loss
 
@@ -263,7 +263,7 @@ def run_train(args, device, world, rank, local_rank, dist, D):
         "dtype": "bf16" if args.math == "bf16" else "bf16x3 forward / bf16 backward", "data": "synthetic",
         "config": {"workload": f"SURVEY 8d config {'3' if world == 1 else '4'}: DSTformer-{args.model} pretrain step, B={B} per GPU, "
                                f"T={T}, fused pretrain loss (mpjpe + 0.5 n_mpjpe + 20 velocity), native backward (bf16 single-pass), fused AdamW", "global_batch": world * B,
-                   "seq_len": T, "parallelism": f"dp{world}" + (" + one flat fp32 gradient all-reduce per step (NCCL)" if world > 1 else ""),
+                   "seq_len": T, "parallelism": f"dp{world}" + (" + per-depth NCCL gradient all-reduce overlapped with the backward (one flat fp32 bucket)" if world > 1 else ""),
                    "l2": "activations >> 126 MB L2, no flush needed", "grad_allreduce_elems": n_param if world > 1 else 0},
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,

@@ -129,7 +129,11 @@ int mb_forward_host(MbEncoder* enc, const void* packed, const float* x_host, flo
  *     workspace : mb_backward_workspace_bytes() bytes, 1024-byte aligned (independent of the forward workspace)
  *     drop_path_scale : the SAME vector given to mb_forward_train (or NULL)
  *     d_x : optional (B,F,J,dim_in) gradient w.r.t. the pose input (NULL: not computed; the reference's training
- *           scripts never need it) */
+ *           scripts never need it)
+ *     phase_events : NULL, or depth + 2 cudaEvent_t handles recorded on `stream` as the gradients of a phase become
+ *           final -- [0] tail (norm, pre_logits, head), [1 + k] depth (depth-1-k) (blocks_st / blocks_ts / ts_attn of
+ *           that depth), [depth + 1] embed -- so that a data-parallel caller can all-reduce phase k on a side stream
+ *           while phase k+1 is still computing (the reference's nn.DataParallel reduces after the whole backward) */
 int mb_saved_bytes(const MbEncoder* enc, int B, int F, size_t* bytes);
 int mb_forward_train(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
                      const float* drop_path_scale, void* saved, size_t saved_bytes, void* workspace,
@@ -139,7 +143,7 @@ int mb_backward_launch_count(const MbEncoder* enc, int has_drop_path, int want_d
 int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x, const float* rep,
                 const void* saved, size_t saved_bytes, const float* drop_path_scale, const float* d_out,
                 const float* d_rep, float* const* grads, float* d_x, void* workspace, size_t workspace_bytes, int B,
-                int F, void* stream);
+                int F, void* const* phase_events, void* stream);
 
 /* ---- pretrain-step losses on the pose output, fused with their gradient ------------
  * 3-D mode (conf == NULL):  losses[0] = loss_mpjpe (lib/model/loss.py:56-63), [1] = n_mpjpe (:80-89),

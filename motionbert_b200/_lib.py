@@ -79,7 +79,7 @@ def load() -> C.CDLL:
     lib.mb_forward_train.argtypes = [vp, vp, fp, fp, fp, fp, vp, sz, vp, sz, i32, i32, u32, vp]
     lib.mb_backward_workspace_bytes.argtypes = [vp, i32, i32, C.POINTER(sz)]
     lib.mb_backward_launch_count.argtypes = [vp, i32, i32]
-    lib.mb_backward.argtypes = [vp, vp, C.POINTER(vp), fp, fp, vp, sz, fp, fp, fp, C.POINTER(vp), fp, vp, sz, i32, i32, vp]
+    lib.mb_backward.argtypes = [vp, vp, C.POINTER(vp), fp, fp, vp, sz, fp, fp, fp, C.POINTER(vp), fp, vp, sz, i32, i32, C.POINTER(vp), vp]
     lib.mb_pretrain_loss.argtypes = [fp, fp, fp, i32, i32, i32, C.c_float, C.c_float, fp, fp, vp, vp]
     lib.mb_test_linear_scratch_bytes.argtypes = [i32, i32, i32, C.POINTER(sz)]
     lib.mb_test_linear.argtypes = [i32, i32, i32, i32, i32, i32, fp, fp, fp, fp, fp, fp, C.c_float, fp, fp, vp, sz, vp]

@@ -1631,7 +1631,7 @@ extern "C" int mb_backward_launch_count(const MbEncoder* enc, int has_drop_path,
 extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x_in,
                            const float* rep, const void* saved_, size_t saved_bytes, const float* drop_path_scale,
                            const float* d_out, const float* d_rep, float* const* grads, float* d_x, void* workspace,
-                           size_t workspace_bytes, int B, int F, void* stream_) {
+                           size_t workspace_bytes, int B, int F, void* const* phase_events, void* stream_) {
     if (!enc || !packed || !params || !x_in || !rep || !saved_ || !grads || !workspace)
         return fail(MB_ERR_NULL, "NULL argument");
     if (!d_out && !d_rep) return fail(MB_ERR_NULL, "both d_out and d_rep are NULL");
@@ -1823,6 +1823,14 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
     if ((rc = ln_linear_backward(enc->lin.back(), dz))) return rc;
     int cur = 0;                                            // g[cur] = gradient w.r.t. the fused output of depth i
     if ((rc = finalize(final_slot, -1, nullptr, cur))) return rc;
+    // phase k's parameter gradients are final once phase_events[k] has been recorded: 0 = tail (norm, pre_logits, head),
+    // 1 + (depth-1-i) = depth i (blocks_st[i], blocks_ts[i], ts_attn[i]), depth+1 = embed.  A data-parallel caller
+    // all-reduces each phase on a side stream while the next phase computes.
+    auto phase_done = [&](int k) -> int {
+        if (phase_events && phase_events[k]) CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(phase_events[k]), st));
+        return MB_OK;
+    };
+    if ((rc = phase_done(0))) return rc;
 
     for (int i = d.depth - 1; i >= 0; --i) {
         const LinearPack* Lst = &enc->lin[(0 * d.depth + i) * L_PER_BLOCK];
@@ -1855,6 +1863,7 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
         if ((rc = mlp_backward(Lts, true, sb + 5, 8 * i + 5, b, nullptr, cur))) return rc;
         if ((rc = attn_backward(Lts, true, sb + 0, 8 * i + 4, cur, g_x[a], b))) return rc;       // total d X0 in g[b]
         cur = b;
+        if ((rc = phase_done(1 + (d.depth - 1 - i)))) return rc;
     }
     // ---- embed (DSTformer.py:333-337)
     embed_bwd_kernel<<<dim3(F, (B + EMB_BATCH - 1) / EMB_BATCH), 256, 0, st>>>(
@@ -1865,7 +1874,7 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
         embed_dx_kernel<<<rows_grid, 256, 0, st>>>(g_x[cur], params[enc->index.at("joints_embed.weight")], M, C, d.dim_in, d_x);
         LAUNCH_CHECK("embed_dx_kernel");
     }
-    return MB_OK;
+    return phase_done(d.depth + 1);
 }
 
 

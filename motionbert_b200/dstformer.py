@@ -78,6 +78,7 @@ class _DeviceState:
         self.pack_key = None
         self.workspaces = {}
         self.zeros = {}
+        self.side_stream = None
 
     def __del__(self):
         try:
@@ -144,6 +145,7 @@ class DSTformer(nn.Module):
         self._kernel_flags = 0
         # shared (by reference) between nn.DataParallel replicas: keyed by device index
         self._dev_state = {}
+        self._grad_sync = None                     # enable_gradient_allreduce(): {'group', 'world'}
 
     # ------------------------------------------------------------------ reference API surface
     def _init_weights(self, m):                                                  # DSTformer.py:313-320
@@ -335,6 +337,33 @@ class DSTformer(nn.Module):
                 "mb_forward_train")
         return out, rep, saved
 
+    def _param_phases(self):
+        """Backward phase of every tensor of `_ordered_params()`: 0 tail, 1 + (depth-1-i) depth i, depth + 1 embed
+        (the order mb_backward finishes their gradients in; include/motionbert_b200.h `phase_events`)."""
+        d = self.depth
+        ph = [d + 1] * 4
+        for _stream in range(2):
+            for i in range(d):
+                ph += [1 + (d - 1 - i)] * 24
+        ph += [0] * 6
+        for i in range(d):
+            ph += [1 + (d - 1 - i)] * 2
+        return ph
+
+    def enable_gradient_allreduce(self, group=None, enabled: bool = True):
+        """Data-parallel training without a wrapper: every native backward averages
+        the parameter gradients over the ranks of `group`, phase by phase (tail, depth d-1 ... 0, embed) on a side
+        stream, overlapped with the rest of the backward.  Needs an initialised torch.distributed process group (NCCL).
+        Replaces `nn.DataParallel`'s reduce (train.py:258) / an external DistributedDataParallel wrapper."""
+        if not enabled:
+            self._grad_sync = None
+            return self
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("enable_gradient_allreduce needs an initialised torch.distributed process group")
+        self._grad_sync = {"group": group, "world": dist.get_world_size(group)}
+        return self
+
     def _launch_backward(self, x, rep, saved, d_out, d_rep, dp_scale=None, want_dx=False):
         """mb_backward on the current stream: returns (parameter gradients in `_ordered_params()` order, d_x or None)."""
         device = x.device
@@ -351,21 +380,52 @@ class DSTformer(nn.Module):
                 _lib.check(lib.mb_backward_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_backward_workspace_bytes")
                 bws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
                 st.workspaces[("bwd", B, F)] = bws
-            sizes = [(p.numel() + 63) // 64 * 64 for p in params]          # 256-byte aligned sub-buffers
-            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
-            grads, off = [], 0
-            for p, n in zip(params, sizes):
-                grads.append(flat[off:off + p.numel()].view(p.shape))
-                off += n
+            # ONE zero-filled flat bucket, laid out phase by phase (tail, depth d-1 ... 0, embed) in the order the backward
+            # finishes them, every tensor 256-byte aligned: the DDP bucket of SURVEY.md section 8e
+            phases = self._param_phases()
+            nph = self.depth + 2
+            sizes = [(p.numel() + 63) // 64 * 64 for p in params]
+            order = sorted(range(len(params)), key=lambda i: phases[i])
+            offs, bounds, off = [0] * len(params), [0] * (nph + 1), 0
+            for i in order:
+                offs[i] = off
+                off += sizes[i]
+                bounds[phases[i] + 1] = off
+            flat = torch.zeros(off, dtype=torch.float32, device=device)
+            grads = [flat[offs[i]:offs[i] + p.numel()].view(p.shape) for i, p in enumerate(params)]
             pp = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
             gp = (ctypes.c_void_p * len(params))(*[g.data_ptr() for g in grads])
             d_x = torch.empty_like(x) if want_dx else None
+            sync = self._grad_sync if self._grad_sync is not None and self._grad_sync["world"] > 1 else None
+            events, ev_ptrs = None, None
+            if sync is not None:
+                cur = torch.cuda.current_stream(device)
+                events = [torch.cuda.Event() for _ in range(nph)]
+                for e in events:
+                    e.record(cur)                       # materialise the cudaEvent_t; the library re-records it
+                ev_ptrs = (ctypes.c_void_p * nph)(*[e.cuda_event for e in events])
             _lib.check(lib.mb_backward(
                 st.handle, self._aligned_ptr(st.packed), pp, x.data_ptr(), rep.data_ptr(), self._aligned_ptr(saved),
                 saved.numel() - 1024, dp_scale.data_ptr() if dp_scale is not None else None,
                 d_out.data_ptr() if d_out is not None else None, d_rep.data_ptr() if d_rep is not None else None, gp,
                 d_x.data_ptr() if d_x is not None else None, self._aligned_ptr(bws), bws.numel() - 1024,
-                B, F, stream_ptr), "mb_backward")
+                B, F, ev_ptrs, stream_ptr), "mb_backward")
+            if sync is not None:
+                # data-parallel exchange overlapped with the backward: phase k is summed over the ranks on a side stream
+                # as soon as its event fires, while the kernels of phase k+1 keep the SMs busy on the main stream
+                import torch.distributed as dist
+                side = st.side_stream
+                if side is None:
+                    side = st.side_stream = torch.cuda.Stream(device=device)
+                flat.record_stream(side)
+                with torch.cuda.stream(side):
+                    for k in range(nph):
+                        if bounds[k + 1] > bounds[k]:
+                            side.wait_event(events[k])
+                            seg = flat[bounds[k]:bounds[k + 1]]
+                            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=sync["group"])
+                            seg.div_(sync["world"])
+                torch.cuda.current_stream(device).wait_stream(side)
         return grads, d_x
 
     def make_graphed(self, B: int, F: int, return_rep: bool = False):

@@ -1,6 +1,7 @@
 """Two-GPU data-parallel training of the drop-in module: one process per GPU over
-NCCL; gradients exchanged (a) by motionbert_b200.dist.allreduce_gradients (one flat bucket) and (b) by torch's own
-DistributedDataParallel wrapper around the unchanged module.  Both must equal the single-process gradient of the whole
+NCCL; gradients exchanged (a) by motionbert_b200.dist.allreduce_gradients (one flat bucket), (b) by torch's own
+DistributedDataParallel wrapper around the unchanged module and (c) by the module's own per-phase exchange overlapped
+with the backward (`enable_gradient_allreduce`).  Both must equal the single-process gradient of the whole
 batch (up to the bf16 arithmetic of the native backward).  Skipped on a single-GPU box."""
 import os
 import socket
@@ -37,6 +38,12 @@ def _worker(rank, world, port, q):
         ddp = torch.nn.parallel.DistributedDataParallel(m, device_ids=[rank])
         (ddp(x[lo:hi]) * w[lo:hi]).sum().backward()
         gb = {k: p.grad.clone() for k, p in m.named_parameters()}
+        # (c) the module's own exchange: per-phase all-reduce on a side stream, overlapped with the backward
+        m.zero_grad(set_to_none=True)
+        m.enable_gradient_allreduce()
+        (m(x[lo:hi]) * w[lo:hi]).sum().backward()
+        gc = {k: p.grad.clone() for k, p in m.named_parameters()}
+        m.enable_gradient_allreduce(enabled=False)
         # single-process reference on rank 0: whole batch, gradient / world
         full = None
         if rank == 0:
@@ -45,7 +52,8 @@ def _worker(rank, world, port, q):
             full = {k: (p.grad / world).cpu() for k, p in m.named_parameters()}
         torch.cuda.synchronize(dev)
         dist.barrier()
-        q.put((rank, n, {k: v.cpu() for k, v in ga.items()}, {k: v.cpu() for k, v in gb.items()}, full))
+        q.put((rank, n, {k: v.cpu() for k, v in ga.items()}, {k: v.cpu() for k, v in gb.items()}, full,
+               {k: v.cpu() for k, v in gc.items()}))
     finally:
         dist.destroy_process_group()
 
@@ -73,7 +81,7 @@ def test_two_gpu_gradient_exchange_matches_single_process():
         if den == 0:
             continue
         for rank in range(2):
-            for which, g in (("flat all-reduce", res[rank][2][k]), ("DDP", res[rank][3][k])):
+            for which, g in (("flat all-reduce", res[rank][2][k]), ("DDP", res[rank][3][k]), ("overlapped", res[rank][5][k])):
                 assert float((g - ref).norm()) / den < 3e-2, f"{which} rank {rank} {k}"
         # both ranks hold the same averaged gradient
         assert torch.allclose(res[0][2][k], res[1][2][k], rtol=0, atol=0)

@@ -93,3 +93,25 @@ def test_shim_shadows_exactly_the_reference_module():
         env["PYTHONPATH"] += os.pathsep + "/root/reference"
         r = subprocess.run([sys.executable, "-P", "-c", code], capture_output=True, text=True, env=env)
         assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_backward_phase_of_every_parameter_matches_its_name():
+    """`_param_phases` lays the flat gradient bucket out in the order mb_backward finishes the gradients
+    (tail, depth d-1 ... 0, embed); check it against the parameter names."""
+    import re
+
+    from motionbert_b200 import DSTformer
+    m = DSTformer(dim_feat=256, depth=3, num_heads=8, mlp_ratio=2)
+    names = {id(p): n for n, p in m.named_parameters()}
+    ph = m._param_phases()
+    ps = m._ordered_params()
+    assert len(ph) == len(ps) == 4 + 2 * 3 * 24 + 6 + 2 * 3
+    for p, k in zip(ps, ph):
+        n = names[id(p)]
+        mt = re.match(r"(blocks_st|blocks_ts|ts_attn)\.(\d+)\.", n)
+        if mt:
+            assert k == 1 + (3 - 1 - int(mt.group(2))), n
+        elif n in ("temp_embed", "pos_embed") or n.startswith("joints_embed"):
+            assert k == 3 + 1, n
+        else:
+            assert k == 0 and (n.startswith("norm.") or n.startswith("pre_logits") or n.startswith("head.")), n
