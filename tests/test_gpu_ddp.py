@@ -49,11 +49,12 @@ def _worker(rank, world, port, q):
         if rank == 0:
             m.zero_grad(set_to_none=True)
             (m(x) * w).sum().backward()
-            full = {k: (p.grad / world).cpu() for k, p in m.named_parameters()}
+            full = {k: (p.grad / world).cpu().numpy() for k, p in m.named_parameters()}
         torch.cuda.synchronize(dev)
         dist.barrier()
-        q.put((rank, n, {k: v.cpu() for k, v in ga.items()}, {k: v.cpu() for k, v in gb.items()}, full,
-               {k: v.cpu() for k, v in gc.items()}))
+        # numpy payloads: pickled by value (torch tensors travel as shared-memory handles that die with this process)
+        q.put((rank, n, {k: v.cpu().numpy() for k, v in ga.items()}, {k: v.cpu().numpy() for k, v in gb.items()}, full,
+               {k: v.cpu().numpy() for k, v in gc.items()}))
     finally:
         dist.destroy_process_group()
 
@@ -73,15 +74,16 @@ def test_two_gpu_gradient_exchange_matches_single_process():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    import numpy as np
     full = res[0][4]
-    n_param = sum(v.numel() for v in full.values())
+    n_param = sum(v.size for v in full.values())
     assert res[0][1] == n_param and res[1][1] == n_param
     for k, ref in full.items():
-        den = float(ref.norm())
+        den = float(np.linalg.norm(ref))
         if den == 0:
             continue
         for rank in range(2):
             for which, g in (("flat all-reduce", res[rank][2][k]), ("DDP", res[rank][3][k]), ("overlapped", res[rank][5][k])):
-                assert float((g - ref).norm()) / den < 3e-2, f"{which} rank {rank} {k}"
+                assert float(np.linalg.norm(g - ref)) / den < 3e-2, f"{which} rank {rank} {k}"
         # both ranks hold the same averaged gradient
-        assert torch.allclose(res[0][2][k], res[1][2][k], rtol=0, atol=0)
+        assert np.array_equal(res[0][2][k], res[1][2][k]) and np.array_equal(res[0][5][k], res[1][5][k])
