@@ -100,8 +100,9 @@ class DSTformerFunction(torch.autograd.Function):
         with torch.no_grad():
             if ctx.native:
                 out, rep, saved = mod._launch_train(x, not return_rep, dp_scale)
-                ctx.saved_region = saved
-                ctx.save_for_backward(x, rep)
+                # the activation region goes through save_for_backward so that autograd releases it right after the
+                # backward (unless retain_graph): two steps' regions never coexist in a train.py-style loop
+                ctx.save_for_backward(x, rep, saved)
                 ctx.pack_versions = tuple(p._version for p in params)
             else:
                 out, rep = mod._launch(x, not return_rep, return_rep, dp_scale)
@@ -111,9 +112,9 @@ class DSTformerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         if ctx.native:
-            x, rep = ctx.saved_tensors
+            x, rep, saved = ctx.saved_tensors
             g = grad.contiguous().float()
-            grads, d_x = ctx.mod._launch_backward(x, rep, ctx.saved_region, None if ctx.return_rep else g,
+            grads, d_x = ctx.mod._launch_backward(x, rep, saved, None if ctx.return_rep else g,
                                                   g if ctx.return_rep else None, ctx.dp_scale, ctx.needs_input_grad[1])
             gp = [gr if ctx.needs_input_grad[4 + i] else None for i, gr in enumerate(grads)]
             return (None, d_x, None, None, *gp)

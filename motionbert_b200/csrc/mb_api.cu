@@ -746,6 +746,11 @@ extern "C" int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint3
 struct SavedLayout {
     size_t x_bytes, st_bytes, slot_bytes, total;
     int slots;
+    // single-pass (bf16) mode only: the qkv plane and the attention output plane of every attention sublayer
+    // (4 per depth: st S-attn, st T-attn, ts T-attn, ts S-attn) are kept as well, so the backward neither re-runs the
+    // qkv GEMM nor the attention forward.  In BF16x3 mode they are recomputed (the forward's hi/lo planes would cost 2x).
+    bool save_attn;
+    size_t attn_base, qkv_bytes, o_bytes, attn_slot_bytes;
 };
 static SavedLayout saved_layout(const MbDesc& d, int B, int F) {
     SavedLayout s;
@@ -754,7 +759,12 @@ static SavedLayout saved_layout(const MbDesc& d, int B, int F) {
     s.st_bytes = align_up(M * (d.dim_feat / STATS_GROUP) * 3 * 4, 1024);
     s.slot_bytes = s.x_bytes + s.st_bytes;
     s.slots = 9 * d.depth + 1;
-    s.total = s.slot_bytes * s.slots;
+    s.attn_base = s.slot_bytes * s.slots;
+    s.save_attn = d.math == MB_MATH_BF16;
+    s.qkv_bytes = align_up(M * 3 * d.dim_feat * 2, 1024);
+    s.o_bytes = align_up(M * d.dim_feat * 2, 1024);
+    s.attn_slot_bytes = s.qkv_bytes + s.o_bytes;
+    s.total = s.attn_base + (s.save_attn ? s.attn_slot_bytes * 4 * d.depth : 0);
     return s;
 }
 
@@ -840,16 +850,50 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
     };
 
     // one residual attention sublayer: dst = src + proj(attn(qkv(LN(src))))      (DSTformer.py:241,243,246,248)
-    auto attn_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst) -> int {
+    auto attn_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst, int attn_idx) -> int {
+        // training in single-pass mode: this sublayer's qkv / attention-output planes live in their saved slot
+        const Plan* AP = &P;
+        Plan SPl;
+        if (saved && sl.save_attn) {
+            SPl = P;
+            uint8_t* slot = saved + sl.attn_base + static_cast<size_t>(attn_idx) * sl.attn_slot_bytes;
+            SPl.qkv = reinterpret_cast<__nv_bfloat16*>(slot);
+            SPl.ao = reinterpret_cast<__nv_bfloat16*>(slot + sl.qkv_bytes);
+            const int hd = C / d.num_heads;
+            const uint64_t Cu = C, C3 = 3ull * C, plane3 = M_ * C3, plane1 = M_ * Cu;
+            int r;
+            if ((r = make_split_store_tmap(&SPl.tm_qkv_st, SPl.qkv, M_, C3, plane3, 1))) return r;
+            const uint64_t dims[5] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B), 1};
+            const uint64_t str[4] = {C3, C3 * J, C3 * J * F, plane3};
+            if (temporal) {
+                const uint32_t NK = static_cast<uint32_t>((F + 15) / 16 * 16);
+                const uint32_t box_q[5] = {static_cast<uint32_t>(hd), 1, ATT_BM, 1, 1};
+                const uint32_t box_kv[5] = {static_cast<uint32_t>(hd), 1, NK, 1, 1};
+                const uint32_t box_t32[5] = {static_cast<uint32_t>(hd), 1, ATS_SLAB, 1, 1};
+                if ((r = make_tmap(&SPl.tm_q, SPl.qkv, 5, dims, str, box_q, hd * 2))) return r;
+                if ((r = make_tmap(&SPl.tm_kv, SPl.qkv, 5, dims, str, box_kv, hd * 2))) return r;
+                if ((r = make_tmap(&SPl.tm_qkv_t32, SPl.qkv, 5, dims, str, box_t32, hd * 2))) return r;
+            } else {
+                const uint64_t dims4[4] = {C3, static_cast<uint64_t>(J), static_cast<uint64_t>(B) * F, 1};
+                const uint64_t str4[3] = {C3, C3 * J, plane3};
+                const uint32_t box4[4] = {static_cast<uint32_t>(hd), ATS_SLAB, ATS_FRAMES, 1};
+                if ((r = make_tmap(&SPl.tm_qkv_sp, SPl.qkv, 4, dims4, str4, box4, hd * 2))) return r;
+            }
+            const uint64_t da[3] = {Cu, M_, 1};
+            const uint64_t sa[2] = {Cu, plane1};
+            const uint32_t ba[3] = {64u, GEMM_BM, 1u};
+            if ((r = make_tmap(&SPl.tm_ao, SPl.ao, 3, da, sa, ba, 128))) return r;
+            AP = &SPl;
+        }
         GemmParams p = base;
         p.stats_in = src.stats;
-        p.out_hi = P.qkv;
-        p.out_lo = P.qkv + qkv_plane_el;
+        p.out_hi = AP->qkv;
+        p.out_lo = AP->qkv + qkv_plane_el;
         EpiMaps em;
-        em.out_s = &P.tm_qkv_st;
+        em.out_s = &AP->tm_qkv_st;
         int r = launch_gemm<EPI_LN_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_QKV_T : L_QKV_S], pk, p, em, st);
         if (r) return r;
-        r = launch_attn(enc, flags, temporal, P, B, F, qkv_plane_el, ao_plane_el, st);
+        r = launch_attn(enc, flags, temporal, *AP, B, F, qkv_plane_el, ao_plane_el, st);
         if (r) return r;
         GemmParams q = base;
         q.resid = src.x;
@@ -862,7 +906,7 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
         em2.resid = &src.tm_x;
         em2.out_x = &dst.tm_x;
         em2.out_s = &dst.tm_st;
-        return launch_gemm<EPI_RESID>(enc, flags, P.tm_ao, P.ao, P.ao + ao_plane_el, L[temporal ? L_PROJ_T : L_PROJ_S], pk, q, em2, st);
+        return launch_gemm<EPI_RESID>(enc, flags, AP->tm_ao, AP->ao, AP->ao + ao_plane_el, L[temporal ? L_PROJ_T : L_PROJ_S], pk, q, em2, st);
     };
     // one residual MLP sublayer: dst = src + fc2(gelu(fc1(LN(src))))             (DSTformer.py:242,244,247,249)
     auto mlp_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst,
@@ -901,14 +945,14 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
             (rc = slot_buf(3, sb + 7, &T1b)) || (rc = slot_buf(1, sb + 8, &S1d)))
             return rc;
         // blocks_st[i] : 'stage_st'  S-attn, S-mlp, T-attn, T-mlp   (DSTformer.py:240-244)  X0 -> S1 -> S2 -> S1 -> S2
-        if ((rc = attn_sublayer(Lst, false, X0, S1))) return rc;
+        if ((rc = attn_sublayer(Lst, false, X0, S1, 4 * i + 0))) return rc;
         if ((rc = mlp_sublayer(Lst, false, S1, S2, false))) return rc;
-        if ((rc = attn_sublayer(Lst, true, S2, S1b))) return rc;
+        if ((rc = attn_sublayer(Lst, true, S2, S1b, 4 * i + 1))) return rc;
         if ((rc = mlp_sublayer(Lst, true, S1b, S2b, true))) return rc;
         // blocks_ts[i] : 'stage_ts'  T-attn, T-mlp, S-attn, S-mlp   (DSTformer.py:245-249)  X0 -> T1 -> S1 -> T1 -> S1
-        if ((rc = attn_sublayer(Lts, true, X0, T1))) return rc;
+        if ((rc = attn_sublayer(Lts, true, X0, T1, 4 * i + 2))) return rc;
         if ((rc = mlp_sublayer(Lts, true, T1, S1c, false))) return rc;
-        if ((rc = attn_sublayer(Lts, false, S1c, T1b))) return rc;
+        if ((rc = attn_sublayer(Lts, false, S1c, T1b, 4 * i + 3))) return rc;
         if ((rc = mlp_sublayer(Lts, false, T1b, S1d, true))) return rc;
         // fusion (DSTformer.py:343-349): (x_st = S2b, x_ts = S1d) -> X0 of the next depth
         ActBuf Xn;
@@ -1625,7 +1669,8 @@ static int bwd_wgrad(const DevInfo& dev, const __nv_bfloat16* G, int N, const __
 // + 4 attention sublayers x 13 (+ 8 DropPath row scalings), embed 1 (+ 1 for d_x)
 extern "C" int mb_backward_launch_count(const MbEncoder* enc, int has_drop_path, int want_dx) {
     if (!enc) return fail(MB_ERR_NULL, "enc is NULL");
-    return 8 + enc->d.depth * (1 + 4 * 10 + 4 * 13 + (has_drop_path ? 8 : 0)) + 1 + (want_dx ? 1 : 0);
+    const int attn = enc->d.math == MB_MATH_BF16 ? 11 : 13;      // single-pass mode: qkv / attention are saved, not recomputed
+    return 8 + enc->d.depth * (1 + 4 * 10 + 4 * attn + (has_drop_path ? 8 : 0)) + 1 + (want_dx ? 1 : 0);
 }
 
 extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* const* params, const float* x_in,
@@ -1786,23 +1831,33 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
     one_pass.device = enc->device;
     one_pass.dev = enc->dev;
     // attention sublayer  y = x + proj(attn(qkv(LN(x))))   (DSTformer.py:241,243,246,248)
-    auto attn_backward = [&](const LinearPack* L, bool temporal, int slot, int sub, int g_in, const float* extra, int g_out) -> int {
+    auto attn_backward = [&](const LinearPack* L, bool temporal, int slot, int sub, int attn_idx, int g_in, const float* extra,
+                             int g_out) -> int {
         const LinearPack& Lq = L[temporal ? L_QKV_T : L_QKV_S];
         const LinearPack& Lp = L[temporal ? L_PROJ_T : L_PROJ_S];
         int r, gb;
         if ((r = branch_grad(sub, g_in, &gb))) return r;
         if ((r = make_xhat(slot))) return r;
-        // recompute qkv = xhat Wq'^T + cq and the attention output O
-        if ((r = bwd_gemm<EPI_BIAS_SPLIT, false>(di, xhat, M, C, 3 * C, Lq.tmap_k1, reinterpret_cast<const float*>(pk + Lq.off_c),
-                                                 nullptr, wide[0], st))) return r;
-        if ((r = launch_attn(&one_pass, 0u, temporal, AP, B, F, M_ * 3 * C, M_ * C, st))) return r;
+        const __nv_bfloat16* qkv_pl = wide[0];
+        const __nv_bfloat16* o_cur = o_pl;
+        if (sl.save_attn) {
+            // single-pass training forward kept this sublayer's qkv and attention output: nothing to recompute
+            const uint8_t* aslot = saved + sl.attn_base + static_cast<size_t>(attn_idx) * sl.attn_slot_bytes;
+            qkv_pl = reinterpret_cast<const __nv_bfloat16*>(aslot);
+            o_cur = reinterpret_cast<const __nv_bfloat16*>(aslot + sl.qkv_bytes);
+        } else {
+            // recompute qkv = xhat Wq'^T + cq and the attention output O
+            if ((r = bwd_gemm<EPI_BIAS_SPLIT, false>(di, xhat, M, C, 3 * C, Lq.tmap_k1, reinterpret_cast<const float*>(pk + Lq.off_c),
+                                                     nullptr, wide[0], st))) return r;
+            if ((r = launch_attn(&one_pass, 0u, temporal, AP, B, F, M_ * 3 * C, M_ * C, st))) return r;
+        }
         // proj: dWp += dy^T O ; dbp += sum dy ; dO = dy Wp
-        if ((r = bwd_wgrad(di, g_p[gb], C, o_pl, C, M, G(Lp, 0), st))) return r;
+        if ((r = bwd_wgrad(di, g_p[gb], C, o_cur, C, M, G(Lp, 0), st))) return r;
         if ((r = colsum_f32(g_x[gb], C, G(Lp, 1)))) return r;
         if ((r = bwd_gemm<EPI_BIAS_SPLIT, true>(di, g_p[gb], M, C, C, Lp.tmap_mn, zero, nullptr, do_pl, st))) return r;
         // attention core: (qkv, O, dO) -> dqkv
-        if (temporal) r = launch_attn_bwd(di, B, F, J, C, H, scale, wide[0], o_pl, do_pl, lse2, delta, wide[1], st);
-        else r = launch_attn_bwd(di, B * F, J, 1, C, H, scale, wide[0], o_pl, do_pl, lse2, delta, wide[1], st);
+        if (temporal) r = launch_attn_bwd(di, B, F, J, C, H, scale, qkv_pl, o_cur, do_pl, lse2, delta, wide[1], st);
+        else r = launch_attn_bwd(di, B * F, J, 1, C, H, scale, qkv_pl, o_cur, do_pl, lse2, delta, wide[1], st);
         if (r) return r;
         if ((r = ln_linear_backward(Lq, wide[1]))) return r;
         return finalize(slot, g_in, extra, g_out);
@@ -1854,14 +1909,14 @@ extern "C" int mb_backward(MbEncoder* enc, const void* packed, const float* cons
         // blocks_st[i] backward: T-mlp(in slot 3), T-attn(2), S-mlp(1), S-attn(0); gradient ping-pongs a <-> cur.
         // DropPath sublayer indices follow the forward: blocks_st[i] = 8i + {0 S-attn, 1 S-mlp, 2 T-attn, 3 T-mlp}
         if ((rc = mlp_backward(Lst, true, sb + 3, 8 * i + 3, a, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lst, true, sb + 2, 8 * i + 2, cur, nullptr, a))) return rc;
+        if ((rc = attn_backward(Lst, true, sb + 2, 8 * i + 2, 4 * i + 1, cur, nullptr, a))) return rc;
         if ((rc = mlp_backward(Lst, false, sb + 1, 8 * i + 1, a, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lst, false, sb + 0, 8 * i + 0, cur, nullptr, a))) return rc;      // d X0 via the st stream in g[a]
+        if ((rc = attn_backward(Lst, false, sb + 0, 8 * i + 0, 4 * i + 0, cur, nullptr, a))) return rc;   // d X0 via the st stream in g[a]
         // blocks_ts[i] = 8i + {4 T-attn, 5 T-mlp, 6 S-attn, 7 S-mlp}: S-mlp(in slot 7), S-attn(6), T-mlp(5), T-attn(0)
         if ((rc = mlp_backward(Lts, false, sb + 7, 8 * i + 7, b, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lts, false, sb + 6, 8 * i + 6, cur, nullptr, b))) return rc;
+        if ((rc = attn_backward(Lts, false, sb + 6, 8 * i + 6, 4 * i + 3, cur, nullptr, b))) return rc;
         if ((rc = mlp_backward(Lts, true, sb + 5, 8 * i + 5, b, nullptr, cur))) return rc;
-        if ((rc = attn_backward(Lts, true, sb + 0, 8 * i + 4, cur, g_x[a], b))) return rc;       // total d X0 in g[b]
+        if ((rc = attn_backward(Lts, true, sb + 0, 8 * i + 4, 4 * i + 2, cur, g_x[a], b))) return rc;    // total d X0 in g[b]
         cur = b;
         if ((rc = phase_done(1 + (d.depth - 1 - i)))) return rc;
     }

@@ -232,3 +232,42 @@ def test_native_backward_with_drop_path_and_input_gradient(cuda_device):
     print(f"input-gradient rel L2 error {rel_x:.3e}")
     assert rel_x < REL_L2
     _compare(m, list(ref[1:]), "drop_path")
+
+
+def test_single_pass_mode_saves_attention_operands(cuda_device):
+    """set_math_mode('bf16') (the training configuration of bench.py --mode train): the forward keeps the qkv and
+    attention-output planes of every attention sublayer in the saved region and the backward uses them instead of
+    recomputing.  The forward itself is bf16 single-pass here, so the bar against fp64 autograd is the bf16 forward's."""
+    import ctypes
+
+    from motionbert_b200 import _lib
+    m = _module(cuda_device, 256, 2, 8, 2, seed=12)
+    B, F = 2, 40
+    x = torch.from_numpy(O.make_input(B, F, 17, 9)).to(cuda_device)
+    w = torch.randn(B, F, 17, 3, generator=torch.Generator().manual_seed(6)).to(cuda_device)
+    lib = _lib.load()
+    nb3, nb1 = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(lib.mb_saved_bytes(m._state_for(x.device).handle, B, F, ctypes.byref(nb3)))
+    m.set_math_mode("bf16")
+    _lib.check(lib.mb_saved_bytes(m._state_for(x.device).handle, B, F, ctypes.byref(nb1)))
+    M = B * F * 17
+    assert nb1.value - nb3.value >= 8 * M * 4 * 256 * 2          # 4 attention sublayers x depth 2 x (3C + C) bf16
+    out = m(x)
+    (out * w).sum().backward()
+    grads_ref, y_ref = _reference_grads(m, x, w, False)
+    assert float((out.detach().double() - y_ref).abs().max()) < 3e-2 * float(y_ref.abs().max())
+    names = [n for n, _ in m.named_parameters()]
+    order = {id(p): i for i, p in enumerate(m._ordered_params())}
+    worst = (0.0, "")
+    for n, p in m.named_parameters():
+        if n.startswith("ts_attn."):
+            continue
+        gr = grads_ref[order[id(p)]]
+        den = float(gr.norm())
+        if den == 0:
+            continue
+        rel = float((p.grad.double() - gr).norm()) / den
+        cos = float((p.grad.double() * gr).sum()) / (float(p.grad.double().norm()) * den)
+        worst = max(worst, (rel, n))
+        assert rel < 1e-1 and cos > 0.995, (n, rel, cos)
+    print(f"bf16 mode (saved attention operands): worst per-parameter rel L2 {worst[0]:.3e} ({worst[1]}) over {len(names)} tensors")
