@@ -4,8 +4,11 @@
     PYTHONPATH=/root/repo/shim:/path/to/MotionBERT python -P train.py ...   # reference scripts unchanged
 
 The package holds only what the hot path needs: `csrc/` (CUDA kernels + the C ABI of
-include/motionbert_b200.h), the ctypes binding (`_lib`), and the host-side mirror of the reference
-class (`dstformer`).  Importing it never builds anything; `python -m motionbert_b200.build` does.
+include/motionbert_b200.h), the ctypes binding (`_lib`), the host-side mirror of the reference
+class (`dstformer`, with `_autograd` wiring `loss.backward()` to the native backward), and the two
+steps either side of the path: `loss` (pretrain losses fused with their gradient), `tta` (flip-TTA as
+one call), `dist` (sharding + gradient exchange).  Importing it never builds anything;
+`python -m motionbert_b200.build` does.
 """
 from .dstformer import DSTformer  # noqa: F401
 

@@ -4,7 +4,8 @@ Same constructor signature, same parameter tree (260 tensors, identical names / 
 consumption), same `forward(x, return_rep=False)` / `get_representation(x)` / `get_classifier()` /
 `reset_classifier()` surface -- so `lib/utils/learning.py::load_backbone`, `ActionNet`, `MeshRegressor`,
 `nn.DataParallel`, `load_state_dict(strict=True)` and `partial_train_layers` keep working unchanged --
-but the forward is ONE call into the sm_100a CUDA library through the C ABI (`mb_forward`).
+but the forward is ONE call into the sm_100a CUDA library through the C ABI (`mb_forward`; under autograd
+`mb_forward_train`, with `loss.backward()` running `mb_backward`).
 
 The sub-modules below (`nn.Linear`, `nn.LayerNorm`) are parameter containers only; they are never
 called.  There is no CPU and no PyTorch-op fallback for the forward: a CPU tensor or a missing
