@@ -115,3 +115,25 @@ def test_backward_phase_of_every_parameter_matches_its_name():
             assert k == 3 + 1, n
         else:
             assert k == 0 and (n.startswith("norm.") or n.startswith("pre_logits") or n.startswith("head.")), n
+
+
+def test_gradient_allreduce_needs_a_process_group_and_can_be_switched_off():
+    from motionbert_b200 import DSTformer
+    m = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2)
+    assert m._grad_sync is None
+    with pytest.raises(RuntimeError, match="process group"):
+        m.enable_gradient_allreduce()
+    assert m.enable_gradient_allreduce(enabled=False) is m and m._grad_sync is None
+
+
+def test_native_backward_eligibility_is_decided_on_the_host():
+    import torch
+
+    from motionbert_b200 import DSTformer
+    m = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2)
+    x = torch.zeros(1, 2, 17, 3)
+    assert m._native_backward_ok(x, None)                      # fp32 contiguous parameters on x's device
+    m.ts_attn[0].weight.data = m.ts_attn[0].weight.data.double()
+    assert not m._native_backward_ok(x, None)                  # non-fp32 parameter -> torch-op fallback
+    m2 = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2, att_fuse=False)
+    assert not m2._native_backward_ok(x, None)                 # no fusion head -> fallback
