@@ -253,7 +253,7 @@ def run_train(args, device, world, rank, local_rank, dist, D):
     n_param = sum(p.numel() for p in params)
     from motionbert_b200 import _lib
     lib = _lib.load()
-    hnd = model._state_for(device).handle
+    hnd = model._state_for(device, model.train_math_mode).handle
     # kernels of this library per step: forward + backward + fused loss (2); the per-step weight re-pack is not counted
     launches_per_step = _lib.check(lib.mb_forward_launch_count(hnd, 1, 0)) + _lib.check(lib.mb_backward_launch_count(hnd, 0, 0)) + 2
     line = {
@@ -293,15 +293,15 @@ def main():
                     help="forward = BASELINE config 2 (the headline); train = config 3/4 pretrain step (fwd+bwd+AdamW)")
     ap.add_argument("--batch", type=int, default=None, help="sequences per GPU per step (default 256 forward / 128 train)")
     ap.add_argument("--frames", type=int, default=243)
-    ap.add_argument("--math", default=None, choices=["bf16x3", "bf16"],
-                    help="default bf16x3 (fp32 parity) for forward, bf16 for train (config 3 is a bf16 step)")
+    ap.add_argument("--math", default=None, choices=["f16c", "bf16x3", "bf16"],
+                    help="default f16c (fp32 parity, 2 pass-equivalents) for forward, bf16 for train (config 3 is a bf16 step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.batch is None:
         args.batch = 128 if args.mode == "train" else 256
     if args.math is None:
-        args.math = "bf16" if args.mode == "train" else "bf16x3"
+        args.math = "bf16" if args.mode == "train" else "f16c"
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -404,10 +404,10 @@ def main():
     gemm_flop = gemm_flops_per_sequence(cfg["dim_feat"], hidden, T) * B
     achieved_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     total_flop = flops_per_sequence(cfg["dim_feat"], hidden, T) * B
-    passes = 3 if args.math == "bf16x3" else 1
+    passes = {"bf16x3": 3, "f16c": 2, "bf16": 1}[args.math]
     # DRAM traffic of the GEMM class from the committed ncu --set full capture of this same configuration
     traffic, traffic_src = None, None
-    if args.model == "base" and B == 256 and T == 243 and passes == 3:
+    if args.model == "base" and B == 256 and T == 243 and passes == 2:
         import glob
         for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
             try:
@@ -441,7 +441,9 @@ def main():
         "metric": f"sequences/sec DSTformer-{args.model} fwd (Bx{T}x17)",
         "value": value, "unit": "sequences/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x3 (fp32-parity split-bf16 tensor-core arithmetic, fp32 accumulate/residual)" if passes == 3 else "bf16",
+        "dtype": {3: "bf16x3 (fp32-parity split-bf16 tensor-core arithmetic, fp32 accumulate/residual)",
+                  2: "f16c (fp32-parity: fp16 tensor-core pass + e5m2 compensation pass, fp32 accumulate/residual)",
+                  1: "bf16"}[passes],
         "data": "synthetic",
         "config": {"workload": f"BASELINE config 2: DSTformer-{args.model} (depth=5, dim={cfg['dim_feat']}, 8 heads) forward, "
                                f"B={B} per GPU, T={T}, 17 joints, fp32 I/O", "global_batch": world * B, "seq_len": T,

@@ -43,10 +43,13 @@ typedef enum MbStatus {
     MB_ERR_WORKSPACE = -6   /* workspace too small                                                          */
 } MbStatus;
 
-/* Arithmetic mode of the GEMM-shaped work (operands are always bf16 on the tensor cores, fp32 accumulate). */
+/* Arithmetic mode of the GEMM-shaped work (tensor-core operand formats; fp32 accumulate in all modes). */
 typedef enum MbMath {
-    MB_MATH_BF16X3 = 0,     /* x = hi + lo split, 3 MMA passes: fp32 parity (~1e-5 rel)  -- default, "fp32" configs */
-    MB_MATH_BF16 = 1        /* single bf16 pass: for the reference's bf16/AMP-style training configs             */
+    MB_MATH_BF16X3 = 0,     /* x = hi + lo bf16 split, 3 MMA passes: fp32 parity (~1.5e-5 rel); training forward      */
+    MB_MATH_BF16 = 1,       /* single bf16 pass: for the reference's bf16/AMP-style training configs                 */
+    MB_MATH_F16C = 2        /* "F16C": x = h + l, one fp16 pass + both cross terms as ONE e5m2 pass (K = 32 per
+                             * instruction at twice the rate) = 2 pass-equivalents: fp32 parity (~7e-5 rel, inside the
+                             * 1e-3 / 0.1 mm targets) -- the inference default.  Forward only (mb_forward).          */
 } MbMath;
 
 /* Mirrors the constructor arguments of DSTformer.__init__ (DSTformer.py:270-273) as the factory passes

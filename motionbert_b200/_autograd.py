@@ -3,129 +3,43 @@
 Forward = the sm_100a CUDA library (`mb_forward`, or `mb_forward_train` when a gradient is needed).
 Backward = `mb_backward`: hand-written tcgen05 data-/weight-gradient GEMMs,
 attention-core backward and CUDA-core LayerNorm / GELU / fusion / embed kernels, bf16 single-pass arithmetic.
-`recompute_forward` below is a differentiable torch-op restatement kept for (a) the gradient-parity tests and
-(b) the rare configurations the native backward does not cover (no fusion head, dim_out > 8): there the backward
-recomputes the chain with torch CUDA ops under autograd.  No forward / inference call uses it.
+There is no PyTorch-op fallback: configurations the native backward does not cover raise.
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as Fn
-
-
-def _attention(x, qkv_w, qkv_b, proj_w, proj_b, temporal, F, H, scale):
-    BF, J, C = x.shape
-    d = C // H
-    qkv = Fn.linear(x, qkv_w, qkv_b).reshape(BF, J, 3, H, d).permute(2, 0, 3, 1, 4)
-    q, k, v = qkv[0], qkv[1], qkv[2]
-    if temporal:
-        q = q.reshape(-1, F, H, J, d).permute(0, 2, 3, 1, 4)
-        k = k.reshape(-1, F, H, J, d).permute(0, 2, 3, 1, 4)
-        v = v.reshape(-1, F, H, J, d).permute(0, 2, 3, 1, 4)
-        o = Fn.scaled_dot_product_attention(q, k, v, scale=scale)
-        o = o.permute(0, 3, 2, 1, 4).reshape(BF, J, C)
-    else:
-        o = Fn.scaled_dot_product_attention(q, k, v, scale=scale)
-        o = o.transpose(1, 2).reshape(BF, J, C)
-    return Fn.linear(o, proj_w, proj_b)
-
-
-def recompute_forward(mod, x, return_rep, dp_scale, P):
-    """Differentiable torch-op restatement of the forward used only inside backward."""
-    B, F, J, _ = x.shape
-    C, H = mod.dim_feat, mod.num_heads
-    scale = mod.qk_scale or (C // H) ** -0.5
-    it = iter(P)
-    nxt = lambda: next(it)   # noqa: E731
-    temp, pos, je_w, je_b = nxt(), nxt(), nxt(), nxt()
-    blocks = []
-    for _s in range(2):
-        for _i in range(mod.depth):
-            blocks.append([nxt() for _ in range(24)])
-    norm_w, norm_b, pl_w, pl_b, head_w, head_b = nxt(), nxt(), nxt(), nxt(), nxt(), nxt()
-    ts = [(nxt(), nxt()) for _ in range(mod.depth)] if mod.att_fuse else None
-
-    h = Fn.linear(x.reshape(B * F, J, -1), je_w, je_b) + pos
-    h = (h.reshape(B, F, J, C) + temp[:, :F]).reshape(B * F, J, C)
-
-    def run_block(h, w, order, sub0):
-        (n1s_w, n1s_b, n1t_w, n1t_b, ps_w, ps_b, qs_w, qs_b, pt_w, pt_b, qt_w, qt_b,
-         n2s_w, n2s_b, n2t_w, n2t_b, f1s_w, f1s_b, f2s_w, f2s_b, f1t_w, f1t_b, f2t_w, f2t_b) = w
-        sub = sub0
-        for which in order:
-            if which == "S":
-                n1, n2 = (n1s_w, n1s_b), (n2s_w, n2s_b)
-                att, mlp = (qs_w, qs_b, ps_w, ps_b), (f1s_w, f1s_b, f2s_w, f2s_b)
-            else:
-                n1, n2 = (n1t_w, n1t_b), (n2t_w, n2t_b)
-                att, mlp = (qt_w, qt_b, pt_w, pt_b), (f1t_w, f1t_b, f2t_w, f2t_b)
-            y = _attention(Fn.layer_norm(h, (C,), n1[0], n1[1], mod.eps), *att, which == "T", F, H, scale)
-            if dp_scale is not None:
-                y = y * dp_scale[sub].view(-1, 1, 1)
-            h = h + y
-            sub += 1
-            y = Fn.layer_norm(h, (C,), n2[0], n2[1], mod.eps)
-            y = Fn.linear(Fn.gelu(Fn.linear(y, mlp[0], mlp[1])), mlp[2], mlp[3])
-            if dp_scale is not None:
-                y = y * dp_scale[sub].view(-1, 1, 1)
-            h = h + y
-            sub += 1
-        return h
-
-    for i in range(mod.depth):
-        x_st = run_block(h, blocks[i], "ST", i * 8)
-        x_ts = run_block(h, blocks[mod.depth + i], "TS", i * 8 + 4)
-        if ts is not None:
-            a = Fn.linear(torch.cat([x_st, x_ts], dim=-1), ts[i][0], ts[i][1]).softmax(dim=-1)
-            h = x_st * a[:, :, 0:1] + x_ts * a[:, :, 1:2]
-        else:
-            h = (x_st + x_ts) * 0.5
-    h = Fn.layer_norm(h, (C,), norm_w, norm_b, mod.eps).reshape(B, F, J, C)
-    rep = torch.tanh(Fn.linear(h, pl_w, pl_b))
-    return rep if return_rep else Fn.linear(rep, head_w, head_b)
 
 
 class DSTformerFunction(torch.autograd.Function):
-    """forward = mb_forward_train (or mb_forward), backward = mb_backward (hand-written sm_100a kernels).
-    DropPath (per-frame scale vector) and the gradient w.r.t. the pose input are handled natively; configurations
-    the native backward does not cover (missing fusion head, dim_out > 8, non-fp32 parameters) fall back to
-    back-propagating through `recompute_forward` with torch CUDA ops."""
+    """forward = mb_forward_train, backward = mb_backward (hand-written sm_100a kernels).  DropPath (per-frame scale
+    vector), the gradient w.r.t. the pose input and `att_fuse=False` (constant 0.5 / 0.5 fusion) are handled natively."""
 
     @staticmethod
     def forward(ctx, mod, x, return_rep, dp_scale, *params):
         ctx.mod = mod
         ctx.return_rep = return_rep
         ctx.dp_scale = dp_scale
-        ctx.native = mod._native_backward_ok(x, dp_scale)
+        mod._check_native_backward(x)
         with torch.no_grad():
-            if ctx.native:
-                out, rep, saved = mod._launch_train(x, not return_rep, dp_scale)
-                # the activation region goes through save_for_backward so that autograd releases it right after the
-                # backward (unless retain_graph): two steps' regions never coexist in a train.py-style loop
-                ctx.save_for_backward(x, rep, saved)
-                ctx.pack_versions = tuple(p._version for p in params)
-            else:
-                out, rep = mod._launch(x, not return_rep, return_rep, dp_scale)
-                ctx.save_for_backward(x, *params)
+            out, rep, saved = mod._launch_train(x, not return_rep, dp_scale)
+            # the activation region goes through save_for_backward so that autograd releases it right after the
+            # backward (unless retain_graph): two steps' regions never coexist in a train.py-style loop
+            ctx.save_for_backward(x, rep, saved)
+            ctx.param_versions = tuple(p._version for p in params)
         return rep if return_rep else out
 
     @staticmethod
     def backward(ctx, grad):
-        if ctx.native:
-            x, rep, saved = ctx.saved_tensors
-            g = grad.contiguous().float()
-            grads, d_x = ctx.mod._launch_backward(x, rep, saved, None if ctx.return_rep else g,
-                                                  g if ctx.return_rep else None, ctx.dp_scale, ctx.needs_input_grad[1])
-            gp = [gr if ctx.needs_input_grad[4 + i] else None for i, gr in enumerate(grads)]
-            return (None, d_x, None, None, *gp)
-        x, *params = ctx.saved_tensors
-        with torch.enable_grad():
-            xs = x.detach().requires_grad_(ctx.needs_input_grad[1])
-            ps = [p.detach().requires_grad_(ctx.needs_input_grad[4 + i]) for i, p in enumerate(params)]
-            y = recompute_forward(ctx.mod, xs, ctx.return_rep, ctx.dp_scale, ps)
-            wanted = [t for t in [xs] + ps if t.requires_grad]
-            grads = torch.autograd.grad(y, wanted, grad.contiguous(), allow_unused=True)
-        gi = iter(grads)
-        gx = next(gi) if xs.requires_grad else None
-        gp = [next(gi) if p.requires_grad else None for p in ps]
-        return (None, gx, None, None, *gp)
+        mod = ctx.mod
+        live = [p for p in mod._ordered_params() if p is not None]
+        if tuple(p._version for p in live) != ctx.param_versions:
+            raise RuntimeError("a DSTformer parameter was modified in place between forward and backward: the saved "
+                               "activations belong to the old weights (PyTorch would raise 'modified by an inplace "
+                               "operation' here)")
+        x, rep, saved = ctx.saved_tensors
+        g = grad.contiguous().float()
+        grads, d_x = mod._launch_backward(x, rep, saved, None if ctx.return_rep else g,
+                                          g if ctx.return_rep else None, ctx.dp_scale, ctx.needs_input_grad[1])
+        skip = mod._head_param_slots() if ctx.return_rep else ()      # the head is not part of get_representation()
+        gp = [gr if (ctx.needs_input_grad[4 + i] and i not in skip) else None for i, gr in enumerate(grads)]
+        return (None, d_x, None, None, *gp)

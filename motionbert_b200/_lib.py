@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libmotionbert_b200.so")
 
 MB_MATH_BF16X3 = 0
 MB_MATH_BF16 = 1
+MB_MATH_F16C = 2
 MB_FLAG_REF_GEMM = 0x1
 MB_FLAG_REF_ATTN_T = 0x2
 MB_FLAG_GEMM_1CTA = 0x4

@@ -30,6 +30,7 @@ struct AttnSParams {
     float scale_log2e;
     __nv_bfloat16* out_hi;   // [M, C]
     __nv_bfloat16* out_lo;
+    int out_f16c;            // != 0: out_hi is an F16C row buffer [M][C] (see AttnTParams)
 };
 
 template <int HD, int PASSES>
@@ -267,7 +268,16 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 4-D (
                 uint32_t r[32];
                 tmem_ld32(tO + lane_off + c0, r);
                 tmem_ld_wait();
-                if (ok) {
+                if (ok && p.out_f16c) {
+                    uint8_t* rowp = reinterpret_cast<uint8_t*>(p.out_hi) + tok * p.C * 4;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float xv[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) xv[k] = __uint_as_float(r[16 * q + k]) * inv;
+                        store16_f16c(rowp, h * HD + c0 + 16 * q, xv);
+                    }
+                } else if (ok) {
                     const size_t ob = tok * p.C + h * HD + c0;
                     uint32_t hi[16], lo[16];
 #pragma unroll

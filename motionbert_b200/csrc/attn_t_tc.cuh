@@ -32,7 +32,30 @@ struct AttnTParams {
     float scale_log2e;       // d^-1/2 * log2(e)
     __nv_bfloat16* out_hi;   // [M, C]
     __nv_bfloat16* out_lo;   // may be null (PASSES == 1)
+    int out_f16c;            // != 0: out_hi is an F16C row buffer [M][C] (ptx.cuh) for an F16C-mode projection GEMM
 };
+
+// 16 consecutive output values of one row -> F16C block pieces at column `col` (multiple of 16) of row buffer `rowp`
+__device__ __forceinline__ void store16_f16c(uint8_t* rowp, int col, const float (&x)[16]) {
+    uint8_t* blk = rowp + static_cast<size_t>(col >> 5) * 128;
+    const int e = col & 31;
+    uint32_t h[8], l[4], g[4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float xv[8] = {x[8 * q], x[8 * q + 1], x[8 * q + 2], x[8 * q + 3], x[8 * q + 4], x[8 * q + 5], x[8 * q + 6], x[8 * q + 7]};
+        uint32_t h4[4], l2[2], g2[2];
+        split8_f16c(xv, h4, l2, g2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[4 * q + i] = h4[i];
+        l[2 * q] = l2[0]; l[2 * q + 1] = l2[1];
+        g[2 * q] = g2[0]; g[2 * q + 1] = g2[1];
+    }
+    uint4* hp = reinterpret_cast<uint4*>(blk + 2 * e);
+    hp[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    hp[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>(blk + 64 + e) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(blk + 96 + e) = make_uint4(g[0], g[1], g[2], g[3]);
+}
 
 template <int HD, int PASSES>
 struct AttnCfg {
@@ -275,7 +298,12 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                     uint32_t r[16];
                     tmem_ld16(tmem_O + lane_off + c0, r);
                     tmem_ld_wait();
-                    if (ok) {
+                    if (ok && p.out_f16c) {
+                        float xv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) xv[i] = __uint_as_float(r[i]) * inv;
+                        store16_f16c(reinterpret_cast<uint8_t*>(p.out_hi) + tok * p.C * 4, h * HD + c0, xv);
+                    } else if (ok) {
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)

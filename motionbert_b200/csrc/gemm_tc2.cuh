@@ -39,8 +39,12 @@ struct Gemm2Cfg {
     static constexpr int NBUF = (EW == 16 && TWO_PLANES) ? 1 : 2;
     static constexpr int BUF_BYTES = (EW == 16 && !TWO_PLANES) ? 2048 : 4096;
     static constexpr int STAGING_PER_WARP = (EPI == EPI_RESID) ? 12288 : NBUF * BUF_BYTES;
-    static constexpr int BK = (PASSES == 3) ? 32 : 64;
-    static constexpr int SWZ = BK * 2;
+    // PASSES == 2 is the F16C mode (ptx.cuh): one SWIZZLE_128B row of [32 f16 | 32 lo8 | 32 hi8] per 32-element K block,
+    // 2 fp16 MMAs + 2 e5m2 MMAs per block = 2 pass-equivalents of the 16-bit tensor rate.
+    static constexpr bool F16C = (PASSES == 2);
+    static constexpr int BK = (PASSES == 1) ? 64 : 32;
+    static constexpr int SWZ = F16C ? 128 : BK * 2;
+    static constexpr int KSTEP16 = SWZ / 2;                    // tensor-map (16-bit unit) coordinate step per stage
     static constexpr uint32_t LAYOUT = (SWZ == 128) ? 2u : 4u;
     static constexpr int PLANES = (PASSES == 3) ? 2 : 1;
     static constexpr int A_PLANE = 128 * SWZ;                  // this CTA's 128 rows of A
@@ -56,7 +60,9 @@ struct Gemm2Cfg {
 // B_MN = true is the data-gradient form  dX[M, Kf] = G[M, Nf] * W[Nf, Kf]  (backward groundwork, row a15): the
 // contraction runs over W's ROW index, so the very same packed W planes are consumed as an MN-major B operand
 // (64-column SWIZZLE_128B blocks, LBO = block stride) instead of packing a transposed copy of every weight.
-template <int PASSES, int EPI, bool B_MN = false, int EW = G2_EPI_WARPS>
+// OUT16C: the split output (tmS) is an F16C row buffer (2-D map, box (64 x 16-bit, 32 rows), SWIZZLE_128B) instead of
+// bf16 hi/lo planes.
+template <int PASSES, int EPI, bool B_MN = false, int EW = G2_EPI_WARPS, bool OUT16C = (PASSES == 2)>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EW), 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane), box (BK, 128, PLANES)
              const __grid_constant__ CUtensorMap tmB,   // bf16 3D (K, N, plane), box (BK, 128, PLANES); B_MN: (Kf, Nf, plane), box (64, BK, 1)
@@ -73,7 +79,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     constexpr bool kF32Out = (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32);
     constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT ||
                                 EPI == EPI_BIAS_GELU_PAIR || EPI == EPI_GELUBWD_SPLIT);
-    constexpr bool kTwoPlanes = Cfg::TWO_PLANES;                                  // second bf16 plane: lo, or gelu(y)
+    constexpr bool kTwoPlanes = (PASSES == 3 || (PASSES == 2 && !OUT16C)) || (EPI == EPI_BIAS_GELU_PAIR);   // second bf16 plane: lo, or gelu(y)
+    static_assert(!(B_MN && PASSES == 2), "the F16C mode has no MN-major weight form (backward runs in bf16)");
+    static_assert(!OUT16C || EW == 8, "F16C output: 8 epilogue warps");
     constexpr bool kDoubleLd = !kResid && EW == 8;                               // register double-buffered tcgen05.ld
     constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32);
 
@@ -136,9 +144,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     uint8_t* sB = sA + Cfg::A_BYTES;
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                    tma_load_3d_2cta(sA, &tmA, full_leader, kb * Cfg::BK, a_row, 0);
+                    tma_load_3d_2cta(sA, &tmA, full_leader, kb * Cfg::KSTEP16, a_row, 0);
                     if (!B_MN) {
-                        tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::BK, b_row, 0);
+                        tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::KSTEP16, b_row, 0);
                     } else {
                         // this CTA's 128 output columns = two 64-column blocks of [BK contraction rows][128 B] per plane
                         for (int pl = 0; pl < Cfg::PLANES; ++pl)
@@ -153,7 +161,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
         if (rank == 0) {
-            constexpr uint32_t IDESC = umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
+            constexpr uint32_t IDESC = Cfg::F16C ? umma_idesc_fmt(256, 256, 0, 0, 0, 0)      // f16 x f16
+                                                 : umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
+            constexpr uint32_t IDESC8 = umma_idesc_fmt(256, 256, 1, 1, 0, 0);                  // e5m2 x e5m2
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -175,8 +185,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                                                    : umma_smem_desc(sB, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                         const uint64_t b_lo = B_MN ? umma_smem_desc(sB + Cfg::B_PLANE, Cfg::BK * 128, 1024, 2u)
                                                    : umma_smem_desc(sB + Cfg::B_PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
+                        if (Cfg::F16C) {
+                            // K-slices of the 128-byte block: f16 at +0 / +32 B, lo8 at +64 B, hi8 at +96 B (units of 16 B)
+                            umma_ss_2cta(d_tmem, a_hi, b_hi, IDESC, kb != 0);
+                            umma_ss_2cta(d_tmem, a_hi + 2, b_hi + 2, IDESC, 1);
+                            umma_ss_2cta_f8(d_tmem, a_hi + 4, b_hi + 6, IDESC8, 1);     // (al 2^6) * (wh 2^-6)
+                            umma_ss_2cta_f8(d_tmem, a_hi + 6, b_hi + 4, IDESC8, 1);     // (ah 2^-6) * (wl 2^6)
+                        }
 #pragma unroll
-                        for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
+                        for (int ks = 0; ks < (Cfg::F16C ? 0 : Cfg::BK / 16); ++ks) {
                             const uint64_t koff = static_cast<uint64_t>((ks * 32) >> 4);
                             const uint64_t boff = B_MN ? static_cast<uint64_t>((ks * 16 * 128) >> 4) : koff;   // 16 rows down
                             if (PASSES == 3) {
@@ -361,7 +378,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                             make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
                 const bool do_split = kSplitOut && (!kResid || p.out_hi != nullptr);   // block-final residuals feed
-                if (do_split) {                                                        // only the fp32 fusion kernel
+                if (do_split && OUT16C) {
+                    // one F16C block per row: 16-byte units 0..3 = 32 f16, 4..5 = 32 lo8, 6..7 = 32 hi8 (SWIZZLE_128B staging)
+                    uint32_t l8[8], g8[8];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float xv[8] = {v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3],
+                                             v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]};
+                        uint32_t h4[4], l2[2], g2[2];
+                        split8_f16c(xv, h4, l2, g2);
+                        *reinterpret_cast<uint4*>(ss + lane * 128 + ((g ^ sw128) << 4)) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                        l8[2 * g] = l2[0]; l8[2 * g + 1] = l2[1];
+                        g8[2 * g] = g2[0]; g8[2 * g + 1] = g2[1];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        *reinterpret_cast<uint4*>(ss + lane * 128 + (((4 + u) ^ sw128) << 4)) =
+                            make_uint4(l8[4 * u], l8[4 * u + 1], l8[4 * u + 2], l8[4 * u + 3]);
+                        *reinterpret_cast<uint4*>(ss + lane * 128 + (((6 + u) ^ sw128) << 4)) =
+                            make_uint4(g8[4 * u], g8[4 * u + 1], g8[4 * u + 2], g8[4 * u + 3]);
+                    }
+                } else if (do_split) {                                                 // only the fp32 fusion kernel
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -387,7 +424,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 __syncwarp();
                 if (lane == 0) {
                     if (kF32Out) tma_store_2d(&tmX, xs, col0, rowb);
-                    if (do_split) tma_store_3d(&tmS, ss, col0, rowb, 0);
+                    if (do_split) {
+                        if (OUT16C) tma_store_2d(&tmS, ss, col0 * 2, rowb);
+                        else tma_store_3d(&tmS, ss, col0, rowb, 0);
+                    }
                     tma_store_commit();
                 }
             }

@@ -38,6 +38,26 @@ using namespace mb;
         }                                                         \
     } while (0)
 
+// same, for the kernels that emit GEMM operand rows: F16C selects the F16C row format (ptx.cuh) over bf16 hi/lo planes
+#define ROWK_FMT(K, F16C_, ...)                                          \
+    do {                                                                 \
+        if (F16C_) {                                                     \
+            switch (C / 128) {                                           \
+                case 2: K<2, true><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+                case 4: K<4, true><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+                case 6: K<6, true><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+                default: K<8, true><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+            }                                                            \
+        } else {                                                         \
+            switch (C / 128) {                                           \
+                case 2: K<2, false><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+                case 4: K<4, false><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+                case 6: K<6, false><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+                default: K<8, false><<<rows_grid, 256, 0, st>>>(__VA_ARGS__); break; \
+            }                                                            \
+        }                                                                \
+    } while (0)
+
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, ...) {
@@ -118,6 +138,22 @@ static int make_split_store_tmap(CUtensorMap* out, const void* hi, uint64_t rows
     return make_tmap(out, hi, 3, dims, str, box, 64, 2);
 }
 
+// F16C row buffer [rows][cols] (4 bytes per element, 128-byte blocks of 32 elements; ptx.cuh) seen as 16-bit units:
+// GEMM operand map, box = one block x `box_rows` rows, SWIZZLE_128B ...
+static int make_f16c_operand_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    const uint64_t dims[3] = {2 * cols, rows, 1};
+    const uint64_t str[2] = {2 * cols, 2 * cols * rows};
+    const uint32_t box[3] = {64, box_rows, 1};
+    return make_tmap(out, base, 3, dims, str, box, 128, 2);
+}
+// ... and the epilogue's store map: one block x 32 rows per warp chunk
+static int make_f16c_store_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols) {
+    const uint64_t dims[2] = {2 * cols, rows};
+    const uint64_t str[1] = {2 * cols};
+    const uint32_t box[2] = {64, 32};
+    return make_tmap(out, base, 2, dims, str, box, 128, 2);
+}
+
 // ------------------------------------------------------------------------------------ per-device init
 struct DevInfo {
     int sms = 0;
@@ -156,6 +192,13 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         SET_GEMM2(1, EPI_LN_SPLIT); SET_GEMM2(1, EPI_LN_GELU_SPLIT); SET_GEMM2(1, EPI_RESID);
         SET_GEMM2(1, EPI_LN_TANH_F32); SET_GEMM2(1, EPI_BIAS_F32);
 #undef SET_GEMM2
+        // F16C mode (2 pass-equivalents): F16C-row outputs, except the qkv projection which can also emit bf16 planes
+        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_SPLIT>, Gemm2Cfg<2, EPI_LN_SPLIT>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_SPLIT, false, 8, false>, Gemm2Cfg<2, EPI_LN_SPLIT>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_GELU_SPLIT>, Gemm2Cfg<2, EPI_LN_GELU_SPLIT>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_RESID>, Gemm2Cfg<2, EPI_RESID>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_F32>, Gemm2Cfg<2, EPI_LN_TANH_F32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_BIAS_F32>, Gemm2Cfg<2, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<3, EPI_BIAS_F32, true>, Gemm2Cfg<3, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
         // single-pass bf16-plane epilogues run with 16 epilogue warps (gemm_tc2.cuh)
@@ -277,7 +320,8 @@ static void prof_mark(const MbEncoder* ce, cudaStream_t st, int cls) {
     ++e->events_used;
 }
 
-static int passes_of(const MbDesc& d) { return d.math == MB_MATH_BF16 ? 1 : 3; }
+static int passes_of(const MbDesc& d) { return d.math == MB_MATH_BF16 ? 1 : d.math == MB_MATH_F16C ? 2 : 3; }
+static bool is_f16c(const MbDesc& d) { return d.math == MB_MATH_F16C; }
 
 static void add_param(MbEncoder* e, const std::string& n, int64_t numel) {
     e->index[n] = static_cast<int>(e->names.size());
@@ -391,7 +435,8 @@ static int check_desc(const MbDesc* d) {
     if (d->maxlen < 1 || d->maxlen > 256) return fail(MB_ERR_INVALID, "maxlen=%d unsupported (1..256)", d->maxlen);
     if (d->dim_in < 1 || d->dim_in > 8) return fail(MB_ERR_INVALID, "dim_in=%d unsupported (1..8)", d->dim_in);
     if (d->dim_out < 1 || d->depth < 1) return fail(MB_ERR_INVALID, "dim_out/depth must be positive");
-    if (d->math != MB_MATH_BF16X3 && d->math != MB_MATH_BF16) return fail(MB_ERR_INVALID, "unknown math mode %d", d->math);
+    if (d->math != MB_MATH_BF16X3 && d->math != MB_MATH_BF16 && d->math != MB_MATH_F16C)
+        return fail(MB_ERR_INVALID, "unknown math mode %d", d->math);
     if (!(d->eps > 0.f)) return fail(MB_ERR_INVALID, "eps must be positive");
     return MB_OK;
 }
@@ -457,8 +502,16 @@ extern "C" int mb_pack_weights(MbEncoder* enc, const float* const* params, void*
         pack_linear_kernel<<<grid, 256, 0, st>>>(
             params[L.p_w], params[L.p_b], L.ln ? params[L.p_g] : nullptr, L.ln ? params[L.p_beta] : nullptr, L.N, L.K,
             reinterpret_cast<__nv_bfloat16*>(base + L.off_hi), reinterpret_cast<__nv_bfloat16*>(base + L.off_lo),
-            reinterpret_cast<float*>(base + L.off_c), L.ln ? reinterpret_cast<float*>(base + L.off_s) : nullptr);
+            reinterpret_cast<float*>(base + L.off_c), L.ln ? reinterpret_cast<float*>(base + L.off_s) : nullptr,
+            is_f16c(enc->d) ? 1 : 0);
         LAUNCH_CHECK("pack_linear_kernel");
+        if (is_f16c(enc->d)) {
+            // F16C rows [N][K] occupy the (adjacent) hi + lo plane regions; only the 2-CTA operand map exists
+            if (L.off_lo != L.off_hi + static_cast<size_t>(L.N) * L.K * 2) return fail(MB_ERR_INVALID, "internal: packed planes not adjacent");
+            int rc = make_f16c_operand_tmap(&L.tmap2, base + L.off_hi, L.N, L.K, 128);
+            if (rc) return rc;
+            continue;
+        }
         // hi and lo planes are 1024-aligned but not necessarily adjacent: describe them as 2 planes with the
         // actual plane stride
         const uint64_t dims[3] = {static_cast<uint64_t>(L.K), static_cast<uint64_t>(L.N), 2};
@@ -536,7 +589,10 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
     uint8_t* base = static_cast<uint8_t*>(ws);
     const uint64_t M = static_cast<uint64_t>(B) * F * d.num_joints;
     const uint64_t C = d.dim_feat;
-    const int passes = passes_of(d);
+    const bool f16c = is_f16c(d);
+    // F16C: every GEMM operand buffer is an F16C row buffer (in the adjacent hi + lo plane regions).  The attention
+    // kernels read F16C rows too (P->attn_f16c), except behind the test flags that keep the bf16 hi/lo planes.
+    const int passes = f16c ? 3 : passes_of(d);      // plane structure of the bf16-plane maps below
     P->ws = ws; P->B = B; P->F = F;
     int rc;
     for (int i = 0; i < 4; ++i) {
@@ -545,6 +601,13 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
         a.hi = reinterpret_cast<__nv_bfloat16*>(base + w.act_hi[i]);
         a.lo = reinterpret_cast<__nv_bfloat16*>(base + w.act_lo[i]);
         a.stats = reinterpret_cast<float*>(base + w.act_st[i]);
+        if (f16c) {
+            // (the F16C rows [M][C] x 4 B start at the hi plane and run into the lo plane region that follows it)
+            if ((rc = make_f16c_operand_tmap(&a.tmap, a.hi, M, C, GEMM_BM))) return rc;
+            if ((rc = make_f32_tile_tmap(&a.tm_x, a.x, M, C))) return rc;
+            if ((rc = make_f16c_store_tmap(&a.tm_st, a.hi, M, C))) return rc;
+            continue;
+        }
         const uint64_t dims[3] = {C, M, 2};
         const uint64_t str[2] = {C, (w.act_lo[i] - w.act_hi[i]) / 2};
         const int BK = passes == 3 ? 32 : 64;
@@ -570,6 +633,11 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
         if ((rc = make_tmap(&P->tm_ao, P->ao, 3, dims_a, str_a, box, BK * 2))) return rc;
         if ((rc = make_split_store_tmap(&P->tm_qkv_st, P->qkv, M, 3 * C, qkv_plane_el, passes))) return rc;
         if ((rc = make_split_store_tmap(&P->tm_hid_st, P->hid, M, d.hidden, qkv_plane_el, passes))) return rc;
+        if (f16c) {
+            if ((rc = make_f16c_operand_tmap(&P->tm_hid, P->hid, M, d.hidden, GEMM_BM))) return rc;
+            if ((rc = make_f16c_operand_tmap(&P->tm_ao, P->ao, M, C, GEMM_BM))) return rc;
+            if ((rc = make_f16c_store_tmap(&P->tm_hid_st, P->hid, M, d.hidden))) return rc;
+        }
     }
     {
         const int hd = d.dim_feat / d.num_heads;
@@ -599,6 +667,7 @@ struct EpiMaps {
     const CUtensorMap* resid = nullptr;   // fp32 residual tile source       (EPI_RESID)
     const CUtensorMap* out_x = nullptr;   // fp32 output                     (EPI_RESID / *_F32)
     const CUtensorMap* out_s = nullptr;   // bf16 hi/lo split output         (EPI_RESID / *_SPLIT)
+    bool split_bf16 = false;              // F16C mode: out_s is a bf16 hi/lo plane map (not an F16C row map)
 };
 
 template <int EPI>
@@ -613,6 +682,8 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
     if (passes == 1) p.out_lo = nullptr;
     prof_mark(e, st, EPI == EPI_LN_SPLIT ? PC_GEMM_QKV : EPI == EPI_LN_GELU_SPLIT ? PC_GEMM_FC1
                      : EPI == EPI_RESID ? PC_GEMM_RESID : PC_GEMM_TAIL);
+    if (passes == 2 && (flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA)))
+        return fail(MB_ERR_INVALID, "the CUDA-core / 1-CTA test GEMMs exist for the bf16 modes only (math mode F16C)");
     if (flags & MB_FLAG_REF_GEMM) {
         const long warps = static_cast<long>(p.M) * (p.N / STATS_GROUP);
         const int grid = static_cast<int>((warps + 7) / 8);
@@ -646,6 +717,10 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
     constexpr int EW1 = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) ? 16 : 8;   // single-pass epilogue warps
     if (passes == 3)
         gemm2_kernel<3, EPI><<<grid, G2_THREADS, Gemm2Cfg<3, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
+    else if (passes == 2 && EPI == EPI_LN_SPLIT && em.split_bf16)      // qkv planes for the bf16x3 attention kernels
+        gemm2_kernel<2, EPI, false, 8, false><<<grid, G2_THREADS, Gemm2Cfg<2, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
+    else if (passes == 2)
+        gemm2_kernel<2, EPI><<<grid, G2_THREADS, Gemm2Cfg<2, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else
         gemm2_kernel<1, EPI, false, EW1><<<grid, g2_threads(EW1), Gemm2Cfg<1, EPI, EW1>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     LAUNCH_CHECK("gemm2_kernel");
@@ -656,7 +731,10 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
                        size_t qkv_plane_el, size_t ao_plane_el, cudaStream_t st) {
     const MbDesc& d = e->d;
     const int C = d.dim_feat, H = d.num_heads, J = d.num_joints, hd = C / H;
-    const int passes = passes_of(d);
+    const bool f16c = is_f16c(d);
+    const int passes = f16c ? 3 : passes_of(d);      // F16C mode: qkv arrives as bf16 hi/lo planes, output leaves as F16C rows
+    if (f16c && (flags & (MB_FLAG_REF_ATTN_S | MB_FLAG_REF_ATTN_T | MB_FLAG_ATTN_T_V2)))
+        return fail(MB_ERR_INVALID, "the CUDA-core / experimental test attention kernels exist for the bf16 modes only");
     const float scale = d.qk_scale > 0.f ? d.qk_scale : 1.0f / sqrtf(static_cast<float>(hd));   // DSTformer.py:94
     const __nv_bfloat16* q_hi = P.qkv;
     const __nv_bfloat16* q_lo = passes == 3 ? P.qkv + qkv_plane_el : nullptr;
@@ -676,6 +754,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
         sp.scale_log2e = scale * 1.4426950408889634f;
         sp.out_hi = o_hi;
         sp.out_lo = o_lo;
+        sp.out_f16c = f16c ? 1 : 0;
         const int prob = ((B * F + ATS_FRAMES - 1) / ATS_FRAMES) * H;
         const int grid = prob < e->dev.sms ? prob : e->dev.sms;
         if (hd == 64 && passes == 3) attn_s_tc_kernel<64, 3, false><<<grid, ATT_THREADS, AttnSCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_qkv_sp, sp);
@@ -692,6 +771,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
         sp.scale_log2e = scale * 1.4426950408889634f;
         sp.out_hi = o_hi;
         sp.out_lo = o_lo;
+        sp.out_f16c = f16c ? 1 : 0;
         const int prob = ((B * J + ATS_FRAMES - 1) / ATS_FRAMES) * H;
         const int grid = prob < e->dev.sms ? prob : e->dev.sms;
         if (hd == 64 && passes == 3) attn_s_tc_kernel<64, 3, true><<<grid, ATT_THREADS, AttnSCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_qkv_t32, sp);
@@ -714,6 +794,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     ap.scale_log2e = scale * 1.4426950408889634f;
     ap.out_hi = o_hi;
     ap.out_lo = o_lo;
+    ap.out_f16c = f16c ? 1 : 0;
     const int prob = B * J * H;
     const int grid = prob < e->dev.sms ? prob : e->dev.sms;
     if (flags & MB_FLAG_ATTN_T_V2) {
@@ -811,6 +892,8 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
     const size_t ao_plane_el = align_up(M_ * C * 2, 1024) / 2;
     const int rows_grid = (M + 7) / 8;
     const int passes = passes_of(d);
+    const bool f16c = is_f16c(d);
+    if (f16c && saved) return fail(MB_ERR_INVALID, "math mode F16C is forward-only: create the training handle with MB_MATH_BF16X3 or MB_MATH_BF16");
     int rc;
 
     // Residual-stream buffers.  Inference: four rotating buffers.  Training (saved != null): the bf16 operand planes
@@ -829,11 +912,11 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
 
     // embed (DSTformer.py:330-337) -> X0
     prof_mark(enc, st, PC_EMBED);
-    ROWK(embed_kernel,
+    ROWK_FMT(embed_kernel, f16c,
         x, d.dim_in, reinterpret_cast<const float*>(pk + enc->off_small[0]),
         reinterpret_cast<const float*>(pk + enc->off_small[1]), reinterpret_cast<const float*>(pk + enc->off_small[2]),
         reinterpret_cast<const float*>(pk + enc->off_small[3]), M, F, J, C, X0.x, X0.hi,
-        passes == 3 ? X0.lo : nullptr, X0.stats);
+        passes != 1 ? X0.lo : nullptr, X0.stats);
     LAUNCH_CHECK("embed_kernel");
 
     GemmParams base;
@@ -891,6 +974,7 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
         p.out_lo = AP->qkv + qkv_plane_el;
         EpiMaps em;
         em.out_s = &AP->tm_qkv_st;
+        em.split_bf16 = true;
         int r = launch_gemm<EPI_LN_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_QKV_T : L_QKV_S], pk, p, em, st);
         if (r) return r;
         r = launch_attn(enc, flags, temporal, *AP, B, F, qkv_plane_el, ao_plane_el, st);
@@ -958,10 +1042,10 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
         ActBuf Xn;
         if ((rc = slot_buf(0, sb + 9, &Xn))) return rc;
         prof_mark(enc, st, PC_FUSE);
-        ROWK(fuse_kernel,
+        ROWK_FMT(fuse_kernel, f16c,
             S2b.x, S1d.x, reinterpret_cast<const float*>(pk + enc->off_small[6]) + static_cast<size_t>(i) * 4 * C,
             reinterpret_cast<const float*>(pk + enc->off_small[7]) + static_cast<size_t>(i) * 2, M, C, Xn.x, Xn.hi,
-            passes == 3 ? Xn.lo : nullptr, Xn.stats);
+            passes != 1 ? Xn.lo : nullptr, Xn.stats);
         LAUNCH_CHECK("fuse_kernel");
         X0 = Xn;
     }
@@ -1073,6 +1157,14 @@ __global__ void split_flat_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat
     }
 }
 
+__global__ void merge_f16c_kernel(const uint8_t* rows, float* y, int M, int N) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < static_cast<size_t>(M) * N) {
+        const size_t r = i / N;
+        y[i] = f16c_decode(rows + r * N * 4, static_cast<int>(i % N));
+    }
+}
+
 struct LinScratch {
     size_t a_hi, a_lo, a_st, w_hi, w_lo, vc, vs, o_hi, o_lo, total;
 };
@@ -1124,14 +1216,16 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
     auto* vs = reinterpret_cast<float*>(b + s.vs);
     auto* o_hi = reinterpret_cast<__nv_bfloat16*>(b + s.o_hi);
     auto* o_lo = reinterpret_cast<__nv_bfloat16*>(b + s.o_lo);
-    const int passes = math == MB_MATH_BF16 ? 1 : 3;
+    const int passes = math == MB_MATH_BF16 ? 1 : math == MB_MATH_F16C ? 2 : 3;
+    if (passes == 2 && use_ref != 0) return fail(MB_ERR_INVALID, "F16C: production kernel only");
     {
         const int C = K;
         const int rows_grid = (M + 7) / 8;
-        ROWK(split_rows_kernel, A, M, K, a_hi, a_lo, a_st);
+        ROWK_FMT(split_rows_kernel, passes == 2, A, M, K, a_hi, a_lo, a_st);
     }
     LAUNCH_CHECK("split_rows_kernel");
-    pack_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, bias, ln ? gamma : nullptr, ln ? beta : nullptr, N, K, w_hi, w_lo, vc, vs);
+    pack_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, bias, ln ? gamma : nullptr, ln ? beta : nullptr, N, K, w_hi, w_lo, vc, vs,
+                                                     passes == 2 ? 1 : 0);
     LAUNCH_CHECK("pack_linear_kernel");
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -1166,6 +1260,11 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
         if ((rc = make_f32_tile_tmap(&tmR, resid ? resid : y, M, N))) return rc;
         if ((rc = make_f32_tile_tmap(&tmX, y, M, N))) return rc;
         if ((rc = make_split_store_tmap(&tmS, o_hi, M, N, (s.o_lo - s.o_hi) / 2, passes))) return rc;
+        if (passes == 2) {
+            if ((rc = make_f16c_operand_tmap(&tmA, a_hi, M, K, GEMM_BM))) return rc;
+            if ((rc = make_f16c_operand_tmap(&tmB2, w_hi, N, K, 128))) return rc;
+            if ((rc = make_f16c_store_tmap(&tmS, o_hi, M, N))) return rc;
+        }
     }
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
     const int grid = tiles < info.sms ? tiles : info.sms;
@@ -1176,6 +1275,8 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
         if (use_ref == 0) {                                                                                          \
             if (passes == 3)                                                                                         \
                 gemm2_kernel<3, E><<<grid2, G2_THREADS, Gemm2Cfg<3, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
+            else if (passes == 2)                                                                                    \
+                gemm2_kernel<2, E><<<grid2, G2_THREADS, Gemm2Cfg<2, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
             else                                                                                                     \
                 gemm2_kernel<1, E><<<grid2, G2_THREADS, Gemm2Cfg<1, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
         } else if (use_ref == 1) {                                                                                   \
@@ -1199,7 +1300,10 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
     LAUNCH_CHECK("test gemm");
     if (mode == EPI_LN_SPLIT || mode == EPI_LN_GELU_SPLIT) {
         const size_t n = static_cast<size_t>(M) * N;
-        merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(o_hi, passes == 3 ? o_lo : nullptr, y, n);
+        if (passes == 2)
+            merge_f16c_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(o_hi), y, M, N);
+        else
+            merge_planes_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(o_hi, passes == 3 ? o_lo : nullptr, y, n);
         LAUNCH_CHECK("merge_planes_kernel");
     }
     return MB_OK;

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -153,6 +155,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Same descriptor with explicit operand formats.  kind::f16: 0 = f16, 1 = bf16;  kind::f8f6f4: 0 = e4m3, 1 = e5m2.
+__host__ __device__ constexpr uint32_t umma_idesc_fmt(int M, int N, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (static_cast<uint32_t>(a_fmt) << 7) | (static_cast<uint32_t>(b_fmt) << 10) |
+           (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// 8-bit float operands (kind::f8f6f4, K = 32 per instruction, twice the bf16 rate), f32 accumulate in TMEM.
+__device__ __forceinline__ void umma_ss_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_f8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (thread = lane = row).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -298,6 +326,56 @@ __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, u
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+__device__ __forceinline__ void umma_ss_2cta_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ------------------------------------------------- "F16C" compensated split ---
+// x ~= h + l with h = f16_rn(x) (11 significant bits) and l = x - h.  A product a*w is evaluated as
+//      ah*wh                      one fp16 MMA pass (kind::f16)
+//    + q(al 2^6) * q(wh 2^-6)     } both cross terms in e5m2 (kind::f8f6f4, K = 32 per instruction at twice the
+//    + q(ah 2^-6) * q(wl 2^6)     } fp16 rate) -> together ONE more pass-equivalent instead of two
+// with q = e5m2 rounding (3 significant bits: the cross terms are 2^-11 of the product, so 3 bits put the error at
+// ~2^-15 per operand; measured on the whole network in scripts/emulate_math_modes.py).  The symmetric 2^+-6 scaling
+// keeps both 8-bit operands of a cross term in e5m2's normal range for O(1) activations and O(2^-5) weights, and makes
+// the SAME stored format usable as the A and as the B operand.
+// HBM / smem format ("F16C rows"): per 32 consecutive elements one 128-byte block
+//      [ 32 x f16 h | 32 x e5m2 (l 2^6) | 32 x e5m2 (h 2^-6) ]
+// i.e. 4 bytes per element like the bf16 hi/lo planes, but ONE contiguous SWIZZLE_128B row per 32-element K block:
+// K-slices at +0 / +32 B (f16, K = 16 each), +64 B (lo8, K = 32), +96 B (hi8, K = 32).
+constexpr float F16C_SCALE = 64.0f;
+// two values -> packed f16x2 (x0 low), packed lo8 x2 and hi8 x2 (x0 low byte)
+__device__ __forceinline__ void split2_f16c(float x0, float x1, uint32_t& h, uint32_t& lo8, uint32_t& hi8) {
+    const __half2 h2 = __floats2half2_rn(x0, x1);
+    h = *reinterpret_cast<const uint32_t*>(&h2);
+    const float2 hf = __half22float2(h2);
+    lo8 = __nv_cvt_float2_to_fp8x2(make_float2((x0 - hf.x) * F16C_SCALE, (x1 - hf.y) * F16C_SCALE), __NV_SATFINITE, __NV_E5M2);
+    const __half2 hs = __hmul2(h2, __floats2half2_rn(1.0f / F16C_SCALE, 1.0f / F16C_SCALE));
+    hi8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hs), __NV_SATFINITE, __NV_E5M2);
+}
+// 8 consecutive values -> 4 words of f16 pairs + 2 words of lo8 + 2 words of hi8
+__device__ __forceinline__ void split8_f16c(const float (&x)[8], uint32_t (&h)[4], uint32_t (&lo8)[2], uint32_t (&hi8)[2]) {
+    uint32_t l[4], g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2_f16c(x[2 * i], x[2 * i + 1], h[i], l[i], g[i]);
+    lo8[0] = l[0] | (l[1] << 16); lo8[1] = l[2] | (l[3] << 16);
+    hi8[0] = g[0] | (g[1] << 16); hi8[1] = g[2] | (g[3] << 16);
+}
+// decode element c of an F16C row (tests / CUDA-core reference kernels): h + l
+__device__ __forceinline__ float f16c_decode(const uint8_t* row, int c) {
+    const uint8_t* blk = row + static_cast<size_t>(c >> 5) * 128;
+    const int i = c & 31;
+    const float h = __half2float(*reinterpret_cast<const __half*>(blk + 2 * i));
+    const __half_raw lr = __nv_cvt_fp8_to_halfraw(blk[64 + i], __NV_E5M2);
+    return h + __half2float(static_cast<__half>(lr)) * (1.0f / F16C_SCALE);
 }
 
 // ------------------------------------------------------- bf16 hi/lo split ---

@@ -22,7 +22,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // One warp owns one token row of C channels held as float4 per lane per 128-channel slab
 // (channels 128*i + 4*lane .. +3).  Writes fp32 x, bf16 hi/lo planes and the per-128-group
 // LayerNorm partials consumed by the next GEMM's LN-folded epilogue.
-template <int MAXV>
+// F16C: `hi` is an F16C row buffer (ptx.cuh: 4 bytes per element, 128-byte blocks of 32 elements), `lo` is unused.
+template <int MAXV, bool F16C = false>
 __device__ __forceinline__ void emit_row(const float4 (&v)[MAXV], int nv, size_t row, int C, float* __restrict__ x,
                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                          float* __restrict__ stats) {
@@ -33,11 +34,22 @@ __device__ __forceinline__ void emit_row(const float4 (&v)[MAXV], int nv, size_t
         if (i < nv) {
             const int c = 128 * i + 4 * lane;
             if (x) *reinterpret_cast<float4*>(x + base + c) = v[i];
-            uint32_t h0, l0, h1, l1;
-            split2(v[i].x, v[i].y, h0, l0);
-            split2(v[i].z, v[i].w, h1, l1);
-            *reinterpret_cast<uint2*>(hi + base + c) = make_uint2(h0, h1);
-            if (lo) *reinterpret_cast<uint2*>(lo + base + c) = make_uint2(l0, l1);
+            if (F16C) {
+                uint8_t* blk = reinterpret_cast<uint8_t*>(hi) + base * 4 + static_cast<size_t>(c >> 5) * 128;
+                const int e = c & 31;
+                uint32_t h0, l0, g0, h1, l1, g1;
+                split2_f16c(v[i].x, v[i].y, h0, l0, g0);
+                split2_f16c(v[i].z, v[i].w, h1, l1, g1);
+                *reinterpret_cast<uint2*>(blk + 2 * e) = make_uint2(h0, h1);
+                *reinterpret_cast<uint32_t*>(blk + 64 + e) = l0 | (l1 << 16);
+                *reinterpret_cast<uint32_t*>(blk + 96 + e) = g0 | (g1 << 16);
+            } else {
+                uint32_t h0, l0, h1, l1;
+                split2(v[i].x, v[i].y, h0, l0);
+                split2(v[i].z, v[i].w, h1, l1);
+                *reinterpret_cast<uint2*>(hi + base + c) = make_uint2(h0, h1);
+                if (lo) *reinterpret_cast<uint2*>(lo + base + c) = make_uint2(l0, l1);
+            }
         }
     }
     if (stats) {
@@ -66,7 +78,7 @@ __device__ __forceinline__ void emit_row(const float4 (&v)[MAXV], int nv, size_t
 // ---------------------------------------------------------------------------------------------
 // embed (DSTformer.py:330-337): joints_embed Linear(3->C) + pos_embed[j] + temp_embed[f]
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool F16C = false>
 __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ xin, int dim_in,
                                                      const float* __restrict__ W,      // [C, dim_in]
                                                      const float* __restrict__ bias,   // [C]
@@ -101,13 +113,13 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ xi
                                (o[3] + pe.w) + te.w);
         }
     }
-    emit_row<NV>(v, nv, row, C, x, hi, lo, stats);
+    emit_row<NV, F16C>(v, nv, row, C, x, hi, lo, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
 // S/T stream fusion (DSTformer.py:343-349): alpha = softmax(Linear(2C->2)(cat[x_st, x_ts])) per token
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool F16C = false>
 __global__ void __launch_bounds__(256, 4) fuse_kernel(const float* __restrict__ xst, const float* __restrict__ xts,
                                                     const float* __restrict__ Wa,   // [2, 2C]
                                                     const float* __restrict__ ba,   // [2]
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(256, 4) fuse_kernel(const float* __restrict__ 
             v[i] = make_float4(a[i].x * al0 + b[i].x * al1, a[i].y * al0 + b[i].y * al1, a[i].z * al0 + b[i].z * al1,
                                a[i].w * al0 + b[i].w * al1);
     }
-    emit_row<NV>(v, nv, row, C, x, hi, lo, stats);
+    emit_row<NV, F16C>(v, nv, row, C, x, hi, lo, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(256) pack_linear_kernel(const float* __restric
                                                            const float* __restrict__ beta, int N, int K,
                                                            __nv_bfloat16* __restrict__ hi,
                                                            __nv_bfloat16* __restrict__ lo, float* __restrict__ vec_c,
-                                                           float* __restrict__ vec_s) {
+                                                           float* __restrict__ vec_s, int f16c) {
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= N) return;
     const int lane = lane_id();
@@ -193,11 +205,22 @@ __global__ void __launch_bounds__(256) pack_linear_kernel(const float* __restric
     for (int k = lane; k < K; k += 32) {
         const float w = W[static_cast<size_t>(n) * K + k];
         const float wp = gamma ? w * gamma[k] : w;
-        __nv_bfloat16 h, l;
-        split_bf16(wp, h, l);
-        hi[static_cast<size_t>(n) * K + k] = h;
-        lo[static_cast<size_t>(n) * K + k] = l;
-        s += __bfloat162float(h) + __bfloat162float(l);
+        if (f16c) {
+            // F16C rows [N][K]: block k/32 of row n, element `lane` (k % 32 == lane): f16 | lo8 | hi8
+            uint8_t* blk = reinterpret_cast<uint8_t*>(hi) + (static_cast<size_t>(n) * K + (k & ~31)) * 4;
+            uint32_t h2, l2, g2;
+            split2_f16c(wp, 0.f, h2, l2, g2);
+            *reinterpret_cast<uint16_t*>(blk + 2 * lane) = static_cast<uint16_t>(h2 & 0xffffu);
+            blk[64 + lane] = static_cast<uint8_t>(l2 & 0xffu);
+            blk[96 + lane] = static_cast<uint8_t>(g2 & 0xffu);
+            s += wp;
+        } else {
+            __nv_bfloat16 h, l;
+            split_bf16(wp, h, l);
+            hi[static_cast<size_t>(n) * K + k] = h;
+            lo[static_cast<size_t>(n) * K + k] = l;
+            s += __bfloat162float(h) + __bfloat162float(l);
+        }
         if (beta) c = fmaf(beta[k], w, c);
     }
     s = warp_sum(s);
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(256) pack_linear_kernel(const float* __restric
 }
 
 // fp32 [M,K] -> hi/lo planes + LN partial stats (used by the test hooks to feed the GEMM)
-template <int NV>
+template <int NV, bool F16C = false>
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ xin, int M, int C,
                                                           __nv_bfloat16* __restrict__ hi,
                                                           __nv_bfloat16* __restrict__ lo, float* __restrict__ stats) {
@@ -221,7 +244,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 #pragma unroll
     for (int i = 0; i < NV; ++i)
         v[i] = *reinterpret_cast<const float4*>(xin + static_cast<size_t>(row) * C + 128 * i + 4 * lane);
-    emit_row<NV>(v, nv, row, C, nullptr, hi, lo, stats);
+    emit_row<NV, F16C>(v, nv, row, C, nullptr, hi, lo, stats);
 }
 
 // ---------------------------------------------------------------------------------------------

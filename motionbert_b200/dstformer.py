@@ -78,6 +78,7 @@ class _DeviceState:
         self.packed = None
         self.pack_key = None
         self.workspaces = {}
+        self.pinned = set()          # workspace keys baked into a captured CUDA graph (make_graphed)
         self.zeros = {}
         self.side_stream = None
 
@@ -142,7 +143,11 @@ class DSTformer(nn.Module):
             raise NotImplementedError("norm_layer must build nn.LayerNorm (learning.py:84 passes "
                                       "partial(nn.LayerNorm, eps=1e-6))")
         self.eps = float(self.norm.eps)
-        self.math_mode = _lib.MB_MATH_BF16X3      # fp32-parity arithmetic; set_math_mode('bf16') for 1 pass
+        # arithmetic of the GEMM-shaped work (include/motionbert_b200.h MbMath): inference runs F16C (fp16 pass + one
+        # e5m2 compensation pass, fp32 parity at 2 pass-equivalents); a forward that needs gradients runs BF16X3 (its
+        # backward kernels consume bf16 operands).  set_math_mode() overrides both.
+        self.math_mode = _lib.MB_MATH_F16C
+        self.train_math_mode = _lib.MB_MATH_BF16X3
         self._kernel_flags = 0
         # shared (by reference) between nn.DataParallel replicas: keyed by device index
         self._dev_state = {}
@@ -170,9 +175,20 @@ class DSTformer(nn.Module):
         return self.forward(x, return_rep=True)
 
     def set_math_mode(self, mode: str):
-        """'bf16x3' (default; fp32 parity, 3 tensor-core passes) or 'bf16' (1 pass)."""
-        self.math_mode = {"bf16x3": _lib.MB_MATH_BF16X3, "bf16": _lib.MB_MATH_BF16}[mode]
+        """'f16c' (default: fp32 parity, fp16 pass + e5m2 compensation pass; gradient forwards use bf16x3),
+        'bf16x3' (fp32 parity, 3 bf16 passes, inference and training) or 'bf16' (1 pass, inference and training)."""
+        inf, trn = {"f16c": (_lib.MB_MATH_F16C, _lib.MB_MATH_BF16X3),
+                    "bf16x3": (_lib.MB_MATH_BF16X3, _lib.MB_MATH_BF16X3),
+                    "bf16": (_lib.MB_MATH_BF16, _lib.MB_MATH_BF16)}[mode]
+        self.math_mode, self.train_math_mode = inf, trn
         self._dev_state.clear()
+        return self
+
+    def invalidate_packed(self):
+        """Force a weight re-pack at the next call.  Needed only after writes that bypass the version counter of the
+        parameters (`p.data.copy_()`, EMA through `.data`): the packed-weight cache is keyed by (data_ptr, _version)."""
+        for st in self._dev_state.values():
+            st.pack_key = None
         return self
 
     # ------------------------------------------------------------------ host plumbing
@@ -197,8 +213,11 @@ class DSTformer(nn.Module):
                 ps += [None, None]       # zero logits -> alpha = (0.5, 0.5) == (x_st + x_ts) * 0.5 (:351)
         return ps
 
-    def _state_for(self, device: torch.device) -> _DeviceState:
-        key = device.index if device.index is not None else torch.cuda.current_device()
+    def _state_for(self, device: torch.device, math: int = None) -> _DeviceState:
+        """Host state (C handle, packed weights, workspaces) of one (device, math mode)."""
+        if math is None:
+            math = self.math_mode
+        key = (device.index if device.index is not None else torch.cuda.current_device(), math)
         st = self._dev_state.get(key)
         if st is None:
             st = _DeviceState()
@@ -207,7 +226,7 @@ class DSTformer(nn.Module):
                 raise NotImplementedError("head must be Linear(dim_rep, dim_out) for the fused tail")
             desc = _lib.MbDesc(self.dim_in, self.dim_out, self.dim_feat, self.dim_rep, self.depth, self.num_heads,
                                self.hidden, self.num_joints, self.maxlen, self.eps,
-                               float(self.qk_scale) if self.qk_scale else 0.0, self.math_mode)
+                               float(self.qk_scale) if self.qk_scale else 0.0, math)
             h = ctypes.c_void_p()
             _lib.check(lib.mb_create(ctypes.byref(desc), ctypes.byref(h)), "mb_create")
             st.handle = h
@@ -222,6 +241,13 @@ class DSTformer(nn.Module):
             st.packed = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
             self._dev_state[key] = st
         return st
+
+    @staticmethod
+    def _evict_workspaces(st: _DeviceState):
+        """Keep at most 4 inference workspaces per state; workspaces pinned by a captured CUDA graph are never dropped."""
+        if len(st.workspaces) >= 4:
+            for k in [k for k in st.workspaces if k not in st.pinned]:
+                del st.workspaces[k]
 
     @staticmethod
     def _aligned_ptr(t: torch.Tensor) -> int:
@@ -286,8 +312,7 @@ class DSTformer(nn.Module):
             if ws is None:
                 nb = ctypes.c_size_t()
                 _lib.check(lib.mb_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_workspace_bytes")
-                if len(st.workspaces) >= 4:
-                    st.workspaces.clear()
+                self._evict_workspaces(st)
                 ws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
                 st.workspaces[(B, F)] = ws
             out = torch.empty(B, F, J, self.dim_out, dtype=torch.float32, device=device) if want_out else None
@@ -300,14 +325,22 @@ class DSTformer(nn.Module):
         return out, rep
 
     # ------------------------------------------------------------------ training (mb_forward_train / mb_backward)
-    def _native_backward_ok(self, x: torch.Tensor, dp_scale) -> bool:
-        """The hand-written backward needs the fusion head, fp32 contiguous parameters on x's device and dim_out <= 8
-        (every configuration the reference's training scripts build); otherwise the torch-op fallback is used."""
-        if os.environ.get("MB_TORCH_BACKWARD") == "1":
-            return False
-        params = self._ordered_params()
-        return all(p is not None and p.dtype == torch.float32 and p.is_contiguous() and p.device == x.device
-                   for p in params) and self.dim_out <= 8
+    def _check_native_backward(self, x: torch.Tensor):
+        """The hand-written backward needs fp32 contiguous parameters on x's device and dim_out <= 8 (every
+        configuration the reference's training scripts build).  Anything else raises: there is no PyTorch-op fallback."""
+        if self.dim_out > 8:
+            raise NotImplementedError(f"training with dim_out={self.dim_out} > 8 is not supported by the native backward "
+                                      "(head_bwd_kernel keeps the head gradient in registers)")
+        for p in self._ordered_params():
+            if p is not None and (p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device):
+                raise NotImplementedError("the native backward needs fp32, contiguous parameters on the input's device "
+                                          f"(got {p.dtype}, contiguous={p.is_contiguous()}, {p.device} vs {x.device})")
+
+    def _head_param_slots(self):
+        """Positions of head.weight / head.bias among the non-None tensors of `_ordered_params()`."""
+        live = [p for p in self._ordered_params() if p is not None]
+        ids = {id(self.head.weight), id(self.head.bias)} if isinstance(self.head, nn.Linear) else set()
+        return tuple(i for i, p in enumerate(live) if id(p) in ids)
 
     def _launch_train(self, x: torch.Tensor, want_out: bool, dp_scale=None):
         """mb_forward_train on the current stream: returns (out, rep, saved) with `saved` the activation region."""
@@ -315,15 +348,14 @@ class DSTformer(nn.Module):
         B, F, J, _ = x.shape
         lib = _lib.load()
         with torch.cuda.device(device):
-            st = self._state_for(device)
+            st = self._state_for(device, self.train_math_mode)
             stream_ptr = torch.cuda.current_stream(device).cuda_stream
             self._ensure_packed(st, device, stream_ptr)
             ws = st.workspaces.get((B, F))
             if ws is None:
                 nb = ctypes.c_size_t()
                 _lib.check(lib.mb_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_workspace_bytes")
-                if len(st.workspaces) >= 4:
-                    st.workspaces.clear()
+                self._evict_workspaces(st)
                 ws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
                 st.workspaces[(B, F)] = ws
             nb = ctypes.c_size_t()
@@ -366,13 +398,24 @@ class DSTformer(nn.Module):
         return self
 
     def _launch_backward(self, x, rep, saved, d_out, d_rep, dp_scale=None, want_dx=False):
-        """mb_backward on the current stream: returns (parameter gradients in `_ordered_params()` order, d_x or None)."""
+        """mb_backward on the current stream: returns (gradients of the non-None tensors of `_ordered_params()`, in that
+        order; d_x or None).  `att_fuse=False`: the missing fusion-head slots are fed zero weights (alpha = 0.5 / 0.5, which
+        IS DSTformer.py:351) and their gradients land in a scratch tensor that is dropped."""
         device = x.device
         B, F, J, _ = x.shape
         lib = _lib.load()
-        params = self._ordered_params()
+        real = self._ordered_params()
+        st0 = self._state_for(device, self.train_math_mode)
+        params = []
+        for i, p in enumerate(real):
+            if p is None:
+                z = st0.zeros.get(st0.numels[i])
+                if z is None:
+                    z = st0.zeros[st0.numels[i]] = torch.zeros(st0.numels[i], dtype=torch.float32, device=device)
+                p = z
+            params.append(p)
         with torch.cuda.device(device):
-            st = self._state_for(device)
+            st = self._state_for(device, self.train_math_mode)
             stream_ptr = torch.cuda.current_stream(device).cuda_stream
             self._ensure_packed(st, device, stream_ptr)      # no-op unless the weights changed since the forward
             bws = st.workspaces.get(("bwd", B, F))
@@ -427,12 +470,14 @@ class DSTformer(nn.Module):
                             dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=sync["group"])
                             seg.div_(sync["world"])
                 torch.cuda.current_stream(device).wait_stream(side)
-        return grads, d_x
+        return [g for g, p in zip(grads, real) if p is not None], d_x
 
     def make_graphed(self, B: int, F: int, return_rep: bool = False):
         """CUDA-graph the inference forward for a fixed (B, F): returns `run(x) -> out` that copies x into a static
-        device buffer, replays the captured 108-launch forward and returns the static output tensor (valid until the
-        next call).  For latency-bound shapes (infer_wild: B=1 clips); weights must not change between calls."""
+        device buffer, replays the captured forward and returns the static output tensor (valid until the next call).
+        For latency-bound shapes (infer_wild: B=1 clips).  The graph bakes in device pointers of the workspace and of the
+        packed weights: both are pinned for the lifetime of `run` (held by the closure, exempt from workspace eviction),
+        and `run` raises if the parameters changed or the module state was reset since the capture (re-capture then)."""
         dev = next(self.parameters()).device
         static_x = torch.zeros(B, F, self.num_joints, self.dim_in, dtype=torch.float32, device=dev)
         side = torch.cuda.Stream(device=dev)
@@ -441,15 +486,25 @@ class DSTformer(nn.Module):
             for _ in range(2):                      # warm-up: handle, packed weights, workspace, tensor maps
                 self.forward(static_x, return_rep)
         torch.cuda.current_stream(dev).wait_stream(side)
+        st = self._state_for(dev)
+        st.pinned.add((B, F))
+        keep = (st, st.workspaces[(B, F)], st.packed)           # the buffers the captured launches point into
+        pack_key = st.pack_key
         graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(graph):
             static_out = self.forward(static_x, return_rep)
 
         def run(x):
+            cur = self._dev_state.get((dev.index if dev.index is not None else torch.cuda.current_device(), self.math_mode))
+            params = self._ordered_params()
+            key = tuple((p.data_ptr(), p._version) if p is not None else (0, 0) for p in params)
+            if cur is not keep[0] or key != pack_key:
+                raise RuntimeError("make_graphed: parameters or math mode changed since the capture; call make_graphed again")
             static_x.copy_(x, non_blocking=True)
             graph.replay()
             return static_out
         run.graph = graph
+        run._keep = keep
         return run
 
     # ------------------------------------------------------------------ forward (DSTformer.py:329-358)
@@ -469,7 +524,9 @@ class DSTformer(nn.Module):
                                       "(all shipped configs use 0; DropPath is supported)")
         x = x.detach().float().contiguous() if not x.requires_grad else x.float().contiguous()
         dp_scale = self._drop_path_scale(B, F, x.device)
-        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        # (not self.parameters(): nn.DataParallel replicas carry their parameters as plain attributes)
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(
+            p is not None and p.requires_grad for p in self._ordered_params()))
         if needs_grad:
             params = [p for p in self._ordered_params() if p is not None]
             return DSTformerFunction.apply(self, x, bool(return_rep), dp_scale, *params)

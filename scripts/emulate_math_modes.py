@@ -1,0 +1,169 @@
+"""CPU emulation of tensor-core operand formats on the DSTformer forward (SURVEY.md 7.3 #1 style probe).
+
+    python scripts/emulate_math_modes.py [base|lite] [F] [B]
+
+Every GEMM-shaped product of the path (LN-folded linears on the RAW residual stream exactly as the kernels run
+them, attention QK^T and PV) is evaluated in float64 with its OPERANDS rounded the way a given tensor-core scheme
+sees them; everything else (accumulation, LayerNorm statistics, softmax, GELU, residual) stays float64.  Reports the
+per-token relative error of `rep` and the mean joint displacement of `out` against the float64 truth -- the two
+parity metrics of BASELINE.json (<= 1e-3 per token; MPJPE <= 0.1 mm, i.e. <= 1.7e-4 relative at 600 mm joints).
+TEST/DESIGN infrastructure: imports oracle/, never imported by the product.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import dstformer_oracle as O  # noqa: E402
+
+D = torch.float64
+
+
+def rnd(x, dt):
+    return x.to(dt).to(D)
+
+
+def mm_exact(a, w):
+    return a @ w.transpose(-1, -2)
+
+
+def make_mm(scheme):
+    """returns f(a, w) ~ a @ w^T with operands rounded per scheme"""
+    if scheme == "exact":
+        return mm_exact
+    if scheme == "fp32":
+        return lambda a, w: mm_exact(rnd(a, torch.float32), rnd(w, torch.float32))
+    if scheme == "bf16":
+        return lambda a, w: mm_exact(rnd(a, torch.bfloat16), rnd(w, torch.bfloat16))
+    if scheme == "f16":
+        return lambda a, w: mm_exact(rnd(a, torch.float16), rnd(w, torch.float16))
+    if scheme == "bf16x3":
+        def f(a, w):
+            ah = rnd(a, torch.bfloat16); al = rnd(a - ah, torch.bfloat16)
+            wh = rnd(w, torch.bfloat16); wl = rnd(w - wh, torch.bfloat16)
+            return mm_exact(ah, wh) + mm_exact(ah, wl) + mm_exact(al, wh)
+        return f
+    if scheme == "f16x3":
+        def f(a, w):
+            ah = rnd(a, torch.float16); al = rnd(a - ah, torch.float16)
+            wh = rnd(w, torch.float16); wl = rnd(w - wh, torch.float16)
+            return mm_exact(ah, wh) + mm_exact(ah, wl) + mm_exact(al, wh)
+        return f
+    if scheme.startswith("f16+"):
+        # main pass fp16 x fp16; both cross terms in an 8-bit float format at twice the MMA rate:
+        #   a ~ ah + al,  w ~ wh + wl;   a w ~ ah wh  +  q(al) q(wh)  +  q(ah 2^-S) q(wl 2^S)
+        q = {"e5m2": torch.float8_e5m2, "e4m3": torch.float8_e4m3fn}[scheme[4:]]
+        S = 2.0 ** 6    # symmetric scaling: hi8 = q(h 2^-6), lo8 = q(l 2^6) for BOTH operands
+        def f(a, w):
+            ah = rnd(a, torch.float16); al = a - ah
+            wh = rnd(w, torch.float16); wl = w - wh
+            return (mm_exact(ah, wh) + mm_exact(rnd(al * S, q), rnd(wh / S, q))
+                    + mm_exact(rnd(ah / S, q), rnd(wl * S, q)))
+        return f
+    if scheme == "f16w2":   # weights exact (2 fp16 planes), activations single fp16
+        def f(a, w):
+            ah = rnd(a, torch.float16)
+            wh = rnd(w, torch.float16); wl = rnd(w - wh, torch.float16)
+            return mm_exact(ah, wh) + mm_exact(ah, wl)
+        return f
+    raise ValueError(scheme)
+
+
+class Emu:
+    def __init__(self, cfg, P, lin_scheme, att_scheme):
+        self.cfg = cfg
+        self.P = {k: torch.from_numpy(v).to(D) for k, v in P.items()}
+        self.mm = make_mm(lin_scheme)
+        self.amm = make_mm(att_scheme)
+
+    def ln_linear(self, x, ln, lin):
+        """LN(x) W^T + b as the kernels do it: GEMM on raw x with W' = W*gamma, statistics applied afterwards."""
+        P = self.P
+        g, b = P[ln + ".weight"], P[ln + ".bias"]
+        W, bias = P[lin + ".weight"], P[lin + ".bias"]
+        Wf = W * g
+        s = Wf.sum(-1)
+        c = W @ b + bias
+        mu = x.mean(-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(-1, keepdim=True)
+        rstd = 1.0 / torch.sqrt(var + self.cfg.eps)
+        acc = self.mm(x, Wf)
+        return rstd * (acc - mu * s) + c
+
+    def linear(self, x, lin):
+        return self.mm(x, self.P[lin + ".weight"]) + self.P[lin + ".bias"]
+
+    def attention(self, x, ln, p, mode, F):
+        cfg = self.cfg
+        BF, J, C = x.shape
+        H, d = cfg.num_heads, cfg.head_dim
+        qkv = self.ln_linear(x, ln, p + ".qkv").reshape(BF, J, 3, H, d).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        if mode == "temporal":
+            B = BF // F
+            q, k, v = (t.reshape(B, F, H, J, d).permute(0, 2, 3, 1, 4) for t in (q, k, v))
+        att = (self.amm(q, k) * d ** -0.5).softmax(-1)
+        o = self.amm(att, v.transpose(-1, -2))
+        if mode == "temporal":
+            o = o.permute(0, 3, 2, 1, 4).reshape(BF, J, C)
+        else:
+            o = o.transpose(1, 2).reshape(BF, J, C)
+        return self.linear(o, p + ".proj")
+
+    def block(self, x, p, order, F):
+        for which in order:
+            s = "s" if which == "S" else "t"
+            x = x + self.attention(x, p + "norm1_" + s, p + "attn_" + s,
+                                   "spatial" if which == "S" else "temporal", F)
+            h = torch.nn.functional.gelu(self.ln_linear(x, p + "norm2_" + s, p + f"mlp_{s}.fc1"))
+            x = x + self.linear(h, p + f"mlp_{s}.fc2")
+        return x
+
+    def forward(self, x):
+        cfg, P = self.cfg, self.P
+        x = torch.from_numpy(x).to(D)
+        B, F, J, _ = x.shape
+        C = cfg.dim_feat
+        h = x.reshape(B * F, J, -1) @ P["joints_embed.weight"].T + P["joints_embed.bias"] + P["pos_embed"]
+        h = (h.reshape(B, F, J, C) + P["temp_embed"][:, :F]).reshape(B * F, J, C)
+        for i in range(cfg.depth):
+            a = self.block(h, f"blocks_st.{i}.", "ST", F)
+            b = self.block(h, f"blocks_ts.{i}.", "TS", F)
+            al = (torch.cat([a, b], -1) @ P[f"ts_attn.{i}.weight"].T + P[f"ts_attn.{i}.bias"]).softmax(-1)
+            h = a * al[..., 0:1] + b * al[..., 1:2]
+        rep = torch.tanh(self.ln_linear(h, "norm", "pre_logits.fc")).reshape(B, F, J, -1)
+        out = rep @ P["head.weight"].T + P["head.bias"]
+        return out.numpy(), rep.numpy()
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "base"
+    F = int(sys.argv[2]) if len(sys.argv) > 2 else 81
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    cfg = O.BASE if which == "base" else O.LITE
+    torch.set_num_threads(os.cpu_count())
+    for pseed, scale in ((11, 1.0),):
+        P = O.make_params(cfg, pseed, scale)
+        x = O.make_input(B, F, cfg.num_joints, 3)
+        out0, rep0 = Emu(cfg, P, "exact", "exact").forward(x)
+        print(f"# {which} B={B} F={F} params seed {pseed} scale {scale}: |out| mean joint norm "
+              f"{np.linalg.norm(out0, axis=-1).mean():.4f}")
+        for lin, att in (("bf16x3", "bf16x3"), ("f16+e5m2", "f16+e5m2"), ("f16+e5m2", "exact"),
+                         ("exact", "f16+e5m2"), ("exact", "f16")):
+            out, rep = Emu(cfg, P, lin, att).forward(x)
+            tok = np.linalg.norm((rep - rep0).reshape(-1, rep.shape[-1]), axis=-1) / \
+                np.linalg.norm(rep0.reshape(-1, rep.shape[-1]), axis=-1)
+            disp = np.linalg.norm(out - out0, axis=-1).mean()
+            rel = disp / np.linalg.norm(out0, axis=-1).mean()
+            print(f"  linears {lin:9s} attention {att:9s}: rep per-token rel {tok.mean():.2e} / {tok.max():.2e}   "
+                  f"out displacement {disp:.2e} abs, {rel:.2e} rel")
+
+
+if __name__ == "__main__":
+    main()

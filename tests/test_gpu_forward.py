@@ -46,24 +46,34 @@ def test_forward_matches_reference_golden_simt_reference_kernels(cuda_device, na
     cfg, P, x, g = load_case(name)
     if x.shape[0] * x.shape[1] > 64:
         pytest.skip("CUDA-core reference GEMM is only run on the small cases")
-    m = build_module(cfg, P, cuda_device)
+    m = build_module(cfg, P, cuda_device).set_math_mode("bf16x3")     # the CUDA-core test kernels read bf16 hi/lo planes
     m._kernel_flags = _lib.MB_FLAG_REF_GEMM | _lib.MB_FLAG_REF_ATTN_T | _lib.MB_FLAG_REF_ATTN_S
     out, rep = _run(m, x, cuda_device)
     _check_against_golden(out, rep, g, cfg, name + "/simt")
 
 
+@pytest.mark.parametrize("mode", ["f16c", "bf16x3"])
 @pytest.mark.parametrize("name", golden_names())
-def test_forward_matches_reference_golden(cuda_device, name):
-    """The product path (tcgen05 GEMMs + tcgen05 temporal attention), fp32-parity arithmetic."""
+def test_forward_matches_reference_golden(cuda_device, name, mode):
+    """The product path (tcgen05 GEMMs + tcgen05 attention) in both fp32-parity arithmetic modes: F16C (fp16 pass + one
+    e5m2 compensation pass; the inference default) and BF16x3 (three bf16 passes; the training forward)."""
     cfg, P, x, g = load_case(name)
-    m = build_module(cfg, P, cuda_device)
+    m = build_module(cfg, P, cuda_device).set_math_mode(mode)
     out, rep = _run(m, x, cuda_device)
-    _check_against_golden(out, rep, g, cfg, name)
+    _check_against_golden(out, rep, g, cfg, name + "/" + mode)
+
+
+def test_default_math_mode_is_f16c_for_inference_and_bf16x3_for_gradients(cuda_device):
+    cfg, P, x, g = load_case("lite_b2_f27")
+    m = build_module(cfg, P, cuda_device)
+    assert m.math_mode == _lib.MB_MATH_F16C and m.train_math_mode == _lib.MB_MATH_BF16X3
+    _run(m, x, cuda_device)
+    assert (cuda_device.index or 0, _lib.MB_MATH_F16C) in m._dev_state
 
 
 def test_forward_first_generation_1cta_gemm_still_matches(cuda_device):
     cfg, P, x, g = load_case("base_b2_f27")
-    m = build_module(cfg, P, cuda_device)
+    m = build_module(cfg, P, cuda_device).set_math_mode("bf16x3")
     m._kernel_flags = _lib.MB_FLAG_GEMM_1CTA
     out, rep = _run(m, x, cuda_device)
     _check_against_golden(out, rep, g, cfg, "base_b2_f27/1cta")
@@ -131,7 +141,7 @@ def test_drop_path_training_matches_torch_recompute(cuda_device):
     import torch.nn as nn
 
     from motionbert_b200 import DSTformer
-    from motionbert_b200._autograd import recompute_forward
+    from oracle.dstformer_torch_autograd import recompute_forward
     cfg = O.LITE
     torch.manual_seed(3)
     m = DSTformer(dim_in=3, dim_out=3, dim_feat=256, dim_rep=512, depth=5, num_heads=8, mlp_ratio=4,

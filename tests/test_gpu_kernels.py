@@ -66,6 +66,27 @@ def test_linear_bf16x3(cuda_device, M, N, K, mode, use_ref):
         assert float((var_g - e.var(-1, unbiased=False)).abs().max()) < 1e-3
 
 
+@pytest.mark.parametrize("mode", [4, 0, 1, 2, 3], ids=["bias", "ln_split", "ln_gelu", "resid", "ln_tanh"])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_linear_f16c(cuda_device, M, N, K, mode):
+    """F16C arithmetic (ptx.cuh): a w ~ ah wh (fp16 MMA) + q(al 2^6) q(wh 2^-6) + q(ah 2^-6) q(wl 2^6) (e5m2 MMAs, K = 32).
+    Operands carry ~14-15 significant bits -> ~3e-5 per GEMM (BF16x3: ~1e-5); the split-row outputs (modes 0, 1) are
+    decoded as h + l (same 14-15 bits)."""
+    A, W, b, gamma, beta, resid = _mk(M, N, K, cuda_device, seed=M + N + K + mode)
+    y, stats = G.test_linear(mode, A, W, b, gamma, beta, resid, 1e-6, math=2, use_ref=0)
+    exp = _expected(mode, A, W, b, gamma, beta, resid, 1e-6)
+    assert torch.isfinite(y).all(), "non-finite / unwritten output"
+    rel, mx = _rel(y, exp)
+    print(f"f16c M={M} N={N} K={K} mode={mode}: rel {rel:.3e} max {mx:.3e}")
+    assert rel < 1.5e-4, f"rel {rel:.3e} max {mx:.3e}"
+    if mode == 2:
+        e = exp.float().reshape(M, N // 128, 128)
+        mean_g = stats[..., 0] + stats[..., 1] / 128
+        var_g = stats[..., 2] / 128 - (stats[..., 1] / 128) ** 2
+        assert float((mean_g - e.mean(-1)).abs().max()) < 2e-4
+        assert float((var_g - e.var(-1, unbiased=False)).abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 512), (77, 512, 1024)])
 @pytest.mark.parametrize("mode", [4, 0, 2])
 def test_linear_bf16_single_pass(cuda_device, M, N, K, mode):

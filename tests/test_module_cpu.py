@@ -126,14 +126,58 @@ def test_gradient_allreduce_needs_a_process_group_and_can_be_switched_off():
     assert m.enable_gradient_allreduce(enabled=False) is m and m._grad_sync is None
 
 
-def test_native_backward_eligibility_is_decided_on_the_host():
+def test_native_backward_eligibility_is_decided_on_the_host_and_unsupported_configurations_raise():
+    """There is no PyTorch-op fallback backward: configurations mb_backward does not cover raise on the host."""
     import torch
 
     from motionbert_b200 import DSTformer
     m = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2)
     x = torch.zeros(1, 2, 17, 3)
-    assert m._native_backward_ok(x, None)                      # fp32 contiguous parameters on x's device
+    m._check_native_backward(x)                                # fp32 contiguous parameters on x's device: fine
     m.ts_attn[0].weight.data = m.ts_attn[0].weight.data.double()
-    assert not m._native_backward_ok(x, None)                  # non-fp32 parameter -> torch-op fallback
+    with pytest.raises(NotImplementedError, match="fp32"):
+        m._check_native_backward(x)
     m2 = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2, att_fuse=False)
-    assert not m2._native_backward_ok(x, None)                 # no fusion head -> fallback
+    m2._check_native_backward(x)                               # no fusion head: native (constant 0.5 / 0.5 fusion)
+    assert m2._head_param_slots() == (56, 57) and len([p for p in m2._ordered_params() if p is None]) == 2
+    m3 = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2, dim_out=17)
+    with pytest.raises(NotImplementedError, match="dim_out"):
+        m3._check_native_backward(x)
+
+
+def test_data_parallel_replicas_still_see_their_parameters_for_the_gradient_decision():
+    """nn.DataParallel replicas keep their parameters as plain attributes (`_parameters` is empty), so the
+    needs-gradient decision must not go through `self.parameters()` (train.py:256-258 wraps the backbone)."""
+    import torch
+
+    from motionbert_b200 import DSTformer
+    m = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2)
+    rep = m._replicate_for_data_parallel()
+    for name, sub in m.named_modules():
+        if name:
+            parent = rep
+            *path, leaf = name.split(".")
+            for t in path:
+                parent = parent._modules[t]
+            parent._modules[leaf] = sub._replicate_for_data_parallel()
+    # what torch.nn.parallel.replicate does: parameters become non-leaf attribute tensors
+    for name, sub in rep.named_modules():
+        src = dict(m.named_modules())[name]
+        for k, p in src._parameters.items():
+            if p is not None:
+                setattr(sub, k, p * 1.0)
+    assert len(list(rep.parameters())) == 0
+    ps = rep._ordered_params()
+    assert len(ps) == 60 and all(p.requires_grad for p in ps)
+
+
+def test_math_modes_are_a_host_side_switch():
+    from motionbert_b200 import DSTformer, _lib
+    m = DSTformer(dim_feat=256, depth=1, num_heads=8, mlp_ratio=2)
+    assert (m.math_mode, m.train_math_mode) == (_lib.MB_MATH_F16C, _lib.MB_MATH_BF16X3)
+    m.set_math_mode("bf16")
+    assert (m.math_mode, m.train_math_mode) == (_lib.MB_MATH_BF16, _lib.MB_MATH_BF16)
+    m.set_math_mode("bf16x3")
+    assert (m.math_mode, m.train_math_mode) == (_lib.MB_MATH_BF16X3, _lib.MB_MATH_BF16X3)
+    with pytest.raises(KeyError):
+        m.set_math_mode("fp64")
