@@ -188,15 +188,24 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def run_train(args, device, world, rank, local_rank, dist, D):
-    """SURVEY.md 8d config 3 (N=1) / config 4 (N>1): one pretrain step = forward (saved residual stream) -> MPJPE loss
-    -> native backward -> gradient all-reduce over the ranks (N>1) -> fused AdamW -> weight re-pack at the next forward.
-    Supplementary to the headline forward line (BASELINE's metric); printed with the same keys."""
+def _barrier(dist, device):
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+
+
+def train_record(args, device, world, rank, local_rank, dist, D, model_name="base", batch=128, frames=243, math="bf16",
+                 steps=20, warmup=3, e2e_steps=0):
+    """SURVEY.md 8d config 3 (N=1) / config 4 (N>1): one pretrain step = forward (saved residual stream) -> fused pretrain
+    loss (mpjpe + 0.5 n_mpjpe + 20 velocity, train.py:178-191) -> native backward -> gradient all-reduce over the ranks
+    (N>1, per depth, overlapped with the backward) -> fused AdamW -> weight re-pack at the next forward.
+    Returns the record (identical on every rank: times are max over ranks)."""
+    from motionbert_b200 import _lib
     from motionbert_b200.loss import pretrain_loss_3d
-    model = build_model(args.model, device, args.math).train()
-    cfg = MODELS[args.model]
+    model = build_model(model_name, device, math).train()
+    cfg = MODELS[model_name]
     hidden = int(cfg["dim_feat"] * cfg["mlp_ratio"])
-    B, T = args.batch, args.frames
+    B, T = batch, frames
     x_host = synthetic_clips(B, T, seed=1 + rank)
     gt_host = synthetic_clips(B, T, seed=1001 + rank)
     x_dev, gt_dev = x_host.to(device), gt_host.to(device)
@@ -205,81 +214,171 @@ def run_train(args, device, world, rank, local_rank, dist, D):
         model.enable_gradient_allreduce()
     opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.01, fused=True)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
     def step(x, gt):
         opt.zero_grad(set_to_none=True)
         pred = model(x)
-        # loss_mpjpe + 0.5 n_mpjpe + 20 loss_velocity (train.py:178-191, MB_pretrain.yaml:39-44), fused with its gradient
         loss, _parts = pretrain_loss_3d(pred, gt, 0.5, 20.0)
         loss.backward()       # world > 1: gradients are averaged over the ranks inside the backward (phase by phase)
         opt.step()
         return loss
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(x_dev, gt_dev)
-    barrier()
+    _barrier(dist, device)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    _barrier(dist, device)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step(x_dev, gt_dev)
     ev1.record()
-    barrier()
-    ms_per_step = D.max_over_ranks(ev0.elapsed_time(ev1), device) / args.steps
+    _barrier(dist, device)
+    ms_per_step = D.max_over_ranks(ev0.elapsed_time(ev1), device) / steps
     sampler.stop_flag = True
     sampler.join(timeout=3)
     clocks = sampler.summary()
-    value = world * B / (ms_per_step * 1e-3)
-    # end to end: pinned host clip + target -> H2D, step, loss read back to the host every step
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    last = 0.0
-    for _ in range(args.steps):
-        last = float(step(x_host.to(device, non_blocking=True), gt_host.to(device, non_blocking=True)).item())
-    e1.record()
-    barrier()
-    e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), device) / args.steps
+    last = float(loss.detach())
+    e2e = None
+    if e2e_steps > 0:
+        # end to end: pinned host clip + target -> H2D, step, loss read back to the host every step
+        _barrier(dist, device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            last = float(step(x_host.to(device, non_blocking=True), gt_host.to(device, non_blocking=True)).item())
+        e1.record()
+        _barrier(dist, device)
+        e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), device) / e2e_steps
+        e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(2 * x_host.numel() * 4), "d2h_bytes_per_step": 4,
+               "api": "DSTformer.forward -> loss.backward() -> optimizer.step() on pinned host clips"}
     peaks = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     step_flop = 3.0 * flops_per_sequence(cfg["dim_feat"], hidden, T) * B          # fwd + 2x bwd (recompute not counted)
     achieved = step_flop / (ms_per_step * 1e-3) / 1e12
     n_param = sum(p.numel() for p in params)
-    from motionbert_b200 import _lib
     lib = _lib.load()
     hnd = model._state_for(device, model.train_math_mode).handle
-    # kernels of this library per step: forward + backward + fused loss (2); the per-step weight re-pack is not counted
-    launches_per_step = _lib.check(lib.mb_forward_launch_count(hnd, 1, 0)) + _lib.check(lib.mb_backward_launch_count(hnd, 0, 0)) + 2
+    launches_per_step = (_lib.check(lib.mb_forward_launch_count(hnd, 1, 0)) +
+                         _lib.check(lib.mb_backward_launch_count(hnd, 0, 0)) + 2)
+    rec = {
+        "metric": f"sequences/sec DSTformer-{model_name} pretrain step fwd+bwd+AdamW (Bx{T}x17)",
+        "config": f"SURVEY 8d config {'3' if world == 1 else '4'}: B={B} per GPU, T={T}, {math} forward, bf16 native backward, "
+                  "fused pretrain loss, fused AdamW" + (", per-depth NCCL gradient all-reduce overlapped with the backward" if world > 1 else ""),
+        "value": world * B / (ms_per_step * 1e-3), "unit": "sequences/sec", "n_gpus": world, "global_batch": world * B,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "last_loss": last, "clocks": clocks,
+        "whole_step_tflops": achieved, "whole_step_frac": achieved / peak_tf,
+        "frac_note": "3 x forward algorithmic FLOPs / step time / sustained bf16 peak (recompute, optimizer, all-reduce in the time only)",
+        "grad_allreduce_bytes_per_step": n_param * 4 if world > 1 else 0,
+        "gpu_launches_per_step": launches_per_step,
+    }
+    if e2e is not None:
+        rec["e2e"] = e2e
+    del opt, model, x_dev, gt_dev
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_train(args, device, world, rank, local_rank, dist, D):
+    """`--mode train`: the training step as the headline line (supplementary to the forward line)."""
+    rec = train_record(args, device, world, rank, local_rank, dist, D, args.model, args.batch, args.frames, args.math,
+                       steps=args.steps, warmup=args.warmup, e2e_steps=args.steps)
+    peaks = load_peaks()
     line = {
-        "metric": f"sequences/sec DSTformer-{args.model} pretrain step fwd+bwd+AdamW (Bx{T}x17)",
-        "value": value, "unit": "sequences/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.math == "bf16" else "bf16x3 forward / bf16 backward", "data": "synthetic",
-        "config": {"workload": f"SURVEY 8d config {'3' if world == 1 else '4'}: DSTformer-{args.model} pretrain step, B={B} per GPU, "
-                               f"T={T}, fused pretrain loss (mpjpe + 0.5 n_mpjpe + 20 velocity), native backward (bf16 single-pass), fused AdamW", "global_batch": world * B,
-                   "seq_len": T, "parallelism": f"dp{world}" + (" + per-depth NCCL gradient all-reduce overlapped with the backward (one flat fp32 bucket)" if world > 1 else ""),
-                   "l2": "activations >> 126 MB L2, no flush needed", "grad_allreduce_elems": n_param if world > 1 else 0},
-        "clocks": clocks,
-        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(2 * x_host.numel() * 4), "d2h_bytes_per_step": 4, "last_loss": last,
-                "api": "DSTformer.forward -> loss.backward() -> optimizer.step() on pinned host clips"},
-        "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "note": "whole step: 3 x forward algorithmic FLOPs / step time (recompute, optimizer and "
-                                              "all-reduce time included in the denominator, not in the numerator)",
+        "metric": rec["metric"], "value": rec["value"], "unit": "sequences/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.math == "bf16" else "bf16x3 forward / bf16 backward", "data": "synthetic",
+        "config": {"workload": rec["config"], "global_batch": world * args.batch, "seq_len": args.frames,
+                   "parallelism": f"dp{world}", "l2": "activations >> 126 MB L2, no flush needed"},
+        "clocks": rec["clocks"], "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches_per_step"] * args.steps,
+        "roofline": {"bound": "tensor", "achieved": rec["whole_step_tflops"],
+                     "peak": float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))), "unit": "TFLOP/s",
+                     "frac": rec["whole_step_frac"], "traffic": None, "note": rec["frac_note"],
                      "peak_source": peaks["_source"] + " bf16_tflops_sustained"},
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+
+
+def forward_rate(model, x_dev, steps, warmup, dist, device, D):
+    """K forwards with the input resident in HBM, CUDA events on the launching stream, max over ranks -> ms per step."""
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = model(x_dev)
+    _barrier(dist, device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(dist, device)
+    with torch.no_grad():
+        ev0.record()
+        for _ in range(steps):
+            out = model(x_dev)
+        ev1.record()
+    _barrier(dist, device)
+    return D.max_over_ranks(ev0.elapsed_time(ev1), device) / steps, out
+
+
+def parity_check(model, model_name, x_host, out_dev, device, n_check=3):
+    """The output the bench timed, checked against the CPU oracle: sequences first / middle / last of the batch through
+    `oracle/dstformer_torch_cpu.py` in float64 (op-for-op the reference's forward, pinned against the real reference by
+    tests/golden); north-star bars: per-token relative error <= 1e-3, MPJPE <= 2e-4 units (0.1 mm at 500 mm / unit).
+    Also re-runs the three sequences as their own batch for `rep` (the 512-d representation)."""
+    from oracle import dstformer_oracle as O
+    from oracle import dstformer_torch_cpu as OT
+    cfg = O.BASE if model_name == "base" else O.LITE
+    B = x_host.shape[0]
+    idx = sorted({0, B // 2, B - 1})[:n_check]
+    P64 = {k: v.detach().double().cpu() for k, v in model.state_dict().items()}
+    xs = x_host[idx].double()
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    o_ref, r_ref = OT.forward(P64, xs, cfg.depth, cfg.num_heads, cfg.eps)
+    got = out_dev[idx].double().cpu()
+    with torch.no_grad():
+        rep = model.get_representation(x_host[idx].to(device)).double().cpu()
+    tok = (got - o_ref).norm(dim=-1) / o_ref.norm(dim=-1).clamp_min(1e-12)
+    rtok = (rep - r_ref).norm(dim=-1) / r_ref.norm(dim=-1).clamp_min(1e-12)
+    mp = float((got - o_ref).norm(dim=-1).mean())
+    res = {"checked_sequences": idx, "of_batch": B, "out_tok_rel_mean": float(tok.mean()), "out_tok_rel_max": float(tok.max()),
+           "rep_tok_rel_mean": float(rtok.mean()), "rep_tok_rel_max": float(rtok.max()), "mpjpe_units": mp,
+           "mpjpe_mm_at_500mm_per_unit": mp * 500.0, "out_joint_norm_mean": float(o_ref.norm(dim=-1).mean()),
+           "checker": "oracle/dstformer_torch_cpu.py float64 (CPU)", "bars": {"tok_rel": 1e-3, "mpjpe_units": 2e-4}}
+    res["ok"] = bool(res["rep_tok_rel_max"] < 1e-3 and res["out_tok_rel_mean"] < 1e-3 and mp < 2e-4)
+    return res
+
+
+def gpu_eager_baseline(model, model_name, T, device, batch=32, iters=3):
+    """The honest GPU comparator (SURVEY.md 8d / BASELINE.md 3): the reference's forward op for op -- the bit-exact torch
+    port `oracle/dstformer_torch_cpu.py`, which is plain torch ops -- moved to the B200 in eager mode, fp32 and TF32-allowed.
+    A reported baseline; nothing of it is on the product path."""
+    from oracle import dstformer_oracle as O
+    from oracle import dstformer_torch_cpu as OT
+    cfg = O.BASE if model_name == "base" else O.LITE
+    P = {k: v.detach().to(device) for k, v in model.state_dict().items()}
+    x = synthetic_clips(batch, T, seed=5).to(device)
+    res = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                OT.forward(P, x, cfg.depth, cfg.num_heads, cfg.eps)
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                OT.forward(P, x, cfg.depth, cfg.num_heads, cfg.eps)
+            e1.record()
+            torch.cuda.synchronize(device)
+            ms = e0.elapsed_time(e1) / iters
+            res[name] = {"value": batch / (ms * 1e-3), "unit": "sequences/sec", "ms_per_step": ms}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    res["what"] = (f"torch eager (cuBLAS / ATen kernels) port of lib/model/DSTformer.py forward on the same B200, B={batch}, T={T}, "
+                   f"{iters} iterations after 2 warm-ups; torch {torch.__version__}")
+    del P, x
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -290,12 +389,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="base", choices=["base", "lite"])
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
-                    help="forward = BASELINE config 2 (the headline); train = config 3/4 pretrain step (fwd+bwd+AdamW)")
+                    help="forward = BASELINE config 2 (the headline, with train / lite / eager sub-records); train = config 3/4 only")
     ap.add_argument("--batch", type=int, default=None, help="sequences per GPU per step (default 256 forward / 128 train)")
     ap.add_argument("--frames", type=int, default=243)
     ap.add_argument("--math", default=None, choices=["f16c", "bf16x3", "bf16"],
                     help="default f16c (fp32 parity, 2 pass-equivalents) for forward, bf16 for train (config 3 is a bf16 step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline forward only (skip train / lite sweep / eager sub-records)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.batch is None:
@@ -321,6 +421,9 @@ def main():
     from motionbert_b200 import _lib
     if args.mode == "train":
         run_train(args, device, world, rank, local_rank, dist, D)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     model = build_model(args.model, device, args.math)
     cfg = MODELS[args.model]
@@ -331,45 +434,32 @@ def main():
     out_host = torch.empty(B, T, 17, 3).pin_memory()
     x_dev = x_host.to(device)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
     def max_over_ranks(v):
         return D.max_over_ranks(v, device)
 
-    # ---- warm-up (also builds the handle, packs weights, allocates the workspace)
+    # ---- device-resident throughput: K forwards, inputs already in HBM, CUDA events on the launching stream
     with torch.no_grad():
         for _ in range(args.warmup):
-            out = model(x_dev)
-    barrier()
-
-    # ---- device-resident throughput: K forwards, inputs already in HBM, CUDA events on the launching stream
+            model(x_dev)
+    _barrier(dist, device)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.no_grad():
-        ev0.record()
-        for _ in range(args.steps):
-            out = model(x_dev)
-        ev1.record()
-    barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step, out = forward_rate(model, x_dev, args.steps, 0, dist, device, D)
     sampler.stop_flag = True
     sampler.join(timeout=3)
     clocks = sampler.summary()
-    ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
+    # ---- the output that was timed, against the CPU oracle (rank 0; a miss fails the run)
+    parity = parity_check(model, args.model, x_host, out, device) if rank == 0 else None
+
     # ---- end to end through the public API: pinned host clip -> H2D -> forward -> D2H of the 3D pose, every step
-    barrier()
+    _barrier(dist, device)
     with torch.no_grad():
         for _ in range(2):
             out_host.copy_(model(x_host.to(device, non_blocking=True)), non_blocking=True)
         torch.cuda.synchronize(device)
-        barrier()
+        _barrier(dist, device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
@@ -377,7 +467,7 @@ def main():
             out_host.copy_(model(xd), non_blocking=True)
         e1.record()
         torch.cuda.synchronize(device)
-    barrier()
+    _barrier(dist, device)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = world * B / (e2e_ms * 1e-3)
 
@@ -407,13 +497,13 @@ def main():
     passes = {"bf16x3": 3, "f16c": 2, "bf16": 1}[args.math]
     # DRAM traffic of the GEMM class from the committed ncu --set full capture of this same configuration
     traffic, traffic_src = None, None
-    if args.model == "base" and B == 256 and T == 243 and passes == 2:
+    if args.model == "base" and B == 256 and T == 243:
         import glob
         for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
             try:
                 with open(f) as fh:
                     js = json.load(fh)
-                if "gemm_avg_dram_bytes_per_launch" in js:
+                if js.get("math", "bf16x3") == args.math and "gemm_avg_dram_bytes_per_launch" in js:
                     traffic, traffic_src = js["gemm_avg_dram_bytes_per_launch"], os.path.basename(f)
                     break
             except Exception:
@@ -426,8 +516,8 @@ def main():
         "peak_source": peaks["_source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "mma_passes": passes,
         "note": f"achieved = algorithmic GEMM FLOPs per launch ({gemm_flop / max(gemm_launches, 1) / 1e9:.1f} GFLOP avg over "
-                f"{gemm_launches} launches/step) / mean launch time; {passes} bf16 MMA pass(es) per algorithmic FLOP, so the "
-                f"tensor pipe does {passes}x this work (ceiling of frac = {1.0 / passes:.3f})",
+                f"{gemm_launches} launches/step) / mean launch time; the tensor pipe spends {passes} 16-bit-pass equivalent(s) per "
+                f"algorithmic FLOP (f16c: one fp16 pass + one e5m2 pass of twice the rate), ceiling of frac = {1.0 / passes:.3f}",
         "tensor_pipe_tflops_executed": achieved_tf * passes,
         "whole_step_tflops": total_flop / (ms_per_step * 1e-3) / 1e12,
         "whole_step_frac": total_flop / (ms_per_step * 1e-3) / 1e12 / peak_tf,
@@ -456,7 +546,36 @@ def main():
                 "api": "motionbert_b200.DSTformer.forward(x) on a pinned host clip, result copied back to pinned host"},
         "gpu_launches": launches,
         "roofline": roofline,
+        "parity": parity,
     }
+
+    if not args.no_extras and args.model == "base":
+        # release the forward's 26 GB workspace before the sub-records (the training step needs ~125 GB at B = 128)
+        del out, x_dev
+        model._dev_state.clear()
+        torch.cuda.empty_cache()
+        # ---- config 5: DSTformer-Lite inference sweep, B = 512 per GPU (replicas, no collective)
+        sweep = []
+        lite = build_model("lite", device, args.math)
+        for t_len in (27, 81, 243):
+            xl = synthetic_clips(512, t_len, seed=7 + rank).to(device)
+            ms, _o = forward_rate(lite, xl, max(5, min(args.steps, 10)), 3, dist, device, D)
+            fl = flops_per_sequence(256, 1024, t_len) * 512
+            sweep.append({"T": t_len, "B_per_gpu": 512, "value": world * 512 / (ms * 1e-3), "unit": "sequences/sec",
+                          "ms_per_step": ms, "whole_step_tflops": fl / (ms * 1e-3) / 1e12,
+                          "whole_step_frac": fl / (ms * 1e-3) / 1e12 / peak_tf})
+            del xl, _o
+        line["lite_sweep"] = {"config": f"BASELINE config 5: DSTformer-Lite forward, B=512 per GPU, {args.math}, n_gpus={world}",
+                              "points": sweep}
+        del lite
+        torch.cuda.empty_cache()
+        # ---- config 3 (N = 1) / config 4 (N > 1): the pretrain step
+        line["train"] = train_record(args, device, world, rank, local_rank, dist, D, "base", 128, 243, "bf16",
+                                     steps=20, warmup=3)
+        # ---- the reference's forward in torch eager on this same GPU (N = 1 only: a per-GPU comparator)
+        if world == 1:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(build_model(args.model, device, args.math), args.model, T, device)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_rate(args.model, T, budget_s=20.0)
     if rank == 0:
@@ -464,6 +583,8 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: the timed output misses the parity bars: " + json.dumps(parity))
 
 
 if __name__ == "__main__":

@@ -77,6 +77,7 @@ typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 #define MB_FLAG_REF_ATTN_S 0x8u   /* TEST ONLY: CUDA-core reference spatial attention                 */
 #define MB_FLAG_ATTN_T_V2  0x10u  /* TEST ONLY: experimental temporal attention with P in a smem ring   */
 #define MB_FLAG_ATTN_T_UNPACKED 0x20u /* TEST ONLY: one-sequence-per-tile temporal kernel even when F <= 32 */
+#define MB_FLAG_ATTN_BF16X3 0x40u /* TEST ONLY (F16C mode): qkv as bf16 hi/lo planes + the BF16x3 attention kernels    */
 #define MB_FLAG_GEMM_1CTA  0x4u   /* TEST ONLY: first-generation 1-CTA tcgen05 GEMM (LSU epilogue)    */
 
 int mb_version(void);

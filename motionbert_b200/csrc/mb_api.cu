@@ -15,7 +15,9 @@
 
 #include "../../include/motionbert_b200.h"
 #include "attn_bwd_tc.cuh"
+#include "attn_s_f16c.cuh"
 #include "attn_s_tc.cuh"
+#include "attn_t_f16c.cuh"
 #include "attn_t_tc.cuh"
 #include "attn_t_tc2.cuh"
 #include "backward_kernels.cuh"
@@ -231,6 +233,12 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(attn_s_tc_kernel<HD_, P_, true>, AttnSCfg<HD_, P_>::SMEM_BYTES))
         SET_ATS(64, 3); SET_ATS(32, 3); SET_ATS(64, 1); SET_ATS(32, 1);
 #undef SET_ATS
+        CUDA_TRY(set_smem(attn_t16_kernel<64>, AttnT16Cfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_t16_kernel<32>, AttnT16Cfg<32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s16_kernel<64, false>, AttnS16Cfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s16_kernel<64, true>, AttnS16Cfg<64>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s16_kernel<32, false>, AttnS16Cfg<32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(attn_s16_kernel<32, true>, AttnS16Cfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_s_kernel<64>, 200 * 1024));
         CUDA_TRY(set_smem(attn_s_kernel<32>, 200 * 1024));
         CUDA_TRY(set_smem(attn_t_ref_kernel<64>, 200 * 1024));
@@ -278,7 +286,33 @@ struct Plan {
     CUtensorMap tm_qkv_st, tm_hid_st;   // split-store maps of the qkv / hidden buffers
     CUtensorMap tm_qkv_sp;              // 4-D (col, joint, frame, plane) view of qkv for spatial attention
     CUtensorMap tm_qkv_t32;             // 5-D view, box (d, 1, 32 frames, 1, 1): packed temporal attention (F <= 32)
+    // F16C mode: the qkv buffer is one F16C row buffer [M][3C]; maps in 16-bit units over (6C, J, F, B) / (6C, J, B*F)
+    bool attn_f16c = false;
+    CUtensorMap tm_qkv_st16;            // epilogue store map of the qkv projection
+    CUtensorMap tm_q16, tm_kv16;        // temporal: box (64, 1, 128, 1) / (64, 1, NK, 1)
+    CUtensorMap tm_sp16;                // spatial : box (64, 32, 4)
+    CUtensorMap tm_t32_16;              // packed temporal (F <= 32): box (64, 1, 32, 1)
 };
+
+// tensor maps of the F16C attention kernels over an F16C qkv row buffer [B*F*J][3C]
+static int make_attn16_maps(Plan* P, const void* qkv, int B, int F, int J, int C) {
+    const uint64_t W16 = 6ull * C;      // 16-bit units per token row (3C elements x 4 bytes)
+    const uint64_t dims[4] = {W16, static_cast<uint64_t>(J), static_cast<uint64_t>(F), static_cast<uint64_t>(B)};
+    const uint64_t str[3] = {W16, W16 * J, W16 * J * F};
+    const uint32_t NK = static_cast<uint32_t>((F + 31) / 32 * 32);
+    const uint32_t box_q[4] = {64, 1, ATT_BM, 1};
+    const uint32_t box_kv[4] = {64, 1, NK, 1};
+    const uint32_t box_t32[4] = {64, 1, ATS_SLAB, 1};
+    int rc;
+    if ((rc = make_tmap(&P->tm_q16, qkv, 4, dims, str, box_q, 128))) return rc;
+    if ((rc = make_tmap(&P->tm_kv16, qkv, 4, dims, str, box_kv, 128))) return rc;
+    if ((rc = make_tmap(&P->tm_t32_16, qkv, 4, dims, str, box_t32, 128))) return rc;
+    const uint64_t dims3[3] = {W16, static_cast<uint64_t>(J), static_cast<uint64_t>(B) * F};
+    const uint64_t str3[2] = {W16, W16 * J};
+    const uint32_t box3[3] = {64, ATS_SLAB, ATS_FRAMES};
+    if ((rc = make_tmap(&P->tm_sp16, qkv, 3, dims3, str3, box3, 128))) return rc;
+    return make_f16c_store_tmap(&P->tm_qkv_st16, qkv, static_cast<uint64_t>(B) * F * J, 3ull * C);
+}
 
 struct MbEncoder {
     MbDesc d;
@@ -637,6 +671,8 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
             if ((rc = make_f16c_operand_tmap(&P->tm_hid, P->hid, M, d.hidden, GEMM_BM))) return rc;
             if ((rc = make_f16c_operand_tmap(&P->tm_ao, P->ao, M, C, GEMM_BM))) return rc;
             if ((rc = make_f16c_store_tmap(&P->tm_hid_st, P->hid, M, d.hidden))) return rc;
+            if ((rc = make_attn16_maps(P, P->qkv, B, F, d.num_joints, d.dim_feat))) return rc;
+            P->attn_f16c = true;
         }
     }
     {
@@ -732,10 +768,45 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     const MbDesc& d = e->d;
     const int C = d.dim_feat, H = d.num_heads, J = d.num_joints, hd = C / H;
     const bool f16c = is_f16c(d);
-    const int passes = f16c ? 3 : passes_of(d);      // F16C mode: qkv arrives as bf16 hi/lo planes, output leaves as F16C rows
+    // F16C mode + MB_FLAG_ATTN_BF16X3 (test / A-B only): qkv arrives as bf16 hi/lo planes, the BF16x3 kernels run, the
+    // output leaves as F16C rows
+    const int passes = f16c ? 3 : passes_of(d);
     if (f16c && (flags & (MB_FLAG_REF_ATTN_S | MB_FLAG_REF_ATTN_T | MB_FLAG_ATTN_T_V2)))
         return fail(MB_ERR_INVALID, "the CUDA-core / experimental test attention kernels exist for the bf16 modes only");
     const float scale = d.qk_scale > 0.f ? d.qk_scale : 1.0f / sqrtf(static_cast<float>(hd));   // DSTformer.py:94
+    if (f16c && !(flags & MB_FLAG_ATTN_BF16X3)) {
+        if (!P.attn_f16c) return fail(MB_ERR_INVALID, "internal: F16C attention maps missing");
+        prof_mark(e, st, temporal ? PC_ATTN_T : PC_ATTN_S);
+        uint8_t* out = reinterpret_cast<uint8_t*>(P.ao);
+        if (!temporal || (F <= ATS_SLAB && !(flags & MB_FLAG_ATTN_T_UNPACKED))) {
+            AttnS16Params sp;
+            sp.nseq = temporal ? B * J : B * F; sp.L = temporal ? F : J; sp.F = F; sp.J = J; sp.C = C; sp.H = H;
+            sp.scale_log2e = scale * 1.4426950408889634f;
+            sp.out = out;
+            const int prob = ((sp.nseq + ATS_FRAMES - 1) / ATS_FRAMES) * H;
+            const int grid = prob < e->dev.sms ? prob : e->dev.sms;
+            if (!temporal) {
+                if (hd == 64) attn_s16_kernel<64, false><<<grid, ATT_THREADS, AttnS16Cfg<64>::SMEM_BYTES, st>>>(P.tm_sp16, sp);
+                else attn_s16_kernel<32, false><<<grid, ATT_THREADS, AttnS16Cfg<32>::SMEM_BYTES, st>>>(P.tm_sp16, sp);
+            } else {
+                if (hd == 64) attn_s16_kernel<64, true><<<grid, ATT_THREADS, AttnS16Cfg<64>::SMEM_BYTES, st>>>(P.tm_t32_16, sp);
+                else attn_s16_kernel<32, true><<<grid, ATT_THREADS, AttnS16Cfg<32>::SMEM_BYTES, st>>>(P.tm_t32_16, sp);
+            }
+            LAUNCH_CHECK("attn_s16_kernel");
+            return MB_OK;
+        }
+        AttnT16Params ap;
+        ap.B = B; ap.F = F; ap.J = J; ap.C = C; ap.H = H;
+        ap.NK = (F + 31) / 32 * 32;
+        ap.scale_log2e = scale * 1.4426950408889634f;
+        ap.out = out;
+        const int prob = B * J * H;
+        const int grid = prob < e->dev.sms ? prob : e->dev.sms;
+        if (hd == 64) attn_t16_kernel<64><<<grid, ATT_T_THREADS, AttnT16Cfg<64>::SMEM_BYTES, st>>>(P.tm_q16, P.tm_kv16, ap);
+        else attn_t16_kernel<32><<<grid, ATT_T_THREADS, AttnT16Cfg<32>::SMEM_BYTES, st>>>(P.tm_q16, P.tm_kv16, ap);
+        LAUNCH_CHECK("attn_t16_kernel");
+        return MB_OK;
+    }
     const __nv_bfloat16* q_hi = P.qkv;
     const __nv_bfloat16* q_lo = passes == 3 ? P.qkv + qkv_plane_el : nullptr;
     __nv_bfloat16* o_hi = P.ao;
@@ -973,8 +1044,8 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
         p.out_hi = AP->qkv;
         p.out_lo = AP->qkv + qkv_plane_el;
         EpiMaps em;
-        em.out_s = &AP->tm_qkv_st;
-        em.split_bf16 = true;
+        em.split_bf16 = !f16c || (flags & MB_FLAG_ATTN_BF16X3);
+        em.out_s = em.split_bf16 ? &AP->tm_qkv_st : &AP->tm_qkv_st16;
         int r = launch_gemm<EPI_LN_SPLIT>(enc, flags, src.tmap, src.hi, src.lo, L[temporal ? L_QKV_T : L_QKV_S], pk, p, em, st);
         if (r) return r;
         r = launch_attn(enc, flags, temporal, *AP, B, F, qkv_plane_el, ao_plane_el, st);
@@ -1154,6 +1225,21 @@ __global__ void split_flat_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat
         split_bf16(x[i], h, l);
         hi[i] = h;
         if (lo) lo[i] = l;
+    }
+}
+
+// fp32 [rows][cols] (cols % 32 == 0) -> F16C rows; one thread per PAIR of consecutive elements
+__global__ void split_flat_f16c_kernel(const float* x, uint8_t* out, size_t npairs) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < npairs) {
+        const size_t e = 2 * i;                    // flat element index; rows are multiples of 32 elements long
+        uint32_t h, l, g;
+        split2_f16c(x[e], x[e + 1], h, l, g);
+        uint8_t* blk = out + (e >> 5) * 128;
+        const int c = static_cast<int>(e & 31);
+        *reinterpret_cast<uint32_t*>(blk + 2 * c) = h;
+        *reinterpret_cast<uint16_t*>(blk + 64 + c) = static_cast<uint16_t>(l);
+        *reinterpret_cast<uint16_t*>(blk + 96 + c) = static_cast<uint16_t>(g);
     }
 }
 
@@ -1341,6 +1427,21 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
     P.qkv = reinterpret_cast<__nv_bfloat16*>(b);
     P.ao = reinterpret_cast<__nv_bfloat16*>(b + 2 * qkv_plane);
     const int passes = math == MB_MATH_BF16 ? 1 : 3;
+    if (math == MB_MATH_F16C) {
+        // F16C rows in, F16C rows out, the production F16C kernels (use_ref: 0, or 3 = unpacked temporal kernel for F <= 32)
+        if (use_ref != 0 && use_ref != 3) return fail(MB_ERR_INVALID, "F16C: production attention kernels only");
+        const size_t n2 = M * 3 * C / 2;
+        split_flat_f16c_kernel<<<static_cast<int>((n2 + 255) / 256), 256, 0, st>>>(qkv, reinterpret_cast<uint8_t*>(P.qkv), n2);
+        LAUNCH_CHECK("split_flat_f16c_kernel");
+        if ((rc = make_attn16_maps(&P, P.qkv, B, F, J, C))) return rc;
+        P.attn_f16c = true;
+        rc = launch_attn(&e, use_ref == 3 ? MB_FLAG_ATTN_T_UNPACKED : 0u, temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st);
+        if (rc) return rc;
+        const size_t n = M * C;
+        merge_f16c_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(P.ao), y, static_cast<int>(M), C);
+        LAUNCH_CHECK("merge_f16c_kernel");
+        return MB_OK;
+    }
     {
         const size_t n = M * 3 * C;
         split_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(qkv, P.qkv, P.qkv + qkv_plane / 2, n);

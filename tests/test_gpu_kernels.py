@@ -138,6 +138,33 @@ def test_spatial_attention(cuda_device, B, F, J, C, H, use_ref):
     assert rel < 3e-5, f"rel {rel:.3e} max {mx:.3e}"
 
 
+@pytest.mark.parametrize("use_ref", [3, 0], ids=["f16c_unpacked", "f16c"])
+@pytest.mark.parametrize("B,F,J,C,H", ATT_SHAPES)
+def test_temporal_attention_f16c(cuda_device, B, F, J, C, H, use_ref):
+    """F16C attention (attn_t_f16c.cuh, and attn_s_f16c.cuh in its packed-temporal mode for F <= 32): F16C rows in,
+    2 fp16 + 2 e5m2 MMAs per 32-channel block for Q K^T and P V, F16C rows out (decoded as h + l)."""
+    g = torch.Generator().manual_seed(B * 1000 + F)
+    qkv = (torch.randn(B * F * J, 3 * C, generator=g) * 1.2).to(cuda_device)
+    y = G.test_attention(1, qkv, B, F, J, C, H, math=2, use_ref=use_ref)
+    exp = _attn_expected(qkv, B, F, J, C, H, True)
+    assert torch.isfinite(y).all()
+    rel, mx = _rel(y, exp)
+    print(f"f16c temporal B={B} F={F} C={C}: rel {rel:.3e} max {mx:.3e}")
+    assert rel < 2e-4, f"rel {rel:.3e} max {mx:.3e}"
+
+
+@pytest.mark.parametrize("B,F,J,C,H", ATT_SHAPES)
+def test_spatial_attention_f16c(cuda_device, B, F, J, C, H):
+    g = torch.Generator().manual_seed(B * 77 + F)
+    qkv = (torch.randn(B * F * J, 3 * C, generator=g) * 1.2).to(cuda_device)
+    y = G.test_attention(0, qkv, B, F, J, C, H, math=2, use_ref=0)
+    exp = _attn_expected(qkv, B, F, J, C, H, False)
+    assert torch.isfinite(y).all()
+    rel, mx = _rel(y, exp)
+    print(f"f16c spatial B={B} F={F} C={C}: rel {rel:.3e} max {mx:.3e}")
+    assert rel < 2e-4, f"rel {rel:.3e} max {mx:.3e}"
+
+
 @pytest.mark.parametrize("B,F,J,C,H", [(2, 27, 17, 512, 8), (1, 243, 17, 256, 8)])
 def test_temporal_attention_bf16_single_pass(cuda_device, B, F, J, C, H):
     g = torch.Generator().manual_seed(5)
