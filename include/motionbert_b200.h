@@ -159,6 +159,23 @@ int mb_pretrain_loss(const float* pred, const float* target, const float* conf, 
                      float lambda_scale, float lambda_velocity, float* losses, float* d_pred, void* scratch,
                      void* stream);
 
+/* ---- Augmenter2D on the GPU in one pass (lib/data/augmentation.py:29-74, called at
+ * train.py:162-172 immediately before the encoder) ----------------------------------------------------------------
+ * noise != 0: `add_noise` (:29-65).  The caller supplies the random draws in the reference's own order and shapes (so
+ *   the reference's seed reproduces the reference's augmentation): sel (B,K,J) ~ U[0,1), gauss (B,K,J,2) ~ N(0,1),
+ *   unif (B,K,J,2) ~ U[0,1), jitter (F,J,2) ~ N(0,1), shift (B,F,J) ~ N(0,1); K = 27 key frames; mean/std (J,2) and
+ *   weight (J) are params/synthetic_noise.pth, (a, b, m, s) params/d2c_params.pkl, noise_std = 0.002, uniform_range
+ *   = 0.06.  Per (b, key frame, joint): delta = sel < weight[j] ? gauss*std+mean : (unif-0.5)*range; linear
+ *   interpolation over the F frames (align_corners), + jitter*noise_std; x,y += delta; conf = clip(a/(d+a) + b d +
+ *   shift s + m, 0, 1) with d = |delta|.
+ * mask != 0: `add_mask` (:67-74): out *= (mask_u (B,F,J) > mask_ratio) * (maskT_u (F) > mask_T_ratio).
+ * x: (B,F,J,cin) fp32, cin >= 2 (>= 3 when noise == 0); out: (B,F,J,3) fp32.  All device pointers. */
+int mb_augment2d(const float* x, int cin, int B, int F, int J, int K, int noise, int mask, const float* sel,
+                 const float* gauss, const float* unif, const float* jitter, const float* shift, const float* mean,
+                 const float* stdv, const float* weight, float uniform_range, float noise_std, float a, float b, float m,
+                 float s, const float* mask_u, const float* maskT_u, float mask_ratio, float mask_T_ratio, float* out,
+                 void* stream);
+
 /* Number of kernels one mb_forward call launches for this (B, F) (for bench.py's gpu_launches). */
 int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags);
 

@@ -125,3 +125,80 @@ __global__ void pose_loss_finalize_kernel(const double* acc, int B, int T, int J
 }
 
 }  // namespace mb
+
+// ---------------------------------------------------------------------------------------------
+// Augmenter2D (lib/data/augmentation.py:29-74; called in train.py:162-172 right before the encoder):
+//   add_noise: per (clip, 27 key frames, joint) a displacement drawn from a per-joint Gaussian (probability weight[j]) or a
+//              uniform range, interpolated linearly over the F frames (F.interpolate trilinear, align_corners=True: only
+//              the frame axis changes size), plus per-(frame, joint) jitter; the detector confidence is re-synthesised
+//              from the displacement length: conf = clip(a / (d + a) + b d + (shift s + m), 0, 1);
+//   add_mask : per-(clip, frame, joint) and per-frame Bernoulli masks multiply (x, y, conf).
+// The reference runs ~25 elementwise / interpolate kernels over (B, F, J, .) tensors; here ONE pass reads the clip and the
+// random draws (made by the caller in the reference's own order, so a seed reproduces the reference's augmentation) and
+// writes the augmented (B, F, J, 3) clip.  One thread per (b, f, j).
+// ---------------------------------------------------------------------------------------------
+struct Augment2DParams {
+    const float* x;            // (B, F, J, cin) input clip, cin >= 2 (only x, y are read when noise is on)
+    int cin;
+    int B, F, J, K;            // K = key frames of the noise model (27)
+    int do_noise, do_mask;
+    const float* sel;          // (B, K, J)     U[0,1)
+    const float* gauss;        // (B, K, J, 2)  N(0,1)
+    const float* unif;         // (B, K, J, 2)  U[0,1)
+    const float* jitter;       // (F, J, 2)     N(0,1)
+    const float* shift;        // (B, F, J)     N(0,1)
+    const float* mean;         // (J, 2)
+    const float* stdv;         // (J, 2)
+    const float* weight;       // (J)
+    float uniform_range, noise_std, a, b, m, s;
+    const float* mask_u;       // (B, F, J) U[0,1)
+    const float* maskT_u;      // (F)       U[0,1)
+    float mask_ratio, mask_T_ratio;
+    float* out;                // (B, F, J, 3)
+};
+
+__global__ void __launch_bounds__(256) augment2d_kernel(const Augment2DParams p) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t n = static_cast<size_t>(p.B) * p.F * p.J;
+    if (i >= n) return;
+    const int j = static_cast<int>(i % p.J);
+    const int f = static_cast<int>((i / p.J) % p.F);
+    const int b = static_cast<int>(i / (static_cast<size_t>(p.J) * p.F));
+    float x0 = p.x[i * p.cin], x1 = p.x[i * p.cin + 1];
+    float c = p.cin > 2 ? p.x[i * p.cin + 2] : 1.f;
+    if (p.do_noise) {
+        // ATen upsample_trilinear3d, align_corners=True: src = f * (K-1)/(F-1); lambda in fp32
+        const float scale = p.F > 1 ? static_cast<float>(p.K - 1) / static_cast<float>(p.F - 1) : 0.f;
+        const float src = scale * static_cast<float>(f);
+        const int k0 = static_cast<int>(src);
+        const int k1 = k0 + (k0 < p.K - 1 ? 1 : 0);
+        const float l1 = src - static_cast<float>(k0), l0 = 1.0f - l1;
+        const float w = p.weight[j];
+        float d[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            float v[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int k = q == 0 ? k0 : k1;
+                const size_t kj = (static_cast<size_t>(b) * p.K + k) * p.J + j;
+                const float g = p.gauss[kj * 2 + e] * p.stdv[j * 2 + e] + p.mean[j * 2 + e];
+                const float u = (p.unif[kj * 2 + e] - 0.5f) * p.uniform_range;
+                const bool pick_g = p.sel[kj] < w;
+                v[q] = g * (pick_g ? 1.f : 0.f) + u * (pick_g ? 0.f : 1.f);
+            }
+            d[e] = (l0 * v[0] + l1 * v[1]) + (p.jitter[(static_cast<size_t>(f) * p.J + j) * 2 + e] * p.noise_std + 0.f);
+        }
+        x0 += d[0];
+        x1 += d[1];
+        const float dis = sqrtf(d[0] * d[0] + d[1] * d[1]);
+        const float fconf = p.a / (dis + p.a) + p.b * dis;
+        c = fminf(fmaxf(fconf + (p.shift[i] * p.s + p.m), 0.f), 1.f);
+    }
+    if (p.do_mask) {
+        const float mk = (p.mask_u[i] > p.mask_ratio ? 1.f : 0.f);
+        const float mt = (p.maskT_u[f] > p.mask_T_ratio ? 1.f : 0.f);
+        x0 = x0 * mk * mt; x1 = x1 * mk * mt; c = c * mk * mt;
+    }
+    p.out[i * 3] = x0; p.out[i * 3 + 1] = x1; p.out[i * 3 + 2] = c;
+}

@@ -2161,3 +2161,27 @@ extern "C" int mb_pretrain_loss(const float* pred, const float* target, const fl
     LAUNCH_CHECK("pose_loss_finalize_kernel");
     return MB_OK;
 }
+
+// Augmenter2D.add_noise / add_mask (lib/data/augmentation.py:29-74) as one kernel; the caller supplies the random draws
+// (device tensors, shapes in include/motionbert_b200.h).  Any of the two stages may be off (noise != 0 / mask != 0).
+extern "C" int mb_augment2d(const float* x, int cin, int B, int F, int J, int K, int noise, int mask, const float* sel,
+                            const float* gauss, const float* unif, const float* jitter, const float* shift,
+                            const float* mean, const float* stdv, const float* weight, float uniform_range,
+                            float noise_std, float a, float b, float m, float s, const float* mask_u,
+                            const float* maskT_u, float mask_ratio, float mask_T_ratio, float* out, void* stream_) {
+    if (!x || !out) return fail(MB_ERR_NULL, "NULL argument");
+    if (B < 1 || F < 1 || J < 1 || cin < 2 || K < 1) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d J=%d cin=%d K=%d", B, F, J, cin, K);
+    if (noise && (!sel || !gauss || !unif || !jitter || !shift || !mean || !stdv || !weight))
+        return fail(MB_ERR_NULL, "noise stage needs sel/gauss/unif/jitter/shift/mean/std/weight");
+    if (mask && (!mask_u || !maskT_u)) return fail(MB_ERR_NULL, "mask stage needs mask_u/maskT_u");
+    if (!noise && cin < 3) return fail(MB_ERR_INVALID, "mask-only augmentation needs (x, y, conf) input");
+    Augment2DParams p;
+    p.x = x; p.cin = cin; p.B = B; p.F = F; p.J = J; p.K = K; p.do_noise = noise; p.do_mask = mask;
+    p.sel = sel; p.gauss = gauss; p.unif = unif; p.jitter = jitter; p.shift = shift; p.mean = mean; p.stdv = stdv;
+    p.weight = weight; p.uniform_range = uniform_range; p.noise_std = noise_std; p.a = a; p.b = b; p.m = m; p.s = s;
+    p.mask_u = mask_u; p.maskT_u = maskT_u; p.mask_ratio = mask_ratio; p.mask_T_ratio = mask_T_ratio; p.out = out;
+    const size_t n = static_cast<size_t>(B) * F * J;
+    augment2d_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+    LAUNCH_CHECK("augment2d_kernel");
+    return MB_OK;
+}
