@@ -159,6 +159,14 @@ int mb_pretrain_loss(const float* pred, const float* target, const float* conf, 
                      float lambda_scale, float lambda_velocity, float* losses, float* d_pred, void* scratch,
                      void* stream);
 
+/* ---- action-recognition tail (lib/model/model_action.py:15-21, :62-71) ---------------
+ * `ActionHeadClassification` / `ActionHeadEmbed` consume the representation only through its mean over the T frames.
+ * mb_forward_pooled runs the same forward as mb_forward but the tail GEMM's epilogue accumulates
+ *     rep_pool[b, j, :] = mean_f tanh(Linear(LN(x)))[b, f, j, :]           (B, J, dim_rep) fp32, 16-byte aligned
+ * and the (B, F, J, dim_rep) representation (2.2 GB at B=256, T=243) is never written.  Same workspace as mb_forward. */
+int mb_forward_pooled(MbEncoder* enc, const void* packed, const float* x, float* rep_pool, void* workspace,
+                      size_t workspace_bytes, int B, int F, uint32_t flags, void* stream);
+
 /* ---- Augmenter2D on the GPU in one pass (lib/data/augmentation.py:29-74, called at
  * train.py:162-172 immediately before the encoder) ----------------------------------------------------------------
  * noise != 0: `add_noise` (:29-65).  The caller supplies the random draws in the reference's own order and shapes (so

@@ -26,7 +26,7 @@ MB_FLAG_ATTN_BF16X3 = 0x40
 EXPORTS = [
     "mb_version", "mb_last_error", "mb_create", "mb_destroy", "mb_param_count", "mb_param_info",
     "mb_packed_bytes", "mb_pack_weights", "mb_workspace_bytes", "mb_forward", "mb_workspace_bytes_host",
-    "mb_forward_host", "mb_forward_launch_count", "mb_profile_enable", "mb_profile_read",
+    "mb_forward_host", "mb_forward_pooled", "mb_forward_launch_count", "mb_profile_enable", "mb_profile_read",
     "mb_saved_bytes", "mb_forward_train", "mb_backward_workspace_bytes", "mb_backward", "mb_backward_launch_count", "mb_pretrain_loss", "mb_augment2d",
     "mb_test_linear_scratch_bytes", "mb_test_linear",
     "mb_test_attention_scratch_bytes", "mb_test_attention", "mb_test_wgrad_scratch_bytes", "mb_test_wgrad",
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.mb_forward.argtypes = [vp, vp, fp, fp, fp, fp, vp, sz, i32, i32, u32, vp]
     lib.mb_workspace_bytes_host.argtypes = [vp, i32, i32, i32, i32, C.POINTER(sz)]
     lib.mb_forward_host.argtypes = [vp, vp, fp, fp, fp, vp, sz, i32, i32, u32, vp]
+    lib.mb_forward_pooled.argtypes = [vp, vp, fp, fp, vp, sz, i32, i32, u32, vp]
     lib.mb_forward_launch_count.argtypes = [vp, i32, u32]
     lib.mb_profile_enable.argtypes = [vp, i32]
     lib.mb_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]

@@ -27,8 +27,10 @@ namespace mb {
 enum : int { EPI_LN_SPLIT = 0, EPI_LN_GELU_SPLIT = 1, EPI_RESID = 2, EPI_LN_TANH_F32 = 3, EPI_BIAS_F32 = 4,
               EPI_BIAS_SPLIT = 5,      /* y = acc + b[n] -> bf16 plane                          (backward: qkv recompute, dgrad) */
               EPI_BIAS_GELU_PAIR = 6,  /* plane 0 = y = acc + b[n], plane 1 = gelu(y)             (backward: fc1 recompute)         */
-              EPI_GELUBWD_SPLIT = 7    /* y = acc * gelu'(aux[m, n]) -> bf16 plane                (backward: fc2 dgrad -> d h_pre)  */
-};                                     /* 5..7 exist in the 2-CTA kernel only */
+              EPI_GELUBWD_SPLIT = 7,   /* y = acc * gelu'(aux[m, n]) -> bf16 plane                (backward: fc2 dgrad -> d h_pre)  */
+              EPI_LN_TANH_POOL = 8     /* rep = tanh(LN-folded linear), never stored: its mean over the F frames of each
+                                          (clip, joint) is accumulated into out_f32[(b J + j), n]  (model_action.py:20-21)  */
+};                                     /* 5..8 exist in the 2-CTA kernel only */
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
@@ -53,6 +55,7 @@ struct GemmParams {
     __nv_bfloat16* out_lo;    // may be null when PASSES == 1
     float* stats_out;         // RESID: [M][N/128][3]
     const __nv_bfloat16* aux; // GELUBWD: pre-activation plane [M,N] (bf16)
+    int pool_F;               // LN_TANH_POOL: frames per clip (rows are (b F + f) J + j)
 };
 
 template <int PASSES>

@@ -83,7 +83,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     static_assert(!(B_MN && PASSES == 2), "the F16C mode has no MN-major weight form (backward runs in bf16)");
     static_assert(!OUT16C || EW == 8, "F16C output: 8 epilogue warps");
     constexpr bool kDoubleLd = !kResid && EW == 8;                               // register double-buffered tcgen05.ld
-    constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32);
+    constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32 || EPI == EPI_LN_TANH_POOL);
+    constexpr bool kPool = (EPI == EPI_LN_TANH_POOL);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -362,9 +363,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
                     }
-                    if (EPI == EPI_LN_TANH_F32) {
+                    if (EPI == EPI_LN_TANH_F32 || EPI == EPI_LN_TANH_POOL) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+                    }
+                    if (kPool && row_ok) {
+                        // temporal mean pool of the representation: rows (b, f, j) -> (b, j); fp32 vector reductions into L2
+                        const int bj = (row / (p.pool_F * p.J)) * p.J + row % p.J;
+                        float* dst = p.out_f32 + static_cast<size_t>(bj) * p.N + col0;
+                        const float w = 1.0f / static_cast<float>(p.pool_F);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(v[4 * i] * w),
+                                         "f"(v[4 * i + 1] * w), "f"(v[4 * i + 2] * w), "f"(v[4 * i + 3] * w)
+                                         : "memory");
                     }
                 }
                 // all lanes have consumed buf[b] (residual) and lane 0 has seen the older store groups retire

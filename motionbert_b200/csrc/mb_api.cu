@@ -201,6 +201,9 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_RESID>, Gemm2Cfg<2, EPI_RESID>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_F32>, Gemm2Cfg<2, EPI_LN_TANH_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_BIAS_F32>, Gemm2Cfg<2, EPI_BIAS_F32>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<1, EPI_LN_TANH_POOL>, Gemm2Cfg<1, EPI_LN_TANH_POOL>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_POOL>, Gemm2Cfg<2, EPI_LN_TANH_POOL>::SMEM_BYTES));
+        CUDA_TRY(set_smem(gemm2_kernel<3, EPI_LN_TANH_POOL>, Gemm2Cfg<3, EPI_LN_TANH_POOL>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<3, EPI_BIAS_F32, true>, Gemm2Cfg<3, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_BIAS_F32, true>, Gemm2Cfg<1, EPI_BIAS_F32>::SMEM_BYTES));
         // single-pass bf16-plane epilogues run with 16 epilogue warps (gemm_tc2.cuh)
@@ -720,6 +723,7 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
                      : EPI == EPI_RESID ? PC_GEMM_RESID : PC_GEMM_TAIL);
     if (passes == 2 && (flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA)))
         return fail(MB_ERR_INVALID, "the CUDA-core / 1-CTA test GEMMs exist for the bf16 modes only (math mode F16C)");
+    if constexpr (EPI <= EPI_BIAS_F32) {      // the CUDA-core / first-generation test GEMMs know the five forward epilogues
     if (flags & MB_FLAG_REF_GEMM) {
         const long warps = static_cast<long>(p.M) * (p.N / STATS_GROUP);
         const int grid = static_cast<int>((warps + 7) / 8);
@@ -739,6 +743,7 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
         LAUNCH_CHECK("gemm_tc_kernel");
         return MB_OK;
     }
+    }
     // production path: CTA pairs (cluster 2x1), one pair per 256x256 tile, persistent
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int max_pairs = e->dev.sms / 2;
@@ -746,6 +751,8 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
     const CUtensorMap& tmR = em.resid ? *em.resid : tmA;
     const CUtensorMap& tmX = em.out_x ? *em.out_x : tmA;
     const CUtensorMap& tmS = em.out_s ? *em.out_s : tmA;
+    if (EPI == EPI_LN_TANH_POOL && (flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA)))
+        return fail(MB_ERR_INVALID, "pooled tail: production GEMM only");
     if ((EPI == EPI_RESID && (!em.resid || !em.out_x || !em.out_s)) ||
         ((EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) && !em.out_s) ||
         ((EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32) && !em.out_x))
@@ -922,9 +929,11 @@ static SavedLayout saved_layout(const MbDesc& d, int B, int F) {
 
 static int forward_impl(MbEncoder* enc, const void* packed, const float* x, float* out, float* rep,
                         const float* drop_path_scale, void* workspace, size_t workspace_bytes, int B, int F,
-                        uint32_t flags, void* stream_, uint8_t* saved) {
+                        uint32_t flags, void* stream_, uint8_t* saved, float* rep_pool = nullptr) {
     if (!enc || !packed || !x || !workspace) return fail(MB_ERR_NULL, "NULL argument");
-    if (!out && !rep) return fail(MB_ERR_NULL, "both out and rep are NULL");
+    if (!out && !rep && !rep_pool) return fail(MB_ERR_NULL, "out, rep and rep_pool are all NULL");
+    if (rep_pool && (out || rep || saved)) return fail(MB_ERR_INVALID, "rep_pool is a stand-alone output");
+    if (rep_pool && (reinterpret_cast<uintptr_t>(rep_pool) & 15)) return fail(MB_ERR_ALIGN, "rep_pool must be 16-byte aligned");
     const MbDesc& d = enc->d;
     if (B < 1 || F < 1) return fail(MB_ERR_INVALID, "bad shape B=%d F=%d", B, F);
     if (F > d.maxlen) return fail(MB_ERR_INVALID, "F=%d exceeds maxlen=%d (temp_embed, DSTformer.py:336)", F, d.maxlen);
@@ -1121,6 +1130,19 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
         X0 = Xn;
     }
     // tail (DSTformer.py:352-357): rep = tanh(Linear(LN(x))), out = Linear(rep)
+    if (rep_pool) {
+        // action-recognition tail (row f3; model_action.py:20-21): mean over the F frames of rep, accumulated by the tail
+        // GEMM's epilogue -- the (B, F, J, dim_rep) representation itself is never written
+        CUDA_TRY(cudaMemsetAsync(rep_pool, 0, static_cast<size_t>(B) * J * d.dim_rep * sizeof(float), st));
+        GemmParams p = base;
+        p.stats_in = X0.stats;
+        p.out_f32 = rep_pool;
+        p.pool_F = F;
+        EpiMaps em;
+        if ((rc = launch_gemm<EPI_LN_TANH_POOL>(enc, flags, X0.tmap, X0.hi, X0.lo, enc->lin.back(), pk, p, em, st))) return rc;
+        prof_mark(enc, st, -1);
+        return MB_OK;
+    }
     float* rep_buf = rep ? rep : P.rep_ws;
     {
         GemmParams p = base;
@@ -1147,6 +1169,13 @@ extern "C" int mb_forward(MbEncoder* enc, const void* packed, const float* x, fl
                           const float* drop_path_scale, void* workspace, size_t workspace_bytes, int B, int F,
                           uint32_t flags, void* stream_) {
     return forward_impl(enc, packed, x, out, rep, drop_path_scale, workspace, workspace_bytes, B, F, flags, stream_, nullptr);
+}
+
+extern "C" int mb_forward_pooled(MbEncoder* enc, const void* packed, const float* x, float* rep_pool, void* workspace,
+                                 size_t workspace_bytes, int B, int F, uint32_t flags, void* stream_) {
+    if (!rep_pool) return fail(MB_ERR_NULL, "rep_pool is NULL");
+    if (flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA)) return fail(MB_ERR_INVALID, "pooled tail: production GEMM only");
+    return forward_impl(enc, packed, x, nullptr, nullptr, nullptr, workspace, workspace_bytes, B, F, flags, stream_, nullptr, rep_pool);
 }
 
 extern "C" int mb_profile_enable(MbEncoder* enc, int on) {

@@ -174,6 +174,16 @@ class DSTformer(nn.Module):
     def get_representation(self, x):                                             # :360-361
         return self.forward(x, return_rep=True)
 
+    def get_representation_pooled(self, x):
+        """mean over the frames of `get_representation(x)`: (B, F, J, 3) -> (B, J, dim_rep), what the action heads consume
+        (lib/model/model_action.py:20-21).  Without autograd the tail GEMM's epilogue accumulates the mean and the
+        (B, F, J, dim_rep) representation is never written (`mb_forward_pooled`); under autograd it is the plain mean."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(
+                p is not None and p.requires_grad for p in self._ordered_params())):
+            return self.get_representation(x).mean(dim=1)
+        x = self._check_input(x)
+        return self._launch(x, False, False, self._drop_path_scale(x.shape[0], x.shape[1], x.device), pooled=True)
+
     def set_math_mode(self, mode: str):
         """'f16c' (default: fp32 parity, fp16 pass + e5m2 compensation pass; gradient forwards use bf16x3),
         'bf16x3' (fp32 parity, 3 bf16 passes, inference and training) or 'bf16' (1 pass, inference and training)."""
@@ -299,8 +309,9 @@ class DSTformer(nn.Module):
                     rows.append(r.floor_() / keep)
         return torch.stack(rows).contiguous()
 
-    def _launch(self, x: torch.Tensor, want_out: bool, want_rep: bool, dp_scale):
-        """One mb_forward call on the current stream of x.device.  Returns (out, rep)."""
+    def _launch(self, x: torch.Tensor, want_out: bool, want_rep: bool, dp_scale, pooled: bool = False):
+        """One mb_forward (or mb_forward_pooled) call on the current stream of x.device.  Returns (out, rep), or the
+        pooled representation."""
         device = x.device
         B, F, J, _ = x.shape
         lib = _lib.load()
@@ -315,6 +326,14 @@ class DSTformer(nn.Module):
                 self._evict_workspaces(st)
                 ws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
                 st.workspaces[(B, F)] = ws
+            if pooled:
+                if dp_scale is not None:
+                    raise NotImplementedError("get_representation_pooled with DropPath active (training mode)")
+                pool = torch.empty(B, J, self.dim_rep, dtype=torch.float32, device=device)
+                _lib.check(lib.mb_forward_pooled(st.handle, self._aligned_ptr(st.packed), x.data_ptr(), pool.data_ptr(),
+                                                 self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags,
+                                                 stream_ptr), "mb_forward_pooled")
+                return pool
             out = torch.empty(B, F, J, self.dim_out, dtype=torch.float32, device=device) if want_out else None
             rep = torch.empty(B, F, J, self.dim_rep, dtype=torch.float32, device=device) if want_rep else None
             _lib.check(lib.mb_forward(
@@ -508,7 +527,7 @@ class DSTformer(nn.Module):
         return run
 
     # ------------------------------------------------------------------ forward (DSTformer.py:329-358)
-    def forward(self, x, return_rep=False):
+    def _check_input(self, x):
         if x.dim() != 4:
             raise ValueError(f"expected (B, F, J, C) input, got {tuple(x.shape)}")
         B, F, J, Cin = x.shape
@@ -522,7 +541,11 @@ class DSTformer(nn.Module):
         if self.training and (self.drop_rate > 0 or self.attn_drop_rate > 0):
             raise NotImplementedError("dropout / attention dropout > 0 in training mode is not implemented "
                                       "(all shipped configs use 0; DropPath is supported)")
-        x = x.detach().float().contiguous() if not x.requires_grad else x.float().contiguous()
+        return x.detach().float().contiguous() if not x.requires_grad else x.float().contiguous()
+
+    def forward(self, x, return_rep=False):
+        x = self._check_input(x)
+        B, F, J, Cin = x.shape
         dp_scale = self._drop_path_scale(B, F, x.device)
         # (not self.parameters(): nn.DataParallel replicas carry their parameters as plain attributes)
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(
