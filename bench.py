@@ -212,7 +212,8 @@ def train_record(args, device, world, rank, local_rank, dist, D, model_name="bas
     params = [p for p in model.parameters()]
     if world > 1:
         model.enable_gradient_allreduce()
-    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.01, fused=True)
+    from motionbert_b200.optim import AdamW
+    opt = AdamW(model, params, lr=1e-5, weight_decay=0.01)          # grouped native step + grouped re-pack (row f4)
 
     def step(x, gt):
         opt.zero_grad(set_to_none=True)
@@ -265,7 +266,7 @@ def train_record(args, device, world, rank, local_rank, dist, D, model_name="bas
     rec = {
         "metric": f"sequences/sec DSTformer-{model_name} pretrain step fwd+bwd+AdamW (Bx{T}x17)",
         "config": f"SURVEY 8d config {'3' if world == 1 else '4'}: B={B} per GPU, T={T}, {math} forward, bf16 native backward, "
-                  "fused pretrain loss, fused AdamW" + (", per-depth NCCL gradient all-reduce overlapped with the backward" if world > 1 else ""),
+                  "fused pretrain loss, native grouped AdamW + grouped weight re-pack" + (", per-depth NCCL gradient all-reduce overlapped with the backward" if world > 1 else ""),
         "value": world * B / (ms_per_step * 1e-3), "unit": "sequences/sec", "n_gpus": world, "global_batch": world * B,
         "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "last_loss": last, "clocks": clocks,
         "whole_step_tflops": achieved, "whole_step_frac": achieved / peak_tf,

@@ -167,6 +167,16 @@ int mb_pretrain_loss(const float* pred, const float* target, const float* conf, 
 int mb_forward_pooled(MbEncoder* enc, const void* packed, const float* x, float* rep_pool, void* workspace,
                       size_t workspace_bytes, int B, int F, uint32_t flags, void* stream);
 
+/* ---- optimizer step (train.py:289 optim.AdamW, train.py:206 optimizer.step()) ---------
+ * torch.optim.AdamW's arithmetic (decoupled weight decay, bias-corrected moments) over the encoder's parameter tensors
+ * in grouped launches (48 tensors per kernel, pointer table in kernel-parameter space) instead of a 260-tensor walk.
+ * All arrays have mb_param_count() entries in mb_param_info() order; active[i] == 0 (or active == NULL: all active)
+ * skips tensor i (frozen / no gradient).  t = 1-based step count.  mb_pack_weights re-packs all 81 linears in three
+ * grouped launches afterwards. */
+int mb_adamw_step(MbEncoder* enc, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const uint8_t* active, int t, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, void* stream);
+
 /* ---- Augmenter2D on the GPU in one pass (lib/data/augmentation.py:29-74, called at
  * train.py:162-172 immediately before the encoder) ----------------------------------------------------------------
  * noise != 0: `add_noise` (:29-65).  The caller supplies the random draws in the reference's own order and shapes (so

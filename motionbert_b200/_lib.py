@@ -27,7 +27,7 @@ EXPORTS = [
     "mb_version", "mb_last_error", "mb_create", "mb_destroy", "mb_param_count", "mb_param_info",
     "mb_packed_bytes", "mb_pack_weights", "mb_workspace_bytes", "mb_forward", "mb_workspace_bytes_host",
     "mb_forward_host", "mb_forward_pooled", "mb_forward_launch_count", "mb_profile_enable", "mb_profile_read",
-    "mb_saved_bytes", "mb_forward_train", "mb_backward_workspace_bytes", "mb_backward", "mb_backward_launch_count", "mb_pretrain_loss", "mb_augment2d",
+    "mb_saved_bytes", "mb_forward_train", "mb_backward_workspace_bytes", "mb_backward", "mb_backward_launch_count", "mb_pretrain_loss", "mb_augment2d", "mb_adamw_step",
     "mb_test_linear_scratch_bytes", "mb_test_linear",
     "mb_test_attention_scratch_bytes", "mb_test_attention", "mb_test_wgrad_scratch_bytes", "mb_test_wgrad",
     "mb_test_dgrad_scratch_bytes", "mb_test_dgrad",
@@ -87,6 +87,8 @@ def load() -> C.CDLL:
     f32 = C.c_float
     lib.mb_augment2d.argtypes = [fp, i32, i32, i32, i32, i32, i32, i32, fp, fp, fp, fp, fp, fp, fp, fp, f32, f32, f32, f32,
                                  f32, f32, fp, fp, f32, f32, fp, vp]
+    lib.mb_adamw_step.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_char_p, i32, f32, f32, f32,
+                                  f32, f32, vp]
     lib.mb_test_linear_scratch_bytes.argtypes = [i32, i32, i32, C.POINTER(sz)]
     lib.mb_test_linear.argtypes = [i32, i32, i32, i32, i32, i32, fp, fp, fp, fp, fp, fp, C.c_float, fp, fp, vp, sz, vp]
     lib.mb_test_attention_scratch_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]

@@ -24,6 +24,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "loss_kernels.cuh"
+#include "optim_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "wgrad_tc.cuh"
 
@@ -533,16 +534,34 @@ extern "C" int mb_pack_weights(MbEncoder* enc, const float* const* params, void*
     uint8_t* base = static_cast<uint8_t*>(packed);
     std::lock_guard<std::mutex> lk(enc->mu);
     const int passes = passes_of(enc->d);
+    const bool f16c = is_f16c(enc->d);
+    // operand planes / F16C rows + LayerNorm fold vectors of all linears: grouped launches (40 linears each)
+    for (size_t l0 = 0; l0 < enc->lin.size(); l0 += PACK_GROUP) {
+        PackGroup G;
+        memset(&G, 0, sizeof(G));
+        G.f16c = f16c ? 1 : 0;
+        int blocks = 0;
+        for (size_t l = l0; l < enc->lin.size() && l < l0 + PACK_GROUP; ++l) {
+            const LinearPack& L = enc->lin[l];
+            const int t = G.n++;
+            G.W[t] = params[L.p_w]; G.b[t] = params[L.p_b];
+            G.gamma[t] = L.ln ? params[L.p_g] : nullptr;
+            G.beta[t] = L.ln ? params[L.p_beta] : nullptr;
+            G.hi[t] = reinterpret_cast<__nv_bfloat16*>(base + L.off_hi);
+            G.lo[t] = reinterpret_cast<__nv_bfloat16*>(base + L.off_lo);
+            G.vec_c[t] = reinterpret_cast<float*>(base + L.off_c);
+            G.vec_s[t] = L.ln ? reinterpret_cast<float*>(base + L.off_s) : nullptr;
+            G.N[t] = L.N; G.K[t] = L.K;
+            blocks += (L.N + 7) / 8;
+            G.block_end[t] = blocks;
+        }
+        pack_group_kernel<<<blocks, 256, 0, st>>>(G);
+        LAUNCH_CHECK("pack_group_kernel");
+    }
+    const bool same_buffer = (enc->packed_ptr == packed);      // tensor maps depend on the buffer address only
     for (LinearPack& L : enc->lin) {
-        const int warps_per_block = 8;
-        const int grid = (L.N + warps_per_block - 1) / warps_per_block;
-        pack_linear_kernel<<<grid, 256, 0, st>>>(
-            params[L.p_w], params[L.p_b], L.ln ? params[L.p_g] : nullptr, L.ln ? params[L.p_beta] : nullptr, L.N, L.K,
-            reinterpret_cast<__nv_bfloat16*>(base + L.off_hi), reinterpret_cast<__nv_bfloat16*>(base + L.off_lo),
-            reinterpret_cast<float*>(base + L.off_c), L.ln ? reinterpret_cast<float*>(base + L.off_s) : nullptr,
-            is_f16c(enc->d) ? 1 : 0);
-        LAUNCH_CHECK("pack_linear_kernel");
-        if (is_f16c(enc->d)) {
+        if (same_buffer) break;
+        if (f16c) {
             // F16C rows [N][K] occupy the (adjacent) hi + lo plane regions; only the 2-CTA operand map exists
             if (L.off_lo != L.off_hi + static_cast<size_t>(L.N) * L.K * 2) return fail(MB_ERR_INVALID, "internal: packed planes not adjacent");
             int rc = make_f16c_operand_tmap(&L.tmap2, base + L.off_hi, L.N, L.K, 128);
@@ -583,6 +602,46 @@ extern "C" int mb_pack_weights(MbEncoder* enc, const float* const* params, void*
     }
     enc->packed_ptr = packed;
     return MB_OK;
+}
+
+// torch.optim.AdamW's step over the module's parameter tensors in grouped launches (row f4); `active[i] == 0` skips
+// tensor i (frozen by partial_train, or no gradient this step).  t is the 1-based step count.
+extern "C" int mb_adamw_step(MbEncoder* enc, float* const* params, const float* const* grads, float* const* exp_avg,
+                             float* const* exp_avg_sq, const uint8_t* active, int t, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, void* stream_) {
+    if (!enc || !params || !grads || !exp_avg || !exp_avg_sq) return fail(MB_ERR_NULL, "NULL argument");
+    if (t < 1) return fail(MB_ERR_INVALID, "step count must be >= 1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const int np = static_cast<int>(enc->names.size());
+    AdamWGroup G;
+    auto reset = [&]() {
+        memset(&G, 0, sizeof(G));
+        G.lr = lr; G.beta1 = beta1; G.beta2 = beta2; G.eps = eps; G.weight_decay = weight_decay;
+        G.bc1 = 1.0f - powf(beta1, static_cast<float>(t));
+        G.bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(t)));
+    };
+    auto flush = [&]() -> int {
+        if (G.n == 0) return MB_OK;
+        adamw_group_kernel<<<G.chunk_end[G.n - 1], 256, 0, st>>>(G);
+        LAUNCH_CHECK("adamw_group_kernel");
+        return MB_OK;
+    };
+    reset();
+    for (int i = 0; i < np; ++i) {
+        if (active && !active[i]) continue;
+        if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i]) return fail(MB_ERR_NULL, "tensor %d (%s): NULL pointer", i, enc->names[i].c_str());
+        const int k = G.n++;
+        G.p[k] = params[i]; G.g[k] = grads[i]; G.m[k] = exp_avg[i]; G.v[k] = exp_avg_sq[i];
+        G.numel[k] = static_cast<int>(enc->numels[i]);
+        const int chunks = static_cast<int>((enc->numels[i] + ADAMW_CHUNK - 1) / ADAMW_CHUNK);
+        G.chunk_end[k] = (k ? G.chunk_end[k - 1] : 0) + chunks;
+        if (G.n == ADAMW_GROUP) {
+            int rc = flush();
+            if (rc) return rc;
+            reset();
+        }
+    }
+    return flush();
 }
 
 // ------------------------------------------------------------------------------------ workspace
