@@ -72,13 +72,14 @@ typedef struct MbDesc {
 typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 
 /* flags for mb_forward */
+/* The TEST ONLY kernels are compiled into libmotionbert_b200_test.so only (include/motionbert_b200_test.h); the
+ * product library rejects their flags with MB_ERR_INVALID. */
 #define MB_FLAG_REF_GEMM   0x1u   /* TEST ONLY: CUDA-core reference GEMM instead of tcgen05           */
 #define MB_FLAG_REF_ATTN_T 0x2u   /* TEST ONLY: CUDA-core reference temporal attention                */
 #define MB_FLAG_REF_ATTN_S 0x8u   /* TEST ONLY: CUDA-core reference spatial attention                 */
-#define MB_FLAG_ATTN_T_V2  0x10u  /* TEST ONLY: experimental temporal attention with P in a smem ring   */
-#define MB_FLAG_ATTN_T_UNPACKED 0x20u /* TEST ONLY: one-sequence-per-tile temporal kernel even when F <= 32 */
-#define MB_FLAG_ATTN_BF16X3 0x40u /* TEST ONLY (F16C mode): qkv as bf16 hi/lo planes + the BF16x3 attention kernels    */
 #define MB_FLAG_GEMM_1CTA  0x4u   /* TEST ONLY: first-generation 1-CTA tcgen05 GEMM (LSU epilogue)    */
+#define MB_FLAG_ATTN_T_UNPACKED 0x20u /* one-sequence-per-tile temporal kernel even when F <= 32 (both libraries)  */
+#define MB_FLAG_ATTN_BF16X3 0x40u /* F16C mode A/B: qkv as bf16 hi/lo planes + the BF16x3 attention kernels (both)  */
 
 int mb_version(void);
 const char* mb_last_error(void);
@@ -205,41 +206,6 @@ int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags);
 #define MB_PROFILE_CLASSES 9
 int mb_profile_enable(MbEncoder* enc, int on);
 int mb_profile_read(MbEncoder* enc, float* ms_by_class, int* launches_by_class);
-
-/* ------------------------------------------------------------------ kernel-level test hooks ----------
- * Exercise one kernel in isolation so tests/ can localise a failure on the device.  Not used by the
- * product path. */
-
-/* y[M,N] = epilogue(A[M,K] . W[N,K]^T): A, W fp32 on device; scratch >= mb_test_linear_scratch_bytes().
- * mode: 0 LN-folded split (returns hi+lo as fp32), 1 LN+GELU split, 2 residual (+stats), 3 LN+tanh, 4 bias.
- * gamma/beta (LN modes) and resid (mode 2) may be NULL otherwise.  stats_out (mode 2): [M][N/128][3]. */
-int mb_test_linear_scratch_bytes(int M, int N, int K, size_t* bytes);
-int mb_test_linear(int mode, int math, int use_ref /* 0: 2-CTA tcgen05 (product), 1: CUDA-core reference, 2: 1-CTA tcgen05 */, int M, int N, int K, const float* A, const float* W,
-                   const float* bias, const float* gamma, const float* beta, const float* resid, float eps,
-                   float* y, float* stats_out, void* scratch, size_t scratch_bytes, void* stream);
-
-/* Attention over a fp32 qkv buffer [B*F*J, 3C] -> y fp32 [B*F*J, C].  temporal=1: forward_temporal
- * (DSTformer.py:188-200), 0: forward_spatial (:178-186). */
-int mb_test_attention_scratch_bytes(int B, int F, int J, int C, size_t* bytes);
-int mb_test_attention(int temporal, int math, int use_ref /* 0 product, 1 CUDA-core ref, 2 smem-ring T variant, 3 unpacked T */, int B, int F, int J, int C, int H, const float* qkv,
-                      float* y, void* scratch, size_t scratch_bytes, void* stream);
-
-/* Backward groundwork (not yet wired into a native backward pass):
- * dW[N,K] = G[M,N]^T . X[M,K] with the split-K tcgen05 weight-gradient kernel (both operands MN-major, no transposes).
- * G = dL/dy and X = the layer input, token-major fp32 on the device; dW fp32 (overwritten).  N % 128 == 0, K % 256 == 0. */
-int mb_test_wgrad_scratch_bytes(int M, int N, int K, size_t* bytes);
-int mb_test_wgrad(int math, int M, int N, int K, const float* G, const float* X, float* dW, void* scratch,
-                  size_t scratch_bytes, void* stream);
-/* dX[M,K] = G[M,N] . W[N,K]: the production 2-CTA GEMM reading W in its forward layout as an MN-major operand
- * (no transposed weight copy).  N % 64 == 0 (32 for BF16x3), K % 256 == 0. */
-/* d(qkv) [M,3C] of the attention core softmax(q k^T d^-1/2) v for a given d(out) [M,C] (fp32 in/out on the device):
- * flash-style tcgen05 backward in bf16 single-pass arithmetic (attn_bwd_tc.cuh). */
-int mb_test_attention_backward_scratch_bytes(int B, int F, int J, int C, size_t* bytes);
-int mb_test_attention_backward(int temporal, int B, int F, int J, int C, int H, const float* qkv, const float* dO,
-                               float* dqkv, void* scratch, size_t scratch_bytes, void* stream);
-int mb_test_dgrad_scratch_bytes(int M, int N, int K, size_t* bytes);
-int mb_test_dgrad(int math, int M, int N, int K, const float* G, const float* W, float* dX, void* scratch,
-                  size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmotionbert_b200.so")
+TEST_LIB_PATH = os.path.join(HERE, "libmotionbert_b200_test.so")     # tests only: + reference kernels and hooks
 
 MB_MATH_BF16X3 = 0
 MB_MATH_BF16 = 1
@@ -18,16 +19,17 @@ MB_FLAG_REF_GEMM = 0x1
 MB_FLAG_REF_ATTN_T = 0x2
 MB_FLAG_GEMM_1CTA = 0x4
 MB_FLAG_REF_ATTN_S = 0x8
-MB_FLAG_ATTN_T_V2 = 0x10
 MB_FLAG_ATTN_T_UNPACKED = 0x20
 MB_FLAG_ATTN_BF16X3 = 0x40
 
-# every symbol include/motionbert_b200.h declares
+# every symbol include/motionbert_b200.h declares (TEST_EXPORTS: include/motionbert_b200_test.h, test library only)
 EXPORTS = [
     "mb_version", "mb_last_error", "mb_create", "mb_destroy", "mb_param_count", "mb_param_info",
     "mb_packed_bytes", "mb_pack_weights", "mb_workspace_bytes", "mb_forward", "mb_workspace_bytes_host",
     "mb_forward_host", "mb_forward_pooled", "mb_forward_launch_count", "mb_profile_enable", "mb_profile_read",
     "mb_saved_bytes", "mb_forward_train", "mb_backward_workspace_bytes", "mb_backward", "mb_backward_launch_count", "mb_pretrain_loss", "mb_augment2d", "mb_adamw_step",
+]
+TEST_EXPORTS = [
     "mb_test_linear_scratch_bytes", "mb_test_linear",
     "mb_test_attention_scratch_bytes", "mb_test_attention", "mb_test_wgrad_scratch_bytes", "mb_test_wgrad",
     "mb_test_dgrad_scratch_bytes", "mb_test_dgrad",
@@ -48,17 +50,30 @@ class MbError(RuntimeError):
 
 
 _lib = None
+_test_lib = None
 
 
 def load() -> C.CDLL:
-    """dlopen the in-tree library; raises if it has not been built (python -m motionbert_b200.build)."""
+    """dlopen the in-tree product library; raises if it has not been built (python -m motionbert_b200.build)."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise MbError(f"{LIB_PATH} is missing: build it with `python -m motionbert_b200.build` "
+    if _lib is None:
+        _lib = _open(LIB_PATH, test=False)
+    return _lib
+
+
+def load_test() -> C.CDLL:
+    """dlopen the test twin (product ABI + reference kernels + kernel-level hooks).  tests/ only."""
+    global _test_lib
+    if _test_lib is None:
+        _test_lib = _open(TEST_LIB_PATH, test=True)
+    return _test_lib
+
+
+def _open(path: str, test: bool) -> C.CDLL:
+    if not os.path.exists(path):
+        raise MbError(f"{path} is missing: build it with `python -m motionbert_b200.build` "
                       "(there is no CPU / PyTorch fallback for the DSTformer hot path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, u32, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
     fp = C.c_void_p   # device / host float* passed as raw addresses
     lib.mb_version.restype = i32
@@ -89,6 +104,18 @@ def load() -> C.CDLL:
                                  f32, f32, fp, fp, f32, f32, fp, vp]
     lib.mb_adamw_step.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_char_p, i32, f32, f32, f32,
                                   f32, f32, vp]
+    if test:
+        _bind_hooks(lib)
+    for name in EXPORTS + (TEST_EXPORTS if test else []):
+        fn = getattr(lib, name)
+        if name not in ("mb_last_error", "mb_destroy"):
+            fn.restype = C.c_int
+    return lib
+
+
+def _bind_hooks(lib):
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    fp = C.c_void_p
     lib.mb_test_linear_scratch_bytes.argtypes = [i32, i32, i32, C.POINTER(sz)]
     lib.mb_test_linear.argtypes = [i32, i32, i32, i32, i32, i32, fp, fp, fp, fp, fp, fp, C.c_float, fp, fp, vp, sz, vp]
     lib.mb_test_attention_scratch_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
@@ -99,16 +126,11 @@ def load() -> C.CDLL:
     lib.mb_test_dgrad.argtypes = [i32, i32, i32, i32, fp, fp, fp, vp, sz, vp]
     lib.mb_test_attention_backward_scratch_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
     lib.mb_test_attention_backward.argtypes = [i32, i32, i32, i32, i32, i32, fp, fp, fp, vp, sz, vp]
-    for name in EXPORTS:
-        fn = getattr(lib, name)
-        if name not in ("mb_last_error", "mb_destroy"):
-            fn.restype = i32
-    _lib = lib
-    return lib
 
 
-def check(rc: int, what: str = "") -> int:
+def check(rc: int, what: str = "", lib: "C.CDLL | None" = None) -> int:
+    """Raise MbError with the library's thread-local message on a negative status (`lib`: the library that returned it)."""
     if rc < 0:
-        msg = load().mb_last_error().decode("utf-8", "replace")
+        msg = (lib or load()).mb_last_error().decode("utf-8", "replace")
         raise MbError(f"{what or 'libmotionbert_b200'} failed ({rc}): {msg}")
     return rc

@@ -124,6 +124,7 @@ __device__ __forceinline__ void ln_row_stats(const float* __restrict__ st, int n
     rstd = 1.0f / sqrtf(m2_a / dim + eps);
 }
 
+#ifdef MB_TEST_KERNELS   // first-generation 1-CTA kernel: kept for tests (libmotionbert_b200_test.so) only
 template <int PASSES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,   // 3D (K, M, plane), box (BK, 128, PLANES)
@@ -372,5 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,   // 3D (K, M, plane), b
         tmem_dealloc<512>(tmem_base);
     }
 }
+
+#endif  // MB_TEST_KERNELS
 
 }  // namespace mb

@@ -19,7 +19,6 @@
 #include "attn_s_tc.cuh"
 #include "attn_t_f16c.cuh"
 #include "attn_t_tc.cuh"
-#include "attn_t_tc2.cuh"
 #include "backward_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
@@ -183,12 +182,14 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         if (d.cc_major != 10)
             return fail(MB_ERR_ARCH, "device %d is compute capability %d.x; this library is sm_100a only (no fallback)",
                         dev, d.cc_major);
+#ifdef MB_TEST_KERNELS
 #define SET_GEMM(P, E) CUDA_TRY(set_smem(gemm_tc_kernel<P, E>, GemmCfg<P>::SMEM_BYTES))
         SET_GEMM(3, EPI_LN_SPLIT); SET_GEMM(3, EPI_LN_GELU_SPLIT); SET_GEMM(3, EPI_RESID);
         SET_GEMM(3, EPI_LN_TANH_F32); SET_GEMM(3, EPI_BIAS_F32);
         SET_GEMM(1, EPI_LN_SPLIT); SET_GEMM(1, EPI_LN_GELU_SPLIT); SET_GEMM(1, EPI_RESID);
         SET_GEMM(1, EPI_LN_TANH_F32); SET_GEMM(1, EPI_BIAS_F32);
 #undef SET_GEMM
+#endif
 #define SET_GEMM2(P, E) CUDA_TRY(set_smem(gemm2_kernel<P, E>, Gemm2Cfg<P, E>::SMEM_BYTES))
         SET_GEMM2(3, EPI_LN_SPLIT); SET_GEMM2(3, EPI_LN_GELU_SPLIT); SET_GEMM2(3, EPI_RESID);
         SET_GEMM2(3, EPI_LN_TANH_F32); SET_GEMM2(3, EPI_BIAS_F32);
@@ -224,10 +225,6 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(attn_bwd_kv_kernel<32, true>, AttnBwdCfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<3>, WgradCfg<3>::SMEM_BYTES));
         CUDA_TRY(set_smem(wgrad_kernel<1>, WgradCfg<1>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_t2_kernel<64, 3>, Attn2Cfg<64, 3>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_t2_kernel<32, 3>, Attn2Cfg<32, 3>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_t2_kernel<64, 1>, Attn2Cfg<64, 1>::SMEM_BYTES));
-        CUDA_TRY(set_smem(attn_t2_kernel<32, 1>, Attn2Cfg<32, 1>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 3>, AttnCfg<64, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<32, 3>, AttnCfg<32, 3>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_t_tc_kernel<64, 1>, AttnCfg<64, 1>::SMEM_BYTES));
@@ -243,10 +240,12 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(attn_s16_kernel<64, true>, AttnS16Cfg<64>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_s16_kernel<32, false>, AttnS16Cfg<32>::SMEM_BYTES));
         CUDA_TRY(set_smem(attn_s16_kernel<32, true>, AttnS16Cfg<32>::SMEM_BYTES));
+#ifdef MB_TEST_KERNELS
         CUDA_TRY(set_smem(attn_s_kernel<64>, 200 * 1024));
         CUDA_TRY(set_smem(attn_s_kernel<32>, 200 * 1024));
         CUDA_TRY(set_smem(attn_t_ref_kernel<64>, 200 * 1024));
         CUDA_TRY(set_smem(attn_t_ref_kernel<32>, 200 * 1024));
+#endif
         d.attrs_set = true;
     }
     *dev_out = dev;
@@ -782,6 +781,10 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
                      : EPI == EPI_RESID ? PC_GEMM_RESID : PC_GEMM_TAIL);
     if (passes == 2 && (flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA)))
         return fail(MB_ERR_INVALID, "the CUDA-core / 1-CTA test GEMMs exist for the bf16 modes only (math mode F16C)");
+#ifndef MB_TEST_KERNELS
+    if (flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA))
+        return fail(MB_ERR_INVALID, "the CUDA-core / 1-CTA test GEMMs live in libmotionbert_b200_test.so");
+#else
     if constexpr (EPI <= EPI_BIAS_F32) {      // the CUDA-core / first-generation test GEMMs know the five forward epilogues
     if (flags & MB_FLAG_REF_GEMM) {
         const long warps = static_cast<long>(p.M) * (p.N / STATS_GROUP);
@@ -803,6 +806,7 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
         return MB_OK;
     }
     }
+#endif
     // production path: CTA pairs (cluster 2x1), one pair per 256x256 tile, persistent
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int max_pairs = e->dev.sms / 2;
@@ -837,7 +841,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     // F16C mode + MB_FLAG_ATTN_BF16X3 (test / A-B only): qkv arrives as bf16 hi/lo planes, the BF16x3 kernels run, the
     // output leaves as F16C rows
     const int passes = f16c ? 3 : passes_of(d);
-    if (f16c && (flags & (MB_FLAG_REF_ATTN_S | MB_FLAG_REF_ATTN_T | MB_FLAG_ATTN_T_V2)))
+    if (f16c && (flags & (MB_FLAG_REF_ATTN_S | MB_FLAG_REF_ATTN_T)))
         return fail(MB_ERR_INVALID, "the CUDA-core / experimental test attention kernels exist for the bf16 modes only");
     const float scale = d.qk_scale > 0.f ? d.qk_scale : 1.0f / sqrtf(static_cast<float>(hd));   // DSTformer.py:94
     if (f16c && !(flags & MB_FLAG_ATTN_BF16X3)) {
@@ -878,6 +882,10 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     __nv_bfloat16* o_hi = P.ao;
     __nv_bfloat16* o_lo = passes == 3 ? P.ao + ao_plane_el : nullptr;
     prof_mark(e, st, temporal ? PC_ATTN_T : PC_ATTN_S);
+#ifndef MB_TEST_KERNELS
+    if (flags & (MB_FLAG_REF_ATTN_S | MB_FLAG_REF_ATTN_T))
+        return fail(MB_ERR_INVALID, "the CUDA-core test attention kernels live in libmotionbert_b200_test.so");
+#else
     if (!temporal && (flags & MB_FLAG_REF_ATTN_S)) {
         const size_t smem = static_cast<size_t>(J) * 3 * C * 4;
         if (hd == 64) attn_s_kernel<64><<<B * F, 256, smem, st>>>(q_hi, q_lo, B * F, J, C, H, scale, o_hi, o_lo);
@@ -885,6 +893,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
         LAUNCH_CHECK("attn_s_kernel");
         return MB_OK;
     }
+#endif
     if (!temporal) {
         AttnSParams sp;
         sp.nseq = B * F; sp.L = J; sp.F = F; sp.J = J; sp.C = C; sp.H = H;
@@ -901,7 +910,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
         LAUNCH_CHECK("attn_s_tc_kernel");
         return MB_OK;
     }
-    if (F <= ATS_SLAB && !(flags & (MB_FLAG_REF_ATTN_T | MB_FLAG_ATTN_T_V2 | MB_FLAG_ATTN_T_UNPACKED))) {
+    if (F <= ATS_SLAB && !(flags & (MB_FLAG_REF_ATTN_T | MB_FLAG_ATTN_T_UNPACKED))) {
         // short clips: four (batch, joint) sequences per 128-row tile (same kernel as the spatial attention)
         AttnSParams sp;
         sp.nseq = B * J; sp.L = F; sp.F = F; sp.J = J; sp.C = C; sp.H = H;
@@ -918,6 +927,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
         LAUNCH_CHECK("attn_s_tc_kernel<temporal-packed>");
         return MB_OK;
     }
+#ifdef MB_TEST_KERNELS
     if (flags & MB_FLAG_REF_ATTN_T) {
         const size_t smem = static_cast<size_t>(F) * hd * 2 * 4;
         if (hd == 64) attn_t_ref_kernel<64><<<B * J * H, 128, smem, st>>>(q_hi, q_lo, B, F, J, C, H, scale, o_hi, o_lo);
@@ -925,6 +935,7 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
         LAUNCH_CHECK("attn_t_ref_kernel");
         return MB_OK;
     }
+#endif
     AttnTParams ap;
     ap.B = B; ap.F = F; ap.J = J; ap.C = C; ap.H = H;
     ap.NK = (F + 15) / 16 * 16;
@@ -934,14 +945,6 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
     ap.out_f16c = f16c ? 1 : 0;
     const int prob = B * J * H;
     const int grid = prob < e->dev.sms ? prob : e->dev.sms;
-    if (flags & MB_FLAG_ATTN_T_V2) {
-        if (hd == 64 && passes == 3) attn_t2_kernel<64, 3><<<grid, ATT_THREADS, Attn2Cfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
-        else if (hd == 32 && passes == 3) attn_t2_kernel<32, 3><<<grid, ATT_THREADS, Attn2Cfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
-        else if (hd == 64) attn_t2_kernel<64, 1><<<grid, ATT_THREADS, Attn2Cfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
-        else attn_t2_kernel<32, 1><<<grid, ATT_THREADS, Attn2Cfg<32, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
-        LAUNCH_CHECK("attn_t2_kernel");
-        return MB_OK;
-    }
     if (hd == 64 && passes == 3) attn_t_tc_kernel<64, 3><<<grid, ATT_T_THREADS, AttnCfg<64, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
     else if (hd == 32 && passes == 3) attn_t_tc_kernel<32, 3><<<grid, ATT_T_THREADS, AttnCfg<32, 3>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
     else if (hd == 64) attn_t_tc_kernel<64, 1><<<grid, ATT_T_THREADS, AttnCfg<64, 1>::SMEM_BYTES, st>>>(P.tm_q, P.tm_kv, ap);
@@ -1301,6 +1304,7 @@ extern "C" int mb_forward_host(MbEncoder* enc, const void* packed, const float* 
     return MB_OK;
 }
 
+#ifdef MB_TEST_KERNELS   // ---- everything down to the matching #endif exists in libmotionbert_b200_test.so only
 // ------------------------------------------------------------------------------------ test hooks
 __global__ void merge_planes_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* y, size_t n) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1557,7 +1561,7 @@ extern "C" int mb_test_attention(int temporal, int math, int use_ref, int B, int
         const uint32_t box_t32[5] = {static_cast<uint32_t>(hd), 1, ATS_SLAB, 1, 1};
         if ((rc = make_tmap(&P.tm_qkv_t32, P.qkv, 5, dims, str, box_t32, hd * 2))) return rc;
     }
-    rc = launch_attn(&e, use_ref == 3 ? MB_FLAG_ATTN_T_UNPACKED : use_ref == 1 ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : use_ref == 2 ? MB_FLAG_ATTN_T_V2 : 0u,
+    rc = launch_attn(&e, use_ref == 3 ? MB_FLAG_ATTN_T_UNPACKED : use_ref == 1 ? (MB_FLAG_REF_ATTN_T | MB_FLAG_REF_ATTN_S) : 0u,
                      temporal != 0, P, B, F, qkv_plane / 2, ao_plane / 2, st);
     if (rc) return rc;
     const size_t n = M * C;
@@ -1695,6 +1699,8 @@ extern "C" int mb_test_dgrad(int math, int M, int N, int K, const float* G, cons
 }
 
 
+#endif  // MB_TEST_KERNELS
+
 // Attention-core backward launcher: all tensors bf16 (single plane), token-major.  For the spatial attention pass
 // (B*F, J, 1) as (B, F, J): one "sequence" per frame, J rows, token stride 1.
 static int launch_attn_bwd(const DevInfo& dev, int B, int F, int J, int C, int H, float scale, const __nv_bfloat16* qkv,
@@ -1752,6 +1758,7 @@ static size_t attn_bwd_stat_floats(size_t B, size_t F, size_t J, size_t H) {
     return a > b ? a : b;
 }
 
+#ifdef MB_TEST_KERNELS
 extern "C" int mb_test_attention_backward_scratch_bytes(int B, int F, int J, int C, size_t* bytes) {
     if (!bytes) return fail(MB_ERR_NULL, "NULL argument");
     const size_t M = static_cast<size_t>(B) * F * J;
@@ -1830,6 +1837,8 @@ extern "C" int mb_test_attention_backward(int temporal, int B, int F, int J, int
     return MB_OK;
 }
 
+
+#endif  // MB_TEST_KERNELS
 
 // ==================================================================================== training path (row a15)
 // mb_forward_train = the inference forward, with every residual-stream tensor kept in the caller's `saved` region.

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
     emit_row<NV, F16C>(v, nv, row, C, nullptr, hi, lo, stats);
 }
 
+#ifdef MB_TEST_KERNELS   // CUDA-core bring-up / reference kernels: libmotionbert_b200_test.so only
 // ---------------------------------------------------------------------------------------------
 // Spatial attention (DSTformer.py:178-186): per (frame, head) softmax(q k^T d^-1/2) v over J joints.
 // One CTA per frame, one warp per head (looped), lane i < J owns query row i: q row and the output
@@ -475,5 +476,7 @@ __global__ void __launch_bounds__(256) gemm_ref_kernel(const __nv_bfloat16* __re
         }
     }
 }
+
+#endif  // MB_TEST_KERNELS
 
 }  // namespace mb

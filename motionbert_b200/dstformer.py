@@ -75,6 +75,7 @@ class _DeviceState:
 
     def __init__(self):
         self.handle = None
+        self.lib = None
         self.packed = None
         self.pack_key = None
         self.workspaces = {}
@@ -85,7 +86,7 @@ class _DeviceState:
     def __del__(self):
         try:
             if self.handle is not None:
-                _lib.load().mb_destroy(self.handle)
+                self.lib.mb_destroy(self.handle)
         except Exception:
             pass
 
@@ -149,6 +150,7 @@ class DSTformer(nn.Module):
         self.math_mode = _lib.MB_MATH_F16C
         self.train_math_mode = _lib.MB_MATH_BF16X3
         self._kernel_flags = 0
+        self._lib_loader = _lib.load               # tests may switch to the test twin (use_test_library)
         # shared (by reference) between nn.DataParallel replicas: keyed by device index
         self._dev_state = {}
         self._grad_sync = None                     # enable_gradient_allreduce(): {'group', 'world'}
@@ -194,6 +196,13 @@ class DSTformer(nn.Module):
         self._dev_state.clear()
         return self
 
+    def use_test_library(self):
+        """TESTS ONLY: route this module through libmotionbert_b200_test.so (same source + the CUDA-core / first-generation
+        reference kernels behind the MB_FLAG_REF_* / MB_FLAG_GEMM_1CTA test flags)."""
+        self._lib_loader = _lib.load_test
+        self._dev_state.clear()
+        return self
+
     def invalidate_packed(self):
         """Force a weight re-pack at the next call.  Needed only after writes that bypass the version counter of the
         parameters (`p.data.copy_()`, EMA through `.data`): the packed-weight cache is keyed by (data_ptr, _version)."""
@@ -231,23 +240,24 @@ class DSTformer(nn.Module):
         st = self._dev_state.get(key)
         if st is None:
             st = _DeviceState()
-            lib = _lib.load()
+            lib = self._lib_loader()
             if not isinstance(self.head, nn.Linear) or self.head.in_features != self.dim_rep:
                 raise NotImplementedError("head must be Linear(dim_rep, dim_out) for the fused tail")
             desc = _lib.MbDesc(self.dim_in, self.dim_out, self.dim_feat, self.dim_rep, self.depth, self.num_heads,
                                self.hidden, self.num_joints, self.maxlen, self.eps,
                                float(self.qk_scale) if self.qk_scale else 0.0, math)
             h = ctypes.c_void_p()
-            _lib.check(lib.mb_create(ctypes.byref(desc), ctypes.byref(h)), "mb_create")
+            _lib.check(lib.mb_create(ctypes.byref(desc), ctypes.byref(h)), "mb_create", lib)
             st.handle = h
-            n = _lib.check(lib.mb_param_count(h))
+            st.lib = lib
+            n = _lib.check(lib.mb_param_count(h), "mb_param_count", lib)
             st.numels = []
             for i in range(n):
                 ne = ctypes.c_int64()
-                _lib.check(lib.mb_param_info(h, i, None, 0, ctypes.byref(ne)))
+                _lib.check(lib.mb_param_info(h, i, None, 0, ctypes.byref(ne)), "mb_param_info", lib)
                 st.numels.append(ne.value)
             nb = ctypes.c_size_t()
-            _lib.check(lib.mb_packed_bytes(h, ctypes.byref(nb)))
+            _lib.check(lib.mb_packed_bytes(h, ctypes.byref(nb)), "mb_packed_bytes", lib)
             st.packed = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
             self._dev_state[key] = st
         return st
@@ -268,7 +278,7 @@ class DSTformer(nn.Module):
         key = tuple((p.data_ptr(), p._version) if p is not None else (0, 0) for p in params)
         if key == st.pack_key:
             return
-        lib = _lib.load()
+        lib = self._lib_loader()
         ptrs = (ctypes.c_void_p * len(params))()
         keep = []
         for i, p in enumerate(params):
@@ -288,7 +298,7 @@ class DSTformer(nn.Module):
                 if t.numel() != st.numels[i]:
                     raise RuntimeError(f"parameter {i} has {t.numel()} elements, library expects {st.numels[i]}")
             ptrs[i] = t.data_ptr()
-        _lib.check(lib.mb_pack_weights(st.handle, ptrs, self._aligned_ptr(st.packed), stream_ptr), "mb_pack_weights")
+        _lib.check(lib.mb_pack_weights(st.handle, ptrs, self._aligned_ptr(st.packed), stream_ptr), "mb_pack_weights", lib)
         st.pack_key = key
         st.keep = keep
 
@@ -314,7 +324,7 @@ class DSTformer(nn.Module):
         pooled representation."""
         device = x.device
         B, F, J, _ = x.shape
-        lib = _lib.load()
+        lib = self._lib_loader()
         with torch.cuda.device(device):
             st = self._state_for(device)
             stream_ptr = torch.cuda.current_stream(device).cuda_stream
@@ -322,7 +332,7 @@ class DSTformer(nn.Module):
             ws = st.workspaces.get((B, F))
             if ws is None:
                 nb = ctypes.c_size_t()
-                _lib.check(lib.mb_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_workspace_bytes")
+                _lib.check(lib.mb_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_workspace_bytes", lib)
                 self._evict_workspaces(st)
                 ws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
                 st.workspaces[(B, F)] = ws
@@ -332,7 +342,7 @@ class DSTformer(nn.Module):
                 pool = torch.empty(B, J, self.dim_rep, dtype=torch.float32, device=device)
                 _lib.check(lib.mb_forward_pooled(st.handle, self._aligned_ptr(st.packed), x.data_ptr(), pool.data_ptr(),
                                                  self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags,
-                                                 stream_ptr), "mb_forward_pooled")
+                                                 stream_ptr), "mb_forward_pooled", lib)
                 return pool
             out = torch.empty(B, F, J, self.dim_out, dtype=torch.float32, device=device) if want_out else None
             rep = torch.empty(B, F, J, self.dim_rep, dtype=torch.float32, device=device) if want_rep else None
@@ -340,7 +350,7 @@ class DSTformer(nn.Module):
                 st.handle, self._aligned_ptr(st.packed), x.data_ptr(),
                 out.data_ptr() if out is not None else None, rep.data_ptr() if rep is not None else None,
                 dp_scale.data_ptr() if dp_scale is not None else None,
-                self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr), "mb_forward")
+                self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr), "mb_forward", lib)
         return out, rep
 
     # ------------------------------------------------------------------ training (mb_forward_train / mb_backward)
@@ -365,7 +375,7 @@ class DSTformer(nn.Module):
         """mb_forward_train on the current stream: returns (out, rep, saved) with `saved` the activation region."""
         device = x.device
         B, F, J, _ = x.shape
-        lib = _lib.load()
+        lib = self._lib_loader()
         with torch.cuda.device(device):
             st = self._state_for(device, self.train_math_mode)
             stream_ptr = torch.cuda.current_stream(device).cuda_stream
@@ -373,12 +383,12 @@ class DSTformer(nn.Module):
             ws = st.workspaces.get((B, F))
             if ws is None:
                 nb = ctypes.c_size_t()
-                _lib.check(lib.mb_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_workspace_bytes")
+                _lib.check(lib.mb_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_workspace_bytes", lib)
                 self._evict_workspaces(st)
                 ws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
                 st.workspaces[(B, F)] = ws
             nb = ctypes.c_size_t()
-            _lib.check(lib.mb_saved_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_saved_bytes")
+            _lib.check(lib.mb_saved_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_saved_bytes", lib)
             saved = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)   # one per forward call
             out = torch.empty(B, F, J, self.dim_out, dtype=torch.float32, device=device) if want_out else None
             rep = torch.empty(B, F, J, self.dim_rep, dtype=torch.float32, device=device)
@@ -386,7 +396,7 @@ class DSTformer(nn.Module):
                 st.handle, self._aligned_ptr(st.packed), x.data_ptr(), out.data_ptr() if out is not None else None,
                 rep.data_ptr(), dp_scale.data_ptr() if dp_scale is not None else None, self._aligned_ptr(saved),
                 saved.numel() - 1024, self._aligned_ptr(ws), ws.numel() - 1024, B, F, self._kernel_flags, stream_ptr),
-                "mb_forward_train")
+                "mb_forward_train", lib)
         return out, rep, saved
 
     def _param_phases(self):
@@ -422,7 +432,7 @@ class DSTformer(nn.Module):
         IS DSTformer.py:351) and their gradients land in a scratch tensor that is dropped."""
         device = x.device
         B, F, J, _ = x.shape
-        lib = _lib.load()
+        lib = self._lib_loader()
         real = self._ordered_params()
         st0 = self._state_for(device, self.train_math_mode)
         params = []
@@ -440,7 +450,7 @@ class DSTformer(nn.Module):
             bws = st.workspaces.get(("bwd", B, F))
             if bws is None:
                 nb = ctypes.c_size_t()
-                _lib.check(lib.mb_backward_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_backward_workspace_bytes")
+                _lib.check(lib.mb_backward_workspace_bytes(st.handle, B, F, ctypes.byref(nb)), "mb_backward_workspace_bytes", lib)
                 bws = torch.empty(nb.value + 1024, dtype=torch.uint8, device=device)
                 st.workspaces[("bwd", B, F)] = bws
             # ONE zero-filled flat bucket, laid out phase by phase (tail, depth d-1 ... 0, embed) in the order the backward
@@ -472,7 +482,7 @@ class DSTformer(nn.Module):
                 saved.numel() - 1024, dp_scale.data_ptr() if dp_scale is not None else None,
                 d_out.data_ptr() if d_out is not None else None, d_rep.data_ptr() if d_rep is not None else None, gp,
                 d_x.data_ptr() if d_x is not None else None, self._aligned_ptr(bws), bws.numel() - 1024,
-                B, F, ev_ptrs, stream_ptr), "mb_backward")
+                B, F, ev_ptrs, stream_ptr), "mb_backward", lib)
             if sync is not None:
                 # data-parallel exchange overlapped with the backward: phase k is summed over the ranks on a side stream
                 # as soon as its event fires, while the kernels of phase k+1 keep the SMs busy on the main stream

@@ -37,7 +37,7 @@ class AdamW(torch.optim.AdamW):
         enc = self._encoder
         ordered = enc._ordered_params()
         slot = {id(p): i for i, p in enumerate(ordered) if p is not None}
-        lib = _lib.load()
+        lib = enc._lib_loader()
         stashed = []
         for group in self.param_groups:
             if group.get("amsgrad") or group.get("maximize"):

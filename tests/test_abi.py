@@ -12,10 +12,10 @@ from motionbert_b200 import _lib, build as _build_mod  # noqa: F401
 from motionbert_b200 import build
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "motionbert_b200.h")).read()
+def _declared(header="motionbert_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mb_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(mb_[a-z0-9_]+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")
@@ -26,11 +26,31 @@ def lib():
 
 def test_header_and_binding_agree():
     assert _declared() == sorted(_lib.EXPORTS)
+    assert _declared("motionbert_b200_test.h") == sorted(_lib.TEST_EXPORTS)
 
 
 def test_library_exports_every_declared_symbol(lib):
     for name in _declared():
         assert hasattr(lib, name), name
+
+
+def test_product_library_carries_no_test_code_and_the_test_twin_carries_everything(lib):
+    """libmotionbert_b200.so: production kernels + the ABI of include/motionbert_b200.h only.  The test twin (same source,
+    -DMB_TEST_KERNELS) adds the hooks of include/motionbert_b200_test.h and the reference kernels."""
+    for name in _lib.TEST_EXPORTS:
+        with pytest.raises(AttributeError):
+            getattr(lib, name)
+    tl = _lib.load_test()
+    for name in _lib.EXPORTS + _lib.TEST_EXPORTS:
+        assert hasattr(tl, name), name
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        names = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+        for k in ("gemm_ref_kernel", "gemm_tc_kernel", "attn_t_ref_kernel", "attn_s_kernel", "attn_t2_kernel"):
+            assert k not in names, k
+        assert "gemm2_kernel" in names and "attn_t16_kernel" in names
 
 
 def test_version_and_desc_layout(lib):
@@ -70,5 +90,5 @@ def test_sass_contains_blackwell_instructions():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass and "STTM" in sass
+    assert "UTCHMMA" in sass and "UTCQMMA" in sass and "UTMALDG" in sass and "LDTM" in sass and "STTM" in sass
     assert "HMMA." not in sass.replace("UTCHMMA", "")

@@ -46,7 +46,7 @@ def test_forward_matches_reference_golden_simt_reference_kernels(cuda_device, na
     cfg, P, x, g = load_case(name)
     if x.shape[0] * x.shape[1] > 64:
         pytest.skip("CUDA-core reference GEMM is only run on the small cases")
-    m = build_module(cfg, P, cuda_device).set_math_mode("bf16x3")     # the CUDA-core test kernels read bf16 hi/lo planes
+    m = build_module(cfg, P, cuda_device).use_test_library().set_math_mode("bf16x3")   # CUDA-core kernels: test twin, bf16 planes
     m._kernel_flags = _lib.MB_FLAG_REF_GEMM | _lib.MB_FLAG_REF_ATTN_T | _lib.MB_FLAG_REF_ATTN_S
     out, rep = _run(m, x, cuda_device)
     _check_against_golden(out, rep, g, cfg, name + "/simt")
@@ -63,6 +63,29 @@ def test_forward_matches_reference_golden(cuda_device, name, mode):
     _check_against_golden(out, rep, g, cfg, name + "/" + mode)
 
 
+def test_product_library_rejects_the_test_kernel_flags(cuda_device):
+    """The CUDA-core / first-generation kernels are not in libmotionbert_b200.so: their flags fail loudly, no reroute."""
+    cfg, P, x, g = load_case("lite_b2_f27")
+    m = build_module(cfg, P, cuda_device).set_math_mode("bf16x3")
+    m._kernel_flags = _lib.MB_FLAG_REF_GEMM
+    with pytest.raises(_lib.MbError, match="test"):
+        _run(m, x, cuda_device)
+    m._kernel_flags = _lib.MB_FLAG_REF_ATTN_T
+    with pytest.raises(_lib.MbError, match="test"):
+        _run(m, x, cuda_device)
+
+
+def test_f16c_attention_equals_bf16x3_attention_within_tolerance(cuda_device):
+    """A/B inside the F16C mode: the F16C attention kernels against the BF16x3 attention kernels fed with bf16 planes."""
+    cfg, P, x, g = load_case("base_b2_f130")
+    m = build_module(cfg, P, cuda_device)
+    o1, r1 = _run(m, x, cuda_device)
+    m._kernel_flags = _lib.MB_FLAG_ATTN_BF16X3
+    o2, r2 = _run(m, x, cuda_device)
+    assert rel_token_err(r1, r2)[1] < 5e-4
+    _check_against_golden(o2, r2, g, cfg, "base_b2_f130/f16c+bf16x3-attention")
+
+
 def test_default_math_mode_is_f16c_for_inference_and_bf16x3_for_gradients(cuda_device):
     cfg, P, x, g = load_case("lite_b2_f27")
     m = build_module(cfg, P, cuda_device)
@@ -73,7 +96,7 @@ def test_default_math_mode_is_f16c_for_inference_and_bf16x3_for_gradients(cuda_d
 
 def test_forward_first_generation_1cta_gemm_still_matches(cuda_device):
     cfg, P, x, g = load_case("base_b2_f27")
-    m = build_module(cfg, P, cuda_device).set_math_mode("bf16x3")
+    m = build_module(cfg, P, cuda_device).use_test_library().set_math_mode("bf16x3")
     m._kernel_flags = _lib.MB_FLAG_GEMM_1CTA
     out, rep = _run(m, x, cuda_device)
     _check_against_golden(out, rep, g, cfg, "base_b2_f27/1cta")
