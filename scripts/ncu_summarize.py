@@ -59,7 +59,9 @@ for part in ("gemm", "attn", "fuse"):
         if k.get("time_us"):
             k["dram_GBps"] = k["dram_bytes"] / k["time_us"] / 1e3
         out["kernels"].append(k)
-gem = [k for k in out["kernels"] if "gemm2_kernel<3, " in k["kernel"] or "gemm2_kernel<1, " in k["kernel"]]
+math = sys.argv[2] if len(sys.argv) > 2 else "f16c"
+out["math"] = math
+gem = [k for k in out["kernels"] if "gemm2_kernel<" in k["kernel"]]
 if gem:
     out["gemm_avg_dram_bytes_per_launch"] = sum(k["dram_bytes"] for k in gem) / len(gem)
     out["gemm_traffic_note"] = ("mean of dram__bytes_read.sum + dram__bytes_write.sum over one captured launch of each "

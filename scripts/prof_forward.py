@@ -13,7 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="base")
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--frames", type=int, default=243)
-ap.add_argument("--math", default="bf16x3")
+ap.add_argument("--math", default="f16c")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 m = build_model(a.model, dev, a.math)
