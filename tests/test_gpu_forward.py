@@ -267,6 +267,31 @@ def test_data_parallel_wrapper_two_gpus():
     assert O.mpjpe(out.astype(np.float64), g["out64"]) < MPJPE_UNITS
 
 
+def test_data_parallel_training_backward_two_gpus():
+    """train.py:256-258 + :205: the backbone wrapped in nn.DataParallel must TRAIN -- replicas keep their parameters as
+    plain attributes (`_parameters` is empty), so the needs-gradient decision goes through `_ordered_params()`; the
+    gradients reduced onto device 0 must equal the single-device gradients of the same global batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg, P, x, g = load_case("lite_b5_f30")
+    dev0 = torch.device("cuda:0")
+    xt = torch.from_numpy(x[:4]).to(dev0)
+    w = torch.randn(4, 30, 17, 3, generator=torch.Generator().manual_seed(3)).to(dev0)
+    m = build_module(cfg, P, dev0).train()
+    (m(xt) * w).sum().backward()
+    single = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    out = dp(xt)
+    assert out.requires_grad
+    (out * w).sum().backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None, n
+        den = float(single[n].norm())
+        if den > 0 and not n.startswith("ts_attn."):
+            assert float((p.grad - single[n]).norm()) / den < 2e-2, n      # bf16 backward, different batch split
+
+
 def test_input_variants_noncontiguous_strided_and_double(cuda_device):
     """Callers hand over slices / permuted views (train.py:160-172 builds batch_input on the fly); the module must
     accept any strided float tensor and produce a fresh contiguous writable result."""
