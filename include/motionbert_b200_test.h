@@ -24,6 +24,9 @@ int mb_test_linear(int mode, int math, int use_ref /* 0: 2-CTA tcgen05 (product)
                    const float* bias, const float* gamma, const float* beta, const float* resid, float eps,
                    float* y, float* stats_out, void* scratch, size_t scratch_bytes, void* stream);
 
+/* The F16C operand encoder (ptx.cuh) on its own: x fp32 [rows][cols] (cols % 32 == 0) -> out [rows][cols * 4] bytes. */
+int mb_test_f16c_encode(const float* x, int rows, int cols, void* out, void* stream);
+
 /* Attention over a fp32 qkv buffer [B*F*J, 3C] -> y fp32 [B*F*J, C].  temporal=1: forward_temporal
  * (DSTformer.py:188-200), 0: forward_spatial (:178-186). */
 int mb_test_attention_scratch_bytes(int B, int F, int J, int C, size_t* bytes);

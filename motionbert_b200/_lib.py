@@ -35,7 +35,7 @@ TEST_EXPORTS = [
     "mb_test_linear_scratch_bytes", "mb_test_linear",
     "mb_test_attention_scratch_bytes", "mb_test_attention", "mb_test_wgrad_scratch_bytes", "mb_test_wgrad",
     "mb_test_dgrad_scratch_bytes", "mb_test_dgrad",
-    "mb_test_attention_backward_scratch_bytes", "mb_test_attention_backward",
+    "mb_test_attention_backward_scratch_bytes", "mb_test_attention_backward", "mb_test_f16c_encode",
 ]
 
 
@@ -118,6 +118,7 @@ def _open(path: str, test: bool) -> C.CDLL:
 def _bind_hooks(lib):
     vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
     fp = C.c_void_p
+    lib.mb_test_f16c_encode.argtypes = [fp, i32, i32, vp, vp]
     lib.mb_test_linear_scratch_bytes.argtypes = [i32, i32, i32, C.POINTER(sz)]
     lib.mb_test_linear.argtypes = [i32, i32, i32, i32, i32, i32, fp, fp, fp, fp, fp, fp, C.c_float, fp, fp, vp, sz, vp]
     lib.mb_test_attention_scratch_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]

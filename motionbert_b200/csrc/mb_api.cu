@@ -1371,6 +1371,17 @@ __global__ void merge_f16c_kernel(const uint8_t* rows, float* y, int M, int N) {
     }
 }
 
+// F16C encoder on its own (tests check the bytes against oracle/f16c_format.py): x fp32 [rows][cols] -> out [rows][cols*4]
+extern "C" int mb_test_f16c_encode(const float* x, int rows, int cols, void* out, void* stream_) {
+    if (!x || !out) return fail(MB_ERR_NULL, "NULL argument");
+    if (rows < 1 || cols < 32 || cols % 32) return fail(MB_ERR_INVALID, "cols must be a positive multiple of 32");
+    const size_t n2 = static_cast<size_t>(rows) * cols / 2;
+    split_flat_f16c_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        x, static_cast<uint8_t*>(out), n2);
+    LAUNCH_CHECK("split_flat_f16c_kernel");
+    return MB_OK;
+}
+
 struct LinScratch {
     size_t a_hi, a_lo, a_st, w_hi, w_lo, vc, vs, o_hi, o_lo, total;
 };

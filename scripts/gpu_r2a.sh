@@ -8,7 +8,7 @@ run() { local name=$1; shift; local to=$1; shift
   timeout "$to" "$@" >> gpurun_out/$name.log 2>&1
   echo "=== $name exit $?" | tee -a gpurun_out/$name.log; }
 PT="python -m pytest -q -p no:cacheprovider --timeout 600 -m gpu"
-run a_f16c   600 $PT tests/test_gpu_kernels.py -k "linear_f16c" -s
+run a_f16c   600 $PT tests/test_gpu_kernels.py -k "f16c and not attention" -s
 run a_attn16 600 $PT tests/test_gpu_kernels.py -k "attention_f16c" -s
 run a_gold   900 $PT tests/test_gpu_forward.py -k "golden and not simt" -s
 run a_bench_f16c 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline

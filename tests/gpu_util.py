@@ -93,3 +93,15 @@ def test_attention_backward(temporal, qkv, dO, B, F, J, C, H):
                                                   dqkv.data_ptr(), sp, nb.value, st), "mb_test_attention_backward", lib)
         torch.cuda.synchronize(dev)
     return dqkv
+
+
+def f16c_encode(x):
+    """The kernels' F16C encoder: fp32 [rows, cols] -> uint8 [rows, cols * 4]."""
+    lib = _lib.load_test()
+    rows, cols = x.shape
+    out = torch.empty(rows, cols * 4, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mb_test_f16c_encode(x.contiguous().data_ptr(), rows, cols, out.data_ptr(),
+                                           torch.cuda.current_stream(x.device).cuda_stream), "mb_test_f16c_encode", lib)
+        torch.cuda.synchronize(x.device)
+    return out

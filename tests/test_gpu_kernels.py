@@ -87,6 +87,36 @@ def test_linear_f16c(cuda_device, M, N, K, mode):
         assert float((var_g - e.var(-1, unbiased=False)).abs().max()) < 2e-3
 
 
+def test_f16c_encoder_bytes_match_the_reference_encoder(cuda_device):
+    """The device encoder (split2_f16c) against oracle/f16c_format.py, bit for bit: f16 round-to-nearest, e5m2 residual
+    x 2^6 and e5m2 of h x 2^-6, block layout [32 f16 | 32 lo8 | 32 hi8]."""
+    from oracle import f16c_format as F16
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(257, 96, generator=g) * torch.logspace(-6, 2, 96)).to(cuda_device)
+    got = G.f16c_encode(x)
+    exp = F16.encode_rows(x)
+    assert got.shape == exp.shape
+    bad = (got != exp).nonzero()
+    assert bad.numel() == 0, f"{bad.shape[0]} differing bytes, first at {bad[0].tolist()}"
+    assert float((F16.decode_rows(got, 96) - x).abs().max() / x.abs().max()) < 2 ** -12
+
+
+@pytest.mark.parametrize("mode", [4, 2], ids=["bias", "resid"])
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 512), (77, 512, 1024), (4131, 1024, 512)])
+def test_linear_f16c_matches_its_own_arithmetic(cuda_device, M, N, K, mode):
+    """Tight check of the MMA wiring: the kernel against ah.wh + q(al 2^6) q(wh 2^-6) + q(ah 2^-6) q(wl 2^6) evaluated in
+    float64 on the same encoded operands (oracle/f16c_format.py).  Only fp32 accumulation separates the two (~1e-6); a
+    mis-paired K-slice or a wrong operand format would show up at 1e-4 ... 1."""
+    from oracle import f16c_format as F16
+    A, W, b, gamma, beta, resid = _mk(M, N, K, cuda_device, seed=M + N + K + mode)
+    y, _ = G.test_linear(mode, A, W, b, gamma, beta, resid, 1e-6, math=2, use_ref=0)
+    exp = F16.matmul(A, W) + b.double()
+    if mode == 2:
+        exp = exp + resid.double()
+    rel, mx = _rel(y, exp)
+    assert rel < 3e-6, f"rel {rel:.3e} max {mx:.3e}"
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 512), (77, 512, 1024)])
 @pytest.mark.parametrize("mode", [4, 0, 2])
 def test_linear_bf16_single_pass(cuda_device, M, N, K, mode):
