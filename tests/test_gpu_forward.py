@@ -187,9 +187,13 @@ def test_drop_path_training_matches_torch_recompute(cuda_device):
     dp = m._drop_path_scale(2, 9, x.device)
     assert dp is not None and dp.shape == (40, 18) and float(dp.min()) == 0.0
     with torch.no_grad():
-        out, _ = m._launch(x, True, False, dp)
         exp = recompute_forward(m, x.double(), False, dp.double(), [p.double() for p in m._ordered_params()])
-    assert rel_token_err(out.cpu().numpy(), exp.cpu().numpy())[1] < TOK_REL
+        for mode in ("bf16x3", "f16c"):                      # DropPath lives in the residual epilogue of every arithmetic mode
+            m.set_math_mode(mode)
+            out, _ = m._launch(x, True, False, dp)
+            mean_e, max_e = rel_token_err(out.cpu().numpy(), exp.cpu().numpy())
+            print(f"[drop_path/{mode}] out per-token rel mean {mean_e:.2e} max {max_e:.2e}")
+            assert mean_e < TOK_REL and (mode != "bf16x3" or max_e < TOK_REL)
 
 
 def test_autograd_backward_runs_and_matches_torch(cuda_device):
