@@ -164,8 +164,9 @@ def main():
         out0, rep0 = Emu(cfg, P, "exact", "exact").forward(x)
         print(f"# {which} B={B} F={F} params seed {pseed} scale {scale}: |out| mean joint norm "
               f"{np.linalg.norm(out0, axis=-1).mean():.4f}")
-        for lin, att in (("exact", "f16+e5m2"), ("exact", "f16+e5m2|f16c_pv_ph"), ("exact", "f16+e5m2|f16"),
-                         ("exact", "f16|f16+e5m2"), ("f16+e5m2", "f16+e5m2|f16c_pv_ph")):
+        for lin, att in (("fp32", "fp32"), ("bf16x3", "bf16x3"), ("f16+e5m2", "f16+e5m2"), ("f16+e5m2", "exact"),
+                         ("exact", "f16+e5m2"), ("f16", "f16"), ("f16w2", "f16"), ("exact", "f16"),
+                         ("exact", "f16+e5m2|f16c_pv_ph"), ("bf16", "bf16")):
             out, rep = Emu(cfg, P, lin, att).forward(x)
             tok = np.linalg.norm((rep - rep0).reshape(-1, rep.shape[-1]), axis=-1) / \
                 np.linalg.norm(rep0.reshape(-1, rep.shape[-1]), axis=-1)
