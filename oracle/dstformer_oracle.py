@@ -138,6 +138,16 @@ def make_input(B: int, F: int, J: int = 17, seed: int = 1) -> np.ndarray:
     return x.astype(np.float32)
 
 
+def fixture_out_weight(shape, seed: int) -> np.ndarray:
+    """The seeded weight w of the gradient fixtures' scalar loss sum(y * w) (oracle/make_golden_grads.py)."""
+    return np.random.default_rng(seed).standard_normal(shape)
+
+
+def fixture_sample_idx(n: int, nsample: int = 512) -> np.ndarray:
+    """Evenly spaced flat indices at which the gradient fixtures keep entries of an n-element tensor."""
+    return np.unique(np.linspace(0, n - 1, num=min(nsample, n)).round().astype(np.int64))
+
+
 # --------------------------------------------------------------------------- #
 # forward pieces
 # --------------------------------------------------------------------------- #

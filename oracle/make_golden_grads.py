@@ -42,11 +42,11 @@ CASES = [
 
 
 def sample_idx(n: int) -> np.ndarray:
-    return np.unique(np.linspace(0, n - 1, num=min(NSAMPLE, n)).round().astype(np.int64))
+    return O.fixture_sample_idx(n, NSAMPLE)
 
 
 def out_weight(shape, seed: int) -> np.ndarray:
-    return np.random.default_rng(seed).standard_normal(shape)
+    return O.fixture_out_weight(shape, seed)
 
 
 def ordered_names(cfg) -> "list[str]":

@@ -318,14 +318,13 @@ def test_native_backward_matches_reference_gradient_fixtures(cuda_device, name):
     same perturbed parameters, same clip, loss = sum(y * w) with the fixture's seeded w.  Per tensor: relative L2 error
     over the 512 sampled entries, the norm and the input gradient."""
     from conftest import GOLD, build_module
-    from oracle.make_golden_grads import out_weight
     g = np.load(os.path.join(GOLD, name + ".npz"))
     cfg = O.EncoderConfig(dim_feat=int(g["dim_feat"]), mlp_ratio=float(g["mlp_ratio"]))
     B, F, return_rep = int(g["B"]), int(g["F"]), bool(int(g["return_rep"]))
     m = build_module(cfg, O.make_params(cfg, int(g["param_seed"])), cuda_device).train()
     x = torch.from_numpy(O.make_input(B, F, cfg.num_joints, int(g["input_seed"]))).to(cuda_device).requires_grad_(True)
     y = m.get_representation(x) if return_rep else m(x)
-    w = torch.from_numpy(out_weight(tuple(y.shape), int(g["w_seed"]))).float().to(cuda_device)
+    w = torch.from_numpy(O.fixture_out_weight(tuple(y.shape), int(g["w_seed"]))).float().to(cuda_device)
     loss = (y * w).sum()
     loss.backward()
     assert abs(float(loss.detach()) - float(g["loss"])) < 2e-3 * abs(float(g["loss"])) + 1e-2
