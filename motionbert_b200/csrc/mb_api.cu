@@ -1496,11 +1496,11 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
                 gemm2_kernel<3, E><<<grid2, G2_THREADS, Gemm2Cfg<3, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
             else if (passes == 2)                                                                                    \
                 gemm2_kernel<2, E><<<grid2, G2_THREADS, Gemm2Cfg<2, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
-            else                                                                                                     \
-                gemm2_kernel<1, E><<<grid2, G2_THREADS, Gemm2Cfg<1, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
         } else if (use_ref == 4) {                                                                                   \
             const int units = ((M + 511) / 512) * (N / 256);                                                         \
             launch_cl4<E>(4 * (units < info.sms / 4 ? units : info.sms / 4), st, tmA, tmB2, tmR, tmX, tmS, p);        \
+            else                                                                                                     \
+                gemm2_kernel<1, E><<<grid2, G2_THREADS, Gemm2Cfg<1, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
         } else if (use_ref == 1) {                                                                                   \
             const long warps = static_cast<long>(M) * (N / STATS_GROUP);                                             \
             gemm_ref_kernel<E><<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(a_hi, passes == 3 ? a_lo : nullptr, w_hi, \
