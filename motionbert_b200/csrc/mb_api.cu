@@ -1434,8 +1434,7 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
     auto* o_hi = reinterpret_cast<__nv_bfloat16*>(b + s.o_hi);
     auto* o_lo = reinterpret_cast<__nv_bfloat16*>(b + s.o_lo);
     const int passes = math == MB_MATH_BF16 ? 1 : math == MB_MATH_F16C ? 2 : 3;
-    if (passes == 2 && use_ref != 0 && use_ref != 4) return fail(MB_ERR_INVALID, "F16C: production kernels only (use_ref 0, or 4 = 4-CTA clusters)");
-    if (use_ref == 4 && (passes != 2 || mode == EPI_BIAS_F32)) return fail(MB_ERR_INVALID, "use_ref 4: F16C mode, modes 0..3");
+    if (passes == 2 && use_ref != 0) return fail(MB_ERR_INVALID, "F16C: production kernel only");
     {
         const int C = K;
         const int rows_grid = (M + 7) / 8;
@@ -1482,7 +1481,6 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
             if ((rc = make_f16c_operand_tmap(&tmA, a_hi, M, K, GEMM_BM))) return rc;
             if ((rc = make_f16c_operand_tmap(&tmB2, w_hi, N, K, 128))) return rc;
             if ((rc = make_f16c_store_tmap(&tmS, o_hi, M, N))) return rc;
-            if (use_ref == 4 && (rc = make_f16c_operand_tmap(&tmB2, w_hi, N, K, 64))) return rc;
         }
     }
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
@@ -1496,9 +1494,6 @@ extern "C" int mb_test_linear(int mode, int math, int use_ref, int M, int N, int
                 gemm2_kernel<3, E><<<grid2, G2_THREADS, Gemm2Cfg<3, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
             else if (passes == 2)                                                                                    \
                 gemm2_kernel<2, E><<<grid2, G2_THREADS, Gemm2Cfg<2, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
-        } else if (use_ref == 4) {                                                                                   \
-            const int units = ((M + 511) / 512) * (N / 256);                                                         \
-            launch_cl4<E>(4 * (units < info.sms / 4 ? units : info.sms / 4), st, tmA, tmB2, tmR, tmX, tmS, p);        \
             else                                                                                                     \
                 gemm2_kernel<1, E><<<grid2, G2_THREADS, Gemm2Cfg<1, E>::SMEM_BYTES, st>>>(tmA, tmB2, tmR, tmX, tmS, p); \
         } else if (use_ref == 1) {                                                                                   \

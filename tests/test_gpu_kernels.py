@@ -101,20 +101,6 @@ def test_f16c_encoder_bytes_match_the_reference_encoder(cuda_device):
     assert float((F16.decode_rows(got, 96) - x).abs().max() / x.abs().max()) < 2 ** -12
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["ln_split", "ln_gelu", "resid", "ln_tanh"])
-@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 512), (77, 512, 1024), (4131, 1024, 512), (40000, 512, 512)])
-def test_linear_f16c_4cta_clusters_bit_identical(cuda_device, M, N, K, mode):
-    """gemm2_kernel<.., CL = 4>: two CTA pairs per cluster on vertically adjacent tiles, W tile multicast.  Same MMAs per
-    tile in the same order -> bit-identical to the CTA-pair kernel, for odd tile counts and ragged M as well."""
-    A, W, b, gamma, beta, resid = _mk(M, N, K, cuda_device, seed=M + N + K + mode)
-    y2, s2 = G.test_linear(mode, A, W, b, gamma, beta, resid, 1e-6, math=2, use_ref=0)
-    y4, s4 = G.test_linear(mode, A, W, b, gamma, beta, resid, 1e-6, math=2, use_ref=4)
-    assert torch.isfinite(y4).all()
-    assert torch.equal(y2, y4)
-    if mode == 2:
-        assert torch.equal(s2, s4)
-
-
 @pytest.mark.parametrize("mode", [4, 2], ids=["bias", "resid"])
 @pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 512), (77, 512, 1024), (4131, 1024, 512)])
 def test_linear_f16c_matches_its_own_arithmetic(cuda_device, M, N, K, mode):
