@@ -62,12 +62,8 @@ struct Gemm2Cfg {
 // (64-column SWIZZLE_128B blocks, LBO = block stride) instead of packing a transposed copy of every weight.
 // OUT16C: the split output (tmS) is an F16C row buffer (2-D map, box (64 x 16-bit, 32 rows), SWIZZLE_128B) instead of
 // bf16 hi/lo planes.
-// CL = 4: clusters of TWO CTA pairs working on vertically adjacent 256-row tiles of the SAME 256 output columns: the W
-// tile is shared, so every CTA fetches only HALF of its 128 W rows per stage and multicasts them to the CTA of the same
-// pair rank in the other pair (operand feed from L2: 24 KB instead of 32 KB per CTA per stage -- the F16C mainloop is
-// feed-bound at the 2-CTA shape).  A stage slot is recycled when BOTH pairs have consumed it (empty barrier count 2).
-template <int PASSES, int EPI, bool B_MN = false, int EW = G2_EPI_WARPS, bool OUT16C = (PASSES == 2), int CL = 2>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(g2_threads(EW), 1)
+template <int PASSES, int EPI, bool B_MN = false, int EW = G2_EPI_WARPS, bool OUT16C = (PASSES == 2)>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EW), 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane), box (BK, 128, PLANES)
              const __grid_constant__ CUtensorMap tmB,   // bf16 3D (K, N, plane), box (BK, 128, PLANES); B_MN: (Kf, Nf, plane), box (64, BK, 1)
              const __grid_constant__ CUtensorMap tmR,   // fp32 2D (N, M) residual,    box (32, 32)         [RESID]
@@ -86,8 +82,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     constexpr bool kTwoPlanes = (PASSES == 3 || (PASSES == 2 && !OUT16C)) || (EPI == EPI_BIAS_GELU_PAIR);   // second bf16 plane: lo, or gelu(y)
     static_assert(!(B_MN && PASSES == 2), "the F16C mode has no MN-major weight form (backward runs in bf16)");
     static_assert(!OUT16C || EW == 8, "F16C output: 8 epilogue warps");
-    static_assert(CL == 2 || (CL == 4 && Cfg::PLANES == 1 && !B_MN), "4-CTA clusters: single-plane K-major operands only");
-    constexpr int PPC = CL / 2;                                                     // pairs per cluster
     constexpr bool kDoubleLd = !kResid && EW == 8;                               // register double-buffered tcgen05.ld
     constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32 || EPI == EPI_LN_TANH_POOL);
     constexpr bool kPool = (EPI == EPI_LN_TANH_POOL);
@@ -104,22 +98,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t crank = cluster_ctarank();
-    const uint32_t rank = crank & 1u;                       // rank inside the CTA pair (0 = leader: issues the MMAs)
-    const uint32_t pic = crank >> 1;                        // pair inside the cluster
-    const uint32_t lead = crank & ~1u;                      // cluster rank of my pair's leader
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
 
     const int num_mp = (p.M + 255) / 256;
     const int num_n = p.N / 256;
+    const int num_tiles = num_mp * num_n;
     const int num_kb = p.K / Cfg::BK;
-    // work units: CL == 2: one 256x256 tile per pair; CL == 4: two vertically adjacent tiles (one per pair) per cluster
-    const int pair = (CL == 2) ? (blockIdx.x >> 1) : (blockIdx.x / CL);
-    const int npairs = (CL == 2) ? (gridDim.x >> 1) : (gridDim.x / CL);
-    const int num_tiles = (CL == 2) ? num_mp * num_n : ((num_mp + 1) / 2) * num_n;
-    auto unit_coords = [&](int u, int& m_pair, int& n_idx) {
-        n_idx = u % num_n;
-        m_pair = (CL == 2) ? (u / num_n) : ((u / num_n) * 2 + static_cast<int>(pic));   // may be >= num_mp: all-padding tile
-    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -129,7 +115,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         if (kSplitOut) tma_prefetch_desc(&tmS);
         for (int i = 0; i < G2_STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], PPC);
+            mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -150,23 +136,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += npairs) {
-                int m_pair, n_idx;
-                unit_coords(tile, m_pair, n_idx);
+                const int m_pair = tile / num_n, n_idx = tile % num_n;
                 const int a_row = m_pair * 256 + static_cast<int>(rank) * 128;
                 const int b_row = n_idx * 256 + static_cast<int>(rank) * 128;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sB = sA + Cfg::A_BYTES;
-                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), lead);
+                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                     tma_load_3d_2cta(sA, &tmA, full_leader, kb * Cfg::KSTEP16, a_row, 0);
-                    if (CL == 4) {
-                        // my half of the 128 W rows, to me and to the CTA of my pair rank in the other pair
-                        tma_load_3d_2cta_mc(sB + pic * 64 * Cfg::SWZ, &tmB, smem_u32(&full_bar[stage]) & 0xFEFFFFFFu,
-                                            static_cast<uint16_t>((1u << rank) | (1u << (rank + 2))), kb * Cfg::KSTEP16,
-                                            b_row + static_cast<int>(pic) * 64, 0);
-                    } else if (!B_MN) {
+                    if (!B_MN) {
                         tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::KSTEP16, b_row, 0);
                     } else {
                         // this CTA's 128 output columns = two 64-column blocks of [BK contraction rows][128 B] per plane
@@ -225,8 +205,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                                 umma_ss_2cta(d_tmem, a_hi + koff, b_hi + boff, IDESC, (kb | ks) != 0);
                             }
                         }
-                        tc_commit_2cta(&empty_bar[stage], CL == 4 ? 0xF : 0x3);
-                        if (kb == num_kb - 1) tc_commit_2cta(&tfull_bar[acc], static_cast<uint16_t>(0x3u << (2 * pic)));
+                        tc_commit_2cta(&empty_bar[stage], 3);
+                        if (kb == num_kb - 1) tc_commit_2cta(&tfull_bar[acc], 3);
                     }
                     __syncwarp();
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
@@ -251,8 +231,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3);    // SWIZZLE_64B : chunk16 ^= (row / 2) % 4
 
         auto chunk_coords = [&](int tile, int ch, int& col0, int& rowb) {
-            int m_pair, n_idx;
-            unit_coords(tile, m_pair, n_idx);
+            const int m_pair = tile / num_n, n_idx = tile % num_n;
             col0 = n_idx * 256 + half * COLS_PER_WARP + ch * 32;
             rowb = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32;
         };
@@ -266,8 +245,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair; tile < num_tiles; tile += npairs) {
-            int m_pair, n_idx;
-            unit_coords(tile, m_pair, n_idx);
+            const int m_pair = tile / num_n, n_idx = tile % num_n;
             const int row = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32 + lane;
             const bool row_ok = row < p.M;
 
@@ -467,7 +445,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             }
             // every TMEM read of this accumulator is complete -> release it to the leader's MMA warp
             tc_fence_before();
-            mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), lead));
+            mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
             if (kResid) {
                 if (row_ok && p.stats_out) {
                     float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;

@@ -203,9 +203,6 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_RESID>, Gemm2Cfg<2, EPI_RESID>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_F32>, Gemm2Cfg<2, EPI_LN_TANH_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_BIAS_F32>, Gemm2Cfg<2, EPI_BIAS_F32>::SMEM_BYTES));
-#define SET_CL4(E) CUDA_TRY(set_smem(gemm2_kernel<2, E, false, 8, true, 4>, Gemm2Cfg<2, E>::SMEM_BYTES))
-        SET_CL4(EPI_LN_SPLIT); SET_CL4(EPI_LN_GELU_SPLIT); SET_CL4(EPI_RESID); SET_CL4(EPI_LN_TANH_F32);
-#undef SET_CL4
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_LN_TANH_POOL>, Gemm2Cfg<1, EPI_LN_TANH_POOL>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_POOL>, Gemm2Cfg<2, EPI_LN_TANH_POOL>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<3, EPI_LN_TANH_POOL>, Gemm2Cfg<3, EPI_LN_TANH_POOL>::SMEM_BYTES));
@@ -266,7 +263,6 @@ struct LinearPack {
     size_t off_hi = 0, off_lo = 0, off_c = 0, off_s = 0;   // byte offsets into the packed buffer
     CUtensorMap tmap;                                   // 1-CTA kernel: box rows 256; valid for `packed_ptr`
     CUtensorMap tmap2;                                  // 2-CTA kernel: box rows 128 (half of the W tile per CTA)
-    CUtensorMap tmap2h;                                 // 4-CTA clusters (F16C): box rows 64 (a quarter, multicast to the other pair)
     CUtensorMap tmap_k1;                                // backward recompute: hi plane only, K-major, box (64, 128, 1)
     CUtensorMap tmap_mn;                                // backward dgrad: hi plane as MN-major B, box (64, 64, 1)
 };
@@ -361,7 +357,6 @@ static void prof_mark(const MbEncoder* ce, cudaStream_t st, int cls) {
     ++e->events_used;
 }
 
-static const bool g_default_cl4 = false;    // F16C GEMMs: 4-CTA clusters by default? (A/B via MB_FLAG_GEMM_CL4 / MB_FLAG_GEMM_CL2)
 static int passes_of(const MbDesc& d) { return d.math == MB_MATH_BF16 ? 1 : d.math == MB_MATH_F16C ? 2 : 3; }
 static bool is_f16c(const MbDesc& d) { return d.math == MB_MATH_F16C; }
 
@@ -570,7 +565,6 @@ extern "C" int mb_pack_weights(MbEncoder* enc, const float* const* params, void*
             if (L.off_lo != L.off_hi + static_cast<size_t>(L.N) * L.K * 2) return fail(MB_ERR_INVALID, "internal: packed planes not adjacent");
             int rc = make_f16c_operand_tmap(&L.tmap2, base + L.off_hi, L.N, L.K, 128);
             if (rc) return rc;
-            if ((rc = make_f16c_operand_tmap(&L.tmap2h, base + L.off_hi, L.N, L.K, 64))) return rc;
             continue;
         }
         // hi and lo planes are 1024-aligned but not necessarily adjacent: describe them as 2 planes with the
@@ -773,22 +767,6 @@ struct EpiMaps {
     bool split_bf16 = false;              // F16C mode: out_s is a bf16 hi/lo plane map (not an F16C row map)
 };
 
-// 4-CTA-cluster variant of the F16C GEMM (gemm_tc2.cuh, CL = 4): F16C-row outputs of the four forward epilogues
-template <int EPI>
-static bool use_cl4(const MbEncoder* e, uint32_t flags, const GemmParams& p) {
-    (void)e;
-    constexpr bool has = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_RESID || EPI == EPI_LN_TANH_F32);
-    if (!has || (flags & MB_FLAG_ATTN_BF16X3)) return false;      // (the bf16-plane qkv output exists for CL = 2 only)
-    const bool want = g_default_cl4 ? !(flags & MB_FLAG_GEMM_CL2) : (flags & MB_FLAG_GEMM_CL4) != 0;
-    return want && p.M >= 512;
-}
-template <int EPI>
-static void launch_cl4(int grid, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR,
-                       const CUtensorMap& tmX, const CUtensorMap& tmS, const GemmParams& p) {
-    if constexpr (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_RESID || EPI == EPI_LN_TANH_F32)
-        gemm2_kernel<2, EPI, false, 8, true, 4><<<grid, G2_THREADS, Gemm2Cfg<2, EPI>::SMEM_BYTES, st>>>(tmA, tmB, tmR, tmX, tmS, p);
-}
-
 template <int EPI>
 static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tmA, const __nv_bfloat16* a_hi,
                        const __nv_bfloat16* a_lo, const LinearPack& L, const uint8_t* packed, GemmParams p,
@@ -847,13 +825,7 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
         gemm2_kernel<3, EPI><<<grid, G2_THREADS, Gemm2Cfg<3, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else if (passes == 2 && EPI == EPI_LN_SPLIT && em.split_bf16)      // qkv planes for the bf16x3 attention kernels
         gemm2_kernel<2, EPI, false, 8, false><<<grid, G2_THREADS, Gemm2Cfg<2, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
-    else if (passes == 2 && use_cl4<EPI>(e, flags, p)) {
-        // clusters of two CTA pairs sharing the W tile (multicast): units = 2 vertically adjacent tiles
-        const int units = ((p.M + 511) / 512) * (p.N / 256);
-        const int max_cl = e->dev.sms / 4;
-        const int grid4 = 4 * (units < max_cl ? units : max_cl);
-        launch_cl4<EPI>(grid4, st, tmA, L.tmap2h, tmR, tmX, tmS, p);
-    } else if (passes == 2)
+    else if (passes == 2)
         gemm2_kernel<2, EPI><<<grid, G2_THREADS, Gemm2Cfg<2, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else
         gemm2_kernel<1, EPI, false, EW1><<<grid, g2_threads(EW1), Gemm2Cfg<1, EPI, EW1>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);

@@ -274,17 +274,6 @@ __device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorM
         "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// the same, multicast: the box lands at this smem offset in EVERY CTA of `cta_mask` (cluster ranks); each destination
-// CTA's transaction bytes are signalled on the mbarrier at `mbar` 's offset in the LEADER (even) CTA of that CTA's pair
-// (cta_group::2 convention: pass the local barrier address with the pair bit cleared).
-__device__ __forceinline__ void tma_load_3d_2cta_mc(void* smem_dst, const CUtensorMap* m, uint32_t mbar, uint16_t cta_mask,
-                                                    int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-        "[%0], [%1, {%4, %5, %6}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

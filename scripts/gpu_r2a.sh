@@ -12,9 +12,8 @@ run a_f16c   600 $PT tests/test_gpu_kernels.py -k "f16c and not attention" -s
 run a_attn16 600 $PT tests/test_gpu_kernels.py -k "attention_f16c" -s
 run a_gold   900 $PT tests/test_gpu_forward.py -k "golden and not simt" -s
 run a_bench_f16c 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline
-run a_bench_cl4  600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras --kernel-flags 0x80
-run a_bench_x3   600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras --math bf16x3
+run a_bench_x3   600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --math bf16x3
 run a_fwd    900 $PT tests/test_gpu_forward.py -k "not golden" -s
 run a_misc   900 $PT tests/test_action.py tests/test_optim.py tests/test_augment.py tests/test_gpu_losses_tta.py -s
 run a_bwd    1500 $PT tests/test_gpu_backward.py -s
-for f in a_f16c a_attn16 a_gold a_bench_f16c a_bench_cl4 a_bench_x3 a_fwd a_misc a_bwd; do echo "----- $f"; tail -n ${TAILN:-15} gpurun_out/$f.log; done
+for f in a_f16c a_attn16 a_gold a_bench_f16c a_bench_x3 a_fwd a_misc a_bwd; do echo "----- $f"; tail -n ${TAILN:-15} gpurun_out/$f.log; done

@@ -86,18 +86,6 @@ def test_f16c_attention_equals_bf16x3_attention_within_tolerance(cuda_device):
     _check_against_golden(o2, r2, g, cfg, "base_b2_f130/f16c+bf16x3-attention")
 
 
-@pytest.mark.parametrize("name", ["base_b2_f130", "lite_b5_f30", "base_b1_f243"])
-def test_f16c_gemm_4cta_cluster_variant_is_bit_identical(cuda_device, name):
-    """MB_FLAG_GEMM_CL4: clusters of two CTA pairs sharing the W tile by TMA multicast -- the same MMAs in the same order
-    per output tile, so the result must not change by a single bit (odd numbers of 256-row tiles included)."""
-    cfg, P, x, g = load_case(name)
-    m = build_module(cfg, P, cuda_device)
-    o1, r1 = _run(m, x, cuda_device)
-    m._kernel_flags = _lib.MB_FLAG_GEMM_CL4
-    o2, r2 = _run(m, x, cuda_device)
-    assert np.array_equal(o1, o2) and np.array_equal(r1, r2)
-
-
 def test_default_math_mode_is_f16c_for_inference_and_bf16x3_for_gradients(cuda_device):
     cfg, P, x, g = load_case("lite_b2_f27")
     m = build_module(cfg, P, cuda_device)
