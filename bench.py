@@ -395,6 +395,7 @@ def main():
     ap.add_argument("--frames", type=int, default=243)
     ap.add_argument("--math", default=None, choices=["f16c", "bf16x3", "bf16"],
                     help="default f16c (fp32 parity, 2 pass-equivalents) for forward, bf16 for train (config 3 is a bf16 step)")
+    ap.add_argument("--kernel-flags", type=lambda v: int(v, 0), default=0, help="MB_FLAG_* bits for A/B runs (e.g. 0x40 = BF16x3 attention inside F16C)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline forward only (skip train / lite sweep / eager sub-records)")
     args = ap.parse_args()
@@ -427,6 +428,7 @@ def main():
             dist.destroy_process_group()
         return
     model = build_model(args.model, device, args.math)
+    model._kernel_flags = args.kernel_flags
     cfg = MODELS[args.model]
     hidden = int(cfg["dim_feat"] * cfg["mlp_ratio"])
     B, T = args.batch, args.frames
