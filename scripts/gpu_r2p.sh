@@ -1,15 +1,20 @@
 #!/bin/bash
-# round-2 profiling session: re-run the two fixed test files, test durations, then ncu (launch list + --set full)
+# round-2 profiling session: ncu launch list + --set full captures; only CSV exports come back (reports exceed the 64 MiB cap)
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-run() { local name=$1; shift; local to=$1; shift
-  echo "=== $name: $*" | tee gpurun_out/$name.log
-  timeout "$to" "$@" >> gpurun_out/$name.log 2>&1
-  echo "=== $name exit $?" | tee -a gpurun_out/$name.log; }
-PT="python -m pytest -q -p no:cacheprovider --timeout 600 -m gpu"
-run p_fix   900 $PT tests/test_optim.py tests/test_gpu_backward.py -k "adamw or fixtures or batch8" --durations=8
-run p_dur   900 $PT tests/test_gpu_kernels.py -k "f16c and not attention" --durations=12
-bash scripts/gpu_prof.sh r02a 256
-for f in gemm attn fuse; do ncu -i gpurun_out/r02a_$f.ncu-rep --page raw --csv > gpurun_out/r02a_${f}_raw.csv 2>/dev/null; done
-for f in p_fix p_dur; do echo "----- $f"; tail -n 25 gpurun_out/$f.log; done
+TAG=${1:-r02a}; B=${2:-256}
+NCU="ncu --clock-control none --profile-from-start off"
+timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/${TAG}_launches.csv \
+   python scripts/prof_forward.py --batch $B > gpurun_out/${TAG}_launches.log 2>&1
+cap() {  # name, kernel regex, count
+  timeout 900 $NCU --set full --import-source on -k regex:$2 -c $3 -o /tmp/${TAG}_$1 -f \
+     python scripts/prof_forward.py --batch $B > gpurun_out/${TAG}_$1.log 2>&1
+  ncu -i /tmp/${TAG}_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_$1_raw.csv 2>/dev/null
+  ncu -i /tmp/${TAG}_$1.ncu-rep --page source --csv > gpurun_out/${TAG}_$1_source.csv 2>/dev/null
+  ls -la /tmp/${TAG}_$1.ncu-rep gpurun_out/${TAG}_$1_raw.csv gpurun_out/${TAG}_$1_source.csv
+}
+cap gemm gemm2_kernel 4
+cap attn attn_ 2
+cap fuse fuse_kernel 1
+du -sh gpurun_out; tail -n 3 gpurun_out/${TAG}_gemm.log gpurun_out/${TAG}_attn.log
