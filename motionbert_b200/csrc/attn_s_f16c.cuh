@@ -31,6 +31,36 @@ struct AttnS16Cfg {
     static constexpr int TMEM_SET = 192;                       // S/P 128 columns + O 64 columns per problem
 };
 
+// softmax of one row of <= 32 scores (thread = row): probabilities as F16C pieces, returns the row sum.
+// LC > 0: row length known at compile time (J = 17 joints: the 15 padding columns cost no exponentials, no compares).
+template <int LC>
+__device__ __forceinline__ float softmax32_f16c(const uint32_t (&r)[32], int L, float sl2, uint32_t (&hh)[16],
+                                                uint32_t (&l8)[8], uint32_t (&g8)[8]) {
+    const int n = LC > 0 ? LC : L;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < n) mx = fmaxf(mx, __uint_as_float(r[k]));
+    const float mxs = mx * sl2;
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float pv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            pv[k] = (8 * q + k < n) ? ex2_approx(fmaf(__uint_as_float(r[8 * q + k]), sl2, -mxs)) : 0.f;
+            sum += pv[k];
+        }
+        uint32_t h4[4], l2[2], g2[2];
+        split8_f16c(pv, h4, l2, g2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hh[4 * q + k] = h4[k];
+        l8[2 * q] = l2[0]; l8[2 * q + 1] = l2[1];
+        g8[2 * q] = g2[0]; g8[2 * q + 1] = g2[1];
+    }
+    return sum;
+}
+
 template <int HD, bool TEMPORAL>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6C x 16-bit, J, BF), box (64, 32, 4)
@@ -175,7 +205,7 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
         const int half = (warp - 2) >> 2;
         const int r_in_tile = quad * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        float* red_sum = reinterpret_cast<float*>(smem + Cfg::OFF_RED);   // [3][128], slot = problem index % 3
+        const uint32_t red_sum = smem_u32(smem + Cfg::OFF_RED);           // float [3][128], slot = problem index % 3
         const float sl2 = p.scale_log2e;
 
         auto softmax = [&](int i) {
@@ -187,32 +217,12 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
                 uint32_t r[32];
                 tmem_ld32(tS + lane_off + quad * 32, r);
                 tmem_ld_wait();
-                float mx = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < 32; ++k)
-                    if (k < p.L) mx = fmaxf(mx, __uint_as_float(r[k]));
-                const float mxs = mx * sl2;
-                float sum = 0.f;
                 uint32_t hh[16], l8[8], g8[8];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float pv[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        pv[k] = (8 * q + k < p.L) ? ex2_approx(fmaf(__uint_as_float(r[8 * q + k]), sl2, -mxs)) : 0.f;
-                        sum += pv[k];
-                    }
-                    uint32_t h4[4], l2[2], g2[2];
-                    split8_f16c(pv, h4, l2, g2);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) hh[4 * q + k] = h4[k];
-                    l8[2 * q] = l2[0]; l8[2 * q + 1] = l2[1];
-                    g8[2 * q] = g2[0]; g8[2 * q + 1] = g2[1];
-                }
+                const float sum = (p.L == 17) ? softmax32_f16c<17>(r, 17, sl2, hh, l8, g8) : softmax32_f16c<0>(r, p.L, sl2, hh, l8, g8);
                 tmem_st16(tS + lane_off + quad * 32, hh);
                 tmem_st8(tS + lane_off + quad * 32 + 16, l8);
                 tmem_st8(tS + lane_off + quad * 32 + 24, g8);
-                red_sum[(i % 3) * 128 + r_in_tile] = sum;
+                sts_f32(red_sum + ((i % 3) * 128 + r_in_tile) * 4, sum);
             } else {
                 // zero the three off-diagonal blocks of these rows so that sequences do not mix in P V
                 uint32_t z[16];
@@ -236,7 +246,7 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
             const int h = prob % p.H, g = prob / p.H;
             const uint32_t tO = tmem_base + s * Cfg::TMEM_SET + 128;
             named_bar_sync(1, ATT_SM_THREADS);           // red_sum slot written by the half-0 warps is visible
-            const float inv = 1.0f / red_sum[(i % 3) * 128 + r_in_tile];
+            const float inv = 1.0f / lds_f32(red_sum + ((i % 3) * 128 + r_in_tile) * 4);
             mbar_wait(&o_full[s], (i >> 1) & 1);
             tc_fence_after();
             const int seq = g * ATS_FRAMES + quad;

@@ -219,53 +219,70 @@ attn_t16_kernel(const __grid_constant__ CUtensorMap tmQ,    // 4-D (6C x 16-bit,
         const int grp = (warp - 2) >> 2;                // key chunk of each half / 16-column slice of the output
         const int r_in_tile = quad * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        float* red_max = reinterpret_cast<float*>(smem + Cfg::OFF_RED);   // [4][128]
-        float* red_sum = red_max + ATT_T_GROUPS * 128;                    // [4][128]
+        const uint32_t red_max = smem_u32(smem + Cfg::OFF_RED) + 4u * r_in_tile;     // float [4][128], my row
+        const uint32_t red_sum = red_max + ATT_T_GROUPS * 128 * 4;                   // float [4][128]
         const float sl2 = p.scale_log2e;
         const bool has_a = grp * 32 < nk_a;
         const bool has_b = nh == 2 && grp * 32 < nk_b;
+        const int key_a = grp * 32, key_b = 128 + grp * 32;
+        const bool full_a = key_a + 32 <= p.F, full_b = key_b + 32 <= p.F;
 
-        auto epilogue = [&](int t, float inv) {
-            int h, j, b;
-            prob_of(t, h, j, b);
-            const int qt = t % num_qt;
+        // (clip, joint, head) of a q-tile; advanced incrementally (one set of integer divisions per PROBLEM, by hand-over)
+        struct TileId { int h, j, b, qt; };
+        auto tile_id = [&](int t) {
+            TileId id;
+            const int prob = blockIdx.x + (t / num_qt) * gridDim.x;
+            id.h = prob % p.H; id.j = (prob / p.H) % p.J; id.b = prob / (p.H * p.J); id.qt = t % num_qt;
+            return id;
+        };
+        auto epilogue = [&](int t, const TileId& id, float inv) {
             mbar_wait(&o_full[t & 1], (t >> 1) & 1);
             tc_fence_after();
-            const int fr = qt * ATT_BM + r_in_tile;
+            const int fr = id.qt * ATT_BM + r_in_tile;
             if (grp * 16 < HD) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + Cfg::TM_O + (t & 1) * HD + lane_off + grp * 16, r);
                 tmem_ld_wait();
                 if (fr < p.F) {
-                    const size_t tok = (static_cast<size_t>(b) * p.F + fr) * p.J + j;
+                    const size_t tok = (static_cast<size_t>(id.b) * p.F + fr) * p.J + id.j;
                     float xv[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) xv[i] = __uint_as_float(r[i]) * inv;
-                    store16_f16c(p.out + tok * p.C * 4, h * HD + grp * 16, xv);
+                    store16_f16c(p.out + tok * p.C * 4, id.h * HD + grp * 16, xv);
                 }
             }
             tc_fence_before();
             mbar_arrive(&o_empty[t & 1]);
         };
-        // probabilities of my chunk of key half `hf`: exponentials, partial row sum, in-place F16C write-back
-        auto exp_half = [&](int t, int hf, float mxs, float& sum) {
-            const uint32_t tS = tmem_base + Cfg::TM_X + 128u * static_cast<uint32_t>((t * nh + hf) % 3) + lane_off + grp * 32;
-            const int key0 = hf * 128 + grp * 32;
-            uint32_t r[32];
-            tmem_ld32(tS, r);
-            tmem_ld_wait();
+        auto s_addr = [&](int t, int hf) {
+            return tmem_base + Cfg::TM_X + 128u * static_cast<uint32_t>((t * nh + hf) % 3) + lane_off + grp * 32;
+        };
+        auto row_max = [&](const uint32_t (&r)[32], int key0, bool full, float mx) {
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (key0 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+            return mx;
+        };
+        // probabilities of one chunk (32 scores in r): exponentials, partial row sum, in-place F16C write-back over S
+        auto exp_store = [&](uint32_t tS, const uint32_t (&r)[32], int key0, bool full, float mxs, float& sum) {
             uint32_t hh[16], l8[8], g8[8];
-            const bool full = key0 + 32 <= p.F;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float pv[8];
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float e = ex2_approx(fmaf(__uint_as_float(r[8 * q + i]), sl2, -mxs));
-                    if (!full && key0 + 8 * q + i >= p.F) e = 0.f;
-                    pv[i] = e;
-                    sum += e;
+                    for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[8 * q + i]), sl2, -mxs));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        pv[i] = key0 + 8 * q + i < p.F ? ex2_approx(fmaf(__uint_as_float(r[8 * q + i]), sl2, -mxs)) : 0.f;
                 }
+                sum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
                 uint32_t h4[4], l2[2], g2[2];
                 split8_f16c(pv, h4, l2, g2);
 #pragma unroll
@@ -279,50 +296,52 @@ attn_t16_kernel(const __grid_constant__ CUtensorMap tmQ,    // 4-D (6C x 16-bit,
         };
 
         float inv_prev = 0.f;
+        TileId id_prev = {0, 0, 0, 0};
         for (int t = 0; t < T; ++t) {
             mbar_wait(s_full, t & 1);
             tc_fence_after();
-            // pass 1: row max of the raw scores over my chunks (scale > 0 commutes with max)
+            // pass 1: row max of the raw scores over my chunks (scale > 0 commutes with max); half b first, so that the
+            // scores of half a stay in registers for the exponentials (one TMEM read less per tile)
             float mx = -INFINITY;
-            for (int hf = 0; hf < nh; ++hf) {
-                if (hf == 0 ? has_a : has_b) {
-                    const int key0 = hf * 128 + grp * 32;
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + Cfg::TM_X + 128u * static_cast<uint32_t>((t * nh + hf) % 3) + lane_off + grp * 32, r);
-                    tmem_ld_wait();
-                    if (key0 + 32 <= p.F) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (key0 + i < p.F) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    }
-                }
+            uint32_t ra[32];
+            if (has_b) {
+                uint32_t rb[32];
+                tmem_ld32(s_addr(t, 1), rb);
+                tmem_ld_wait();
+                mx = row_max(rb, key_b, full_b, mx);
             }
-            red_max[grp * 128 + r_in_tile] = mx;
+            if (has_a) {
+                tmem_ld32(s_addr(t, 0), ra);
+                tmem_ld_wait();
+                mx = row_max(ra, key_a, full_a, mx);
+            }
+            sts_f32(red_max + grp * 512, mx);
             named_bar_sync(1, ATT_T_SM_THREADS);
-            mx = fmaxf(fmaxf(red_max[r_in_tile], red_max[128 + r_in_tile]),
-                       fmaxf(red_max[256 + r_in_tile], red_max[384 + r_in_tile]));
+            mx = fmaxf(fmaxf(lds_f32(red_max), lds_f32(red_max + 512)), fmaxf(lds_f32(red_max + 1024), lds_f32(red_max + 1536)));
             const float mxs = mx * sl2;
             float sum = 0.f;
-            if (has_a) exp_half(t, 0, mxs, sum);
+            if (has_a) exp_store(s_addr(t, 0), ra, key_a, full_a, mxs, sum);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(pa_full);
-            if (t > 0) epilogue(t - 1, inv_prev);             // under the tensor pipe's P_a V_a / S(t+1)
+            if (t > 0) epilogue(t - 1, id_prev, inv_prev);             // under the tensor pipe's P_a V_a / S(t+1)
             if (nh == 2) {
-                if (has_b) exp_half(t, 1, mxs, sum);
+                if (has_b) {
+                    uint32_t rb[32];
+                    tmem_ld32(s_addr(t, 1), rb);
+                    tmem_ld_wait();
+                    exp_store(s_addr(t, 1), rb, key_b, full_b, mxs, sum);
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(pb_full);
             }
-            red_sum[grp * 128 + r_in_tile] = sum;
+            sts_f32(red_sum + grp * 512, sum);
+            id_prev = tile_id(t);
             named_bar_sync(1, ATT_T_SM_THREADS);
-            inv_prev = 1.0f / ((red_sum[r_in_tile] + red_sum[128 + r_in_tile]) +
-                               (red_sum[256 + r_in_tile] + red_sum[384 + r_in_tile]));
+            inv_prev = 1.0f / ((lds_f32(red_sum) + lds_f32(red_sum + 512)) + (lds_f32(red_sum + 1024) + lds_f32(red_sum + 1536)));
         }
-        if (T > 0) epilogue(T - 1, inv_prev);
+        if (T > 0) epilogue(T - 1, id_prev, inv_prev);
     }
 
     tc_fence_before();

@@ -89,6 +89,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x * (x >= 0.f ? 1.0f - q : q);
 }
 
+// Two values at once on Blackwell's packed fp32x2 pipe instructions (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes'
+// worth of work -- the F16C GEMM epilogues are issue-bound, profiles/r02a).  Same polynomial; the 0.5 of Phi is folded
+// into the coefficients.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+    const float2 u = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+    float2 t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+    float2 poly = __ffma2_rn(make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+    poly = __fmul2_rn(poly, t);
+    const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    const float2 q = __fmul2_rn(poly, make_float2(ex2_approx(a.x), ex2_approx(a.y)));      // 0.5 * erfc(|z|)
+    const float2 om = __fadd2_rn(make_float2(1.0f, 1.0f), make_float2(-q.x, -q.y));
+    return __fmul2_rn(x, make_float2(x.x >= 0.f ? om.x : q.x, x.y >= 0.f ? om.y : q.y));
+}
+
 // d/dx [x Phi(x)] = Phi(x) + x phi(x), with Phi from the same erfc polynomial and phi from the SAME exponential
 // (exp(-z^2) with z = |x|/sqrt(2) is exp(-x^2/2)): one MUFU.RCP + one MUFU.EX2.
 __device__ __forceinline__ float gelu_grad_fast(float x) {

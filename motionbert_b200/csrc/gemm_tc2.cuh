@@ -119,7 +119,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 2 * EW * 32);
+            mbar_init(&tempty_bar[i], 2 * EW);             // one arrival per epilogue warp of the pair
         }
         for (int i = 0; i < 2 * EW; ++i) mbar_init(&rbar[i], 1);
         fence_barrier_init();
@@ -350,18 +350,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     const float4* c4 = reinterpret_cast<const float4*>(p.vec0 + col0);
                     const float4* s4 = reinterpret_cast<const float4*>(p.vec1 + col0);
                     const float ms = -mean * rstd;
+                    const float2 ms2 = make_float2(ms, ms), rstd2 = make_float2(rstd, rstd);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 c = __ldg(c4 + i);
                         const float4 s = __ldg(s4 + i);
-                        v[4 * i + 0] = fmaf(rstd, __uint_as_float(r[4 * i + 0]), fmaf(ms, s.x, c.x));
-                        v[4 * i + 1] = fmaf(rstd, __uint_as_float(r[4 * i + 1]), fmaf(ms, s.y, c.y));
-                        v[4 * i + 2] = fmaf(rstd, __uint_as_float(r[4 * i + 2]), fmaf(ms, s.z, c.z));
-                        v[4 * i + 3] = fmaf(rstd, __uint_as_float(r[4 * i + 3]), fmaf(ms, s.w, c.w));
-                    }
-                    if (EPI == EPI_LN_GELU_SPLIT) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                        // packed fp32x2 FMAs (bit-identical to two scalar fmaf each; half the issue slots)
+                        float2 a = __ffma2_rn(rstd2, make_float2(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1])),
+                                              __ffma2_rn(ms2, make_float2(s.x, s.y), make_float2(c.x, c.y)));
+                        float2 b = __ffma2_rn(rstd2, make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
+                                              __ffma2_rn(ms2, make_float2(s.z, s.w), make_float2(c.z, c.w)));
+                        if (EPI == EPI_LN_GELU_SPLIT) {
+                            a = gelu_erf2(a);
+                            b = gelu_erf2(b);
+                        }
+                        v[4 * i + 0] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
                     }
                     if (EPI == EPI_LN_TANH_F32 || EPI == EPI_LN_TANH_POOL) {
 #pragma unroll
@@ -443,9 +446,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     tma_store_commit();
                 }
             }
-            // every TMEM read of this accumulator is complete -> release it to the leader's MMA warp
+            // every TMEM read of this accumulator is complete -> release it to the leader's MMA warp: each lane fences its
+            // tcgen05.ld's, the warp converges, ONE lane arrives (a 32-way release-arrive cost 11 % of the epilogue's issue
+            // slots in fences, profiles/r02a)
             tc_fence_before();
-            mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
             if (kResid) {
                 if (row_ok && p.stats_out) {
                     float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;

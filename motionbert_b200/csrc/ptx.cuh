@@ -357,7 +357,9 @@ __device__ __forceinline__ void split2_f16c(float x0, float x1, uint32_t& h, uin
     const __half2 h2 = __floats2half2_rn(x0, x1);
     h = *reinterpret_cast<const uint32_t*>(&h2);
     const float2 hf = __half22float2(h2);
-    lo8 = __nv_cvt_float2_to_fp8x2(make_float2((x0 - hf.x) * F16C_SCALE, (x1 - hf.y) * F16C_SCALE), __NV_SATFINITE, __NV_E5M2);
+    // (x - h) * 2^6 on the packed fp32x2 pipe: exact (the residual of an f16 rounding is representable, the scale a power of two)
+    const float2 r = __fmul2_rn(__fadd2_rn(make_float2(x0, x1), make_float2(-hf.x, -hf.y)), make_float2(F16C_SCALE, F16C_SCALE));
+    lo8 = __nv_cvt_float2_to_fp8x2(r, __NV_SATFINITE, __NV_E5M2);
     const __half2 hs = __hmul2(h2, __floats2half2_rn(1.0f / F16C_SCALE, 1.0f / F16C_SCALE));
     hi8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hs), __NV_SATFINITE, __NV_E5M2);
 }
@@ -404,6 +406,16 @@ __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, MUFU.EX2 (rel e
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// explicit shared-window accesses (pointers derived from the aligned dynamic-smem base lose their address space and
+// compile to generic LD / ST)
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

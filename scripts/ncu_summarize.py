@@ -40,9 +40,13 @@ WANT = {"gpu__time_duration.sum": "time_us", "sm__cycles_elapsed.avg.per_second"
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
 for part in ("gemm", "attn", "fuse"):
     rep = f"{G}/{tag}_{part}.ncu-rep"
-    if not os.path.exists(rep):
+    raw = f"{G}/{tag}_{part}_raw.csv"            # exported on the GPU box when the reports exceed gpurun's 64 MiB cap
+    if os.path.exists(raw):
+        txt = open(raw).read()
+    elif os.path.exists(rep):
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         continue
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(txt.splitlines()))
     h, units = rr[0], rr[1]
     for r in rr[2:]:
