@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("MB_LIB_OVERRIDE") or os.path.join(HERE, "libmotionbert_b200.so")   # override: A/B builds only
+LIB_PATH = os.path.join(HERE, "libmotionbert_b200.so")
 TEST_LIB_PATH = os.path.join(HERE, "libmotionbert_b200_test.so")     # tests only: + reference kernels and hooks
 
 MB_MATH_BF16X3 = 0
@@ -21,7 +21,6 @@ MB_FLAG_GEMM_1CTA = 0x4
 MB_FLAG_REF_ATTN_S = 0x8
 MB_FLAG_ATTN_T_UNPACKED = 0x20
 MB_FLAG_ATTN_BF16X3 = 0x40
-MB_FLAG_GEMM_PAIRKB = 0x80
 
 # every symbol include/motionbert_b200.h declares (TEST_EXPORTS: include/motionbert_b200_test.h, test library only)
 EXPORTS = [

@@ -56,7 +56,6 @@ struct GemmParams {
     float* stats_out;         // RESID: [M][N/128][3]
     const __nv_bfloat16* aux; // GELUBWD: pre-activation plane [M,N] (bf16)
     int pool_F;               // LN_TANH_POOL: frames per clip (rows are (b F + f) J + j)
-    int pair_kb;              // F16C A/B: issue the MMAs of two K blocks grouped by kind (f16 x4, then e5m2 x4)
 };
 
 template <int PASSES>

@@ -173,39 +173,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                if (Cfg::F16C && p.pair_kb) {
-                    // two K blocks per round, MMAs grouped by kind: half as many f16 <-> f8f6f4 switches in the tensor pipe
-                    for (int kb = 0; kb < num_kb; kb += 2) {
-                        const int s0 = stage;
-                        const uint32_t ph0 = phase;
-                        int s1 = stage + 1;
-                        uint32_t ph1 = phase;
-                        if (s1 == G2_STAGES) { s1 = 0; ph1 ^= 1; }
-                        mbar_wait(&full_bar[s0], ph0);
-                        mbar_wait(&full_bar[s1], ph1);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t sA0 = smem_u32(smem + s0 * Cfg::STAGE_BYTES), sA1 = smem_u32(smem + s1 * Cfg::STAGE_BYTES);
-                            const uint64_t a0 = umma_smem_desc(sA0, 16, 1024, 2u), b0 = umma_smem_desc(sA0 + Cfg::A_BYTES, 16, 1024, 2u);
-                            const uint64_t a1 = umma_smem_desc(sA1, 16, 1024, 2u), b1 = umma_smem_desc(sA1 + Cfg::A_BYTES, 16, 1024, 2u);
-                            umma_ss_2cta(d_tmem, a0, b0, IDESC, kb != 0);
-                            umma_ss_2cta(d_tmem, a0 + 2, b0 + 2, IDESC, 1);
-                            umma_ss_2cta(d_tmem, a1, b1, IDESC, 1);
-                            umma_ss_2cta(d_tmem, a1 + 2, b1 + 2, IDESC, 1);
-                            umma_ss_2cta_f8(d_tmem, a0 + 4, b0 + 6, IDESC8, 1);
-                            umma_ss_2cta_f8(d_tmem, a0 + 6, b0 + 4, IDESC8, 1);
-                            umma_ss_2cta_f8(d_tmem, a1 + 4, b1 + 6, IDESC8, 1);
-                            umma_ss_2cta_f8(d_tmem, a1 + 6, b1 + 4, IDESC8, 1);
-                            tc_commit_2cta(&empty_bar[s0], 3);
-                            tc_commit_2cta(&empty_bar[s1], 3);
-                            if (kb + 2 >= num_kb) tc_commit_2cta(&tfull_bar[acc], 3);
-                        }
-                        __syncwarp();
-                        stage = s1 + 1;
-                        phase = ph1;
-                        if (stage == G2_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                } else
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();

@@ -777,7 +777,6 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
     p.vec1 = reinterpret_cast<const float*>(packed + L.off_s);
     const int passes = passes_of(e->d);
     if (passes == 1) p.out_lo = nullptr;
-    p.pair_kb = (flags & MB_FLAG_GEMM_PAIRKB) ? 1 : 0;
     prof_mark(e, st, EPI == EPI_LN_SPLIT ? PC_GEMM_QKV : EPI == EPI_LN_GELU_SPLIT ? PC_GEMM_FC1
                      : EPI == EPI_RESID ? PC_GEMM_RESID : PC_GEMM_TAIL);
     if (passes == 2 && (flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA)))
