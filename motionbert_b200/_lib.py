@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmotionbert_b200.so")
+LIB_PATH = os.environ.get("MB_LIB_OVERRIDE") or os.path.join(HERE, "libmotionbert_b200.so")   # override: A/B builds only
 TEST_LIB_PATH = os.path.join(HERE, "libmotionbert_b200_test.so")     # tests only: + reference kernels and hooks
 
 MB_MATH_BF16X3 = 0

@@ -11,10 +11,17 @@
 
 namespace mb {
 
-// Every spin-wait carries a watchdog: a lost TMA / commit turns into a trap
-// (reported as a CUDA launch failure by the host) instead of a hung GPU.
-#ifndef MB_WATCHDOG_CYCLES
-#define MB_WATCHDOG_CYCLES (4000000000LL)   // ~2 s at 1.9 GHz
+// Every wait carries a watchdog: a lost TMA / commit turns into a trap (reported as a CUDA launch failure by the host)
+// instead of a hung GPU.  Waiting itself is a hardware sleep: mbarrier.try_wait with a suspend-time hint parks the warp
+// until the phase completes (or the hint expires), so a waiting warp re-issues a handful of instructions every
+// MB_WAIT_HINT_NS instead of spinning through the scheduler next to the warps that do the work (profiles/r02a: the
+// plain try_wait loops with a clock64 watchdog were ~10 % of all issued instructions of the GEMM and attention kernels;
+// same-box A/B of the two builds: no throughput difference, so this is about issue-slot hygiene, not speed).
+#ifndef MB_WAIT_HINT_NS
+#define MB_WAIT_HINT_NS 20000u
+#endif
+#ifndef MB_WATCHDOG_TRIES
+#define MB_WATCHDOG_TRIES 200000u           // x 20 us = ~4 s
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -50,11 +57,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(MB_WAIT_HINT_NS)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > MB_WATCHDOG_CYCLES) {
+    uint32_t tries = 0;
+    while (!mbar_try_wait_sleep(bar, parity)) {
+        if (++tries > MB_WATCHDOG_TRIES) {
             printf("[mb] mbarrier watchdog: block %d thread %d bar@%u parity %u\n", (int)blockIdx.x,
                    (int)threadIdx.x, smem_u32(bar), parity);
             __trap();
@@ -253,11 +271,22 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_cluster_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(MB_WAIT_HINT_NS)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > MB_WATCHDOG_CYCLES) {
+    uint32_t tries = 0;
+    while (!mbar_try_wait_cluster_sleep(bar, parity)) {
+        if (++tries > MB_WATCHDOG_TRIES) {
             printf("[mb] cluster mbarrier watchdog: block %d thread %d bar@%u parity %u\n", (int)blockIdx.x,
                    (int)threadIdx.x, smem_u32(bar), parity);
             __trap();
