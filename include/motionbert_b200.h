@@ -79,7 +79,6 @@ typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 #define MB_FLAG_REF_ATTN_S 0x8u   /* TEST ONLY: CUDA-core reference spatial attention                 */
 #define MB_FLAG_GEMM_1CTA  0x4u   /* TEST ONLY: first-generation 1-CTA tcgen05 GEMM (LSU epilogue)    */
 #define MB_FLAG_ATTN_T_UNPACKED 0x20u /* one-sequence-per-tile temporal kernel even when F <= 32 (both libraries)  */
-#define MB_FLAG_GEMM_EW8   0x80u  /* F16C qkv / fc1 GEMMs with 8 instead of 16 epilogue warps (A/B switch)                      */
 #define MB_FLAG_ATTN_BF16X3 0x40u /* F16C mode A/B: qkv as bf16 hi/lo planes + the BF16x3 attention kernels (both)  */
 
 int mb_version(void);

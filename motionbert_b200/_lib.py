@@ -21,7 +21,6 @@ MB_FLAG_GEMM_1CTA = 0x4
 MB_FLAG_REF_ATTN_S = 0x8
 MB_FLAG_ATTN_T_UNPACKED = 0x20
 MB_FLAG_ATTN_BF16X3 = 0x40
-MB_FLAG_GEMM_EW8 = 0x80
 
 # every symbol include/motionbert_b200.h declares (TEST_EXPORTS: include/motionbert_b200_test.h, test library only)
 EXPORTS = [

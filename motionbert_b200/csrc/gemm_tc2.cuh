@@ -35,7 +35,7 @@ struct Gemm2Cfg {
     static constexpr int STAGES = (EPI == EPI_RESID) ? G2_STAGES_RESID : G2_STAGES_OTHER;
     // 8 warps: buf0 4 KB | buf1 4 KB | [split 4 KB].  16 warps (bf16-plane outputs only): one 2 KB plane tile per
     // buffer, double-buffered (4 KB), or -- two output planes -- a single 4 KB buffer
-    static constexpr bool TWO_PLANES = (PASSES != 1) || (EPI == EPI_BIAS_GELU_PAIR);   // 4 KB of split staging per chunk
+    static constexpr bool TWO_PLANES = (PASSES == 3) || (EPI == EPI_BIAS_GELU_PAIR);
     static constexpr int NBUF = (EW == 16 && TWO_PLANES) ? 1 : 2;
     static constexpr int BUF_BYTES = (EW == 16 && !TWO_PLANES) ? 2048 : 4096;
     static constexpr int STAGING_PER_WARP = (EPI == EPI_RESID) ? 12288 : NBUF * BUF_BYTES;
@@ -73,15 +73,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     using Cfg = Gemm2Cfg<PASSES, EPI, EW>;
     constexpr int G2_STAGES = Cfg::STAGES;
     static_assert(EW == 8 || (EW == 16 && PASSES == 1 && (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT ||
-                                                          EPI == EPI_BIAS_GELU_PAIR || EPI == EPI_GELUBWD_SPLIT)) ||
-                      (EW == 16 && PASSES == 2 && OUT16C && (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT)),
-                  "16 epilogue warps: single-pass bf16-plane epilogues, and the F16C qkv / fc1 epilogues");
+                                                          EPI == EPI_BIAS_GELU_PAIR || EPI == EPI_GELUBWD_SPLIT)),
+                  "16 epilogue warps: single-pass bf16-plane epilogues only");
     constexpr bool kResid = (EPI == EPI_RESID);
     constexpr bool kF32Out = (EPI == EPI_RESID || EPI == EPI_LN_TANH_F32 || EPI == EPI_BIAS_F32);
     constexpr bool kSplitOut = (EPI == EPI_RESID || EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_BIAS_SPLIT ||
                                 EPI == EPI_BIAS_GELU_PAIR || EPI == EPI_GELUBWD_SPLIT);
     constexpr bool kTwoPlanes = (PASSES == 3 || (PASSES == 2 && !OUT16C)) || (EPI == EPI_BIAS_GELU_PAIR);   // second bf16 plane: lo, or gelu(y)
     static_assert(!(B_MN && PASSES == 2), "the F16C mode has no MN-major weight form (backward runs in bf16)");
+    static_assert(!OUT16C || EW == 8, "F16C output: 8 epilogue warps");
     constexpr bool kDoubleLd = !kResid && EW == 8;                               // register double-buffered tcgen05.ld
     constexpr bool kLn = (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT || EPI == EPI_LN_TANH_F32 || EPI == EPI_LN_TANH_POOL);
     constexpr bool kPool = (EPI == EPI_LN_TANH_POOL);

@@ -203,8 +203,6 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_RESID>, Gemm2Cfg<2, EPI_RESID>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_F32>, Gemm2Cfg<2, EPI_LN_TANH_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_BIAS_F32>, Gemm2Cfg<2, EPI_BIAS_F32>::SMEM_BYTES));
-        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_SPLIT, false, 16>, Gemm2Cfg<2, EPI_LN_SPLIT, 16>::SMEM_BYTES));
-        CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_GELU_SPLIT, false, 16>, Gemm2Cfg<2, EPI_LN_GELU_SPLIT, 16>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_LN_TANH_POOL>, Gemm2Cfg<1, EPI_LN_TANH_POOL>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_POOL>, Gemm2Cfg<2, EPI_LN_TANH_POOL>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<3, EPI_LN_TANH_POOL>, Gemm2Cfg<3, EPI_LN_TANH_POOL>::SMEM_BYTES));
@@ -770,13 +768,6 @@ struct EpiMaps {
 };
 
 template <int EPI>
-static void launch_f16c_ew16(int grid, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR,
-                             const CUtensorMap& tmX, const CUtensorMap& tmS, const GemmParams& p) {
-    if constexpr (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT)
-        gemm2_kernel<2, EPI, false, 16><<<grid, g2_threads(16), Gemm2Cfg<2, EPI, 16>::SMEM_BYTES, st>>>(tmA, tmB, tmR, tmX, tmS, p);
-}
-
-template <int EPI>
 static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tmA, const __nv_bfloat16* a_hi,
                        const __nv_bfloat16* a_lo, const LinearPack& L, const uint8_t* packed, GemmParams p,
                        const EpiMaps& em, cudaStream_t st) {
@@ -834,9 +825,6 @@ static int launch_gemm(const MbEncoder* e, uint32_t flags, const CUtensorMap& tm
         gemm2_kernel<3, EPI><<<grid, G2_THREADS, Gemm2Cfg<3, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else if (passes == 2 && EPI == EPI_LN_SPLIT && em.split_bf16)      // qkv planes for the bf16x3 attention kernels
         gemm2_kernel<2, EPI, false, 8, false><<<grid, G2_THREADS, Gemm2Cfg<2, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
-    else if (passes == 2 && (EPI == EPI_LN_SPLIT || EPI == EPI_LN_GELU_SPLIT) && !(flags & MB_FLAG_GEMM_EW8))
-        // the F16C mainloop is 1/3 shorter than BF16x3's: the 8-warp epilogue became latency-bound (profiles/r02a)
-        launch_f16c_ew16<EPI>(grid, st, tmA, L.tmap2, tmR, tmX, tmS, p);
     else if (passes == 2)
         gemm2_kernel<2, EPI><<<grid, G2_THREADS, Gemm2Cfg<2, EPI>::SMEM_BYTES, st>>>(tmA, L.tmap2, tmR, tmX, tmS, p);
     else
