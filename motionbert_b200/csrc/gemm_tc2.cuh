@@ -30,13 +30,19 @@ constexpr int G2_EPI_WARPS = 8;
 // latency; no register double-buffering at the 112-register cap of 576 threads).
 constexpr int g2_threads(int ew) { return (2 + ew) * 32; }
 
+// MB_F16C_DEEP (A/B build switch): the F16C qkv / fc1 / tail GEMMs trade the second epilogue staging buffer of every warp
+// for a sixth operand stage (a stage lasts 512 MMA-cycles in F16C against 768 in BF16x3: less look-ahead per stage).
+#ifndef MB_F16C_DEEP
+#define MB_F16C_DEEP 0
+#endif
 template <int PASSES, int EPI, int EW = G2_EPI_WARPS>
 struct Gemm2Cfg {
-    static constexpr int STAGES = (EPI == EPI_RESID) ? G2_STAGES_RESID : G2_STAGES_OTHER;
+    static constexpr bool DEEP = MB_F16C_DEEP && PASSES == 2 && EPI != EPI_RESID && EW == 8;
+    static constexpr int STAGES = DEEP ? 6 : (EPI == EPI_RESID) ? G2_STAGES_RESID : G2_STAGES_OTHER;
     // 8 warps: buf0 4 KB | buf1 4 KB | [split 4 KB].  16 warps (bf16-plane outputs only): one 2 KB plane tile per
     // buffer, double-buffered (4 KB), or -- two output planes -- a single 4 KB buffer
     static constexpr bool TWO_PLANES = (PASSES == 3) || (EPI == EPI_BIAS_GELU_PAIR);
-    static constexpr int NBUF = (EW == 16 && TWO_PLANES) ? 1 : 2;
+    static constexpr int NBUF = ((EW == 16 && TWO_PLANES) || DEEP) ? 1 : 2;
     static constexpr int BUF_BYTES = (EW == 16 && !TWO_PLANES) ? 2048 : 4096;
     static constexpr int STAGING_PER_WARP = (EPI == EPI_RESID) ? 12288 : NBUF * BUF_BYTES;
     // PASSES == 2 is the F16C mode (ptx.cuh): one SWIZZLE_128B row of [32 f16 | 32 lo8 | 32 hi8] per 32-element K block,
@@ -96,7 +102,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
     uint64_t* rbar = bars + 2 * G2_STAGES + 4;             // [8 warps][2] residual-tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + 2 * EW);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);     // role dispatch on a value nvcc knows is warp-uniform
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1;
@@ -132,7 +138,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
+        // every lane walks the (warp-uniform) loop and one elected lane issues: nvcc keeps coordinates, shared addresses
+        // and descriptors in uniform registers (with `if (lane == 0)` around the loop every UTMALDG / UTCHMMA was wrapped
+        // in an ELECT + R2UR waterfall of ~10 instructions)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += npairs) {
@@ -141,20 +150,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 const int b_row = n_idx * 256 + static_cast<int>(rank) * 128;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-                    uint8_t* sB = sA + Cfg::A_BYTES;
-                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                    tma_load_3d_2cta(sA, &tmA, full_leader, kb * Cfg::KSTEP16, a_row, 0);
-                    if (!B_MN) {
-                        tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::KSTEP16, b_row, 0);
-                    } else {
-                        // this CTA's 128 output columns = two 64-column blocks of [BK contraction rows][128 B] per plane
-                        for (int pl = 0; pl < Cfg::PLANES; ++pl)
-                            for (int blk = 0; blk < 2; ++blk)
-                                tma_load_3d_2cta(sB + pl * Cfg::B_PLANE + blk * (Cfg::BK * 128), &tmB, full_leader,
-                                                 b_row + blk * 64, kb * Cfg::BK, pl);
+                    if (elect_one()) {
+                        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                        uint8_t* sB = sA + Cfg::A_BYTES;
+                        const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        tma_load_3d_2cta(sA, &tmA, full_leader, kb * Cfg::KSTEP16, a_row, 0);
+                        if (!B_MN) {
+                            tma_load_3d_2cta(sB, &tmB, full_leader, kb * Cfg::KSTEP16, b_row, 0);
+                        } else {
+                            // this CTA's 128 output columns = two 64-column blocks of [BK contraction rows][128 B] per plane
+                            for (int pl = 0; pl < Cfg::PLANES; ++pl)
+                                for (int blk = 0; blk < 2; ++blk)
+                                    tma_load_3d_2cta(sB + pl * Cfg::B_PLANE + blk * (Cfg::BK * 128), &tmB, full_leader,
+                                                     b_row + blk * 64, kb * Cfg::BK, pl);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -176,7 +188,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                         const uint32_t sB = sA + Cfg::A_BYTES;
                         const uint64_t a_hi = umma_smem_desc(sA, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
@@ -236,7 +248,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             rowb = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32;
         };
         uint32_t ci = 0;   // chunks processed by this warp (buffer parity / rbar phase)
-        if (kResid && lane == 0 && pair < num_tiles) {
+        if (kResid && pair < num_tiles && elect_one()) {
             int c0, r0;
             chunk_coords(pair, 0, c0, r0);
             mbar_arrive_expect_tx(&my_rbar[0], 4096);
@@ -262,6 +274,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + half * COLS_PER_WARP + (static_cast<uint32_t>(quad * 32) << 16);
+#ifdef MB_EXP_NO_EPI
+            // timing experiment (A/B builds only, results are garbage): the accumulator is released unread
+            if (Cfg::F16C && !kResid) {
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+#endif
             uint32_t racc[kDoubleLd ? 2 : 1][32];
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch, ++ci) {
@@ -270,7 +292,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 chunk_coords(tile, ch, col0, rowb);
                 if (kResid) {
                     mbar_wait(&my_rbar[b], (ci >> 1) & 1);            // residual chunk landed in buf[b]
-                    if (lane == 0) {
+                    if (elect_one()) {
                         tma_store_wait_read<0>();                      // group ci-1 no longer reads buf[b^1] / bufS
                         int nt = tile, nc = ch + 1;
                         if (nc == NCH) { nc = 0; nt = tile + npairs; }
@@ -282,9 +304,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         }
                     }
                 } else if (Cfg::NBUF == 2) {
-                    if (lane == 0) tma_store_wait_read<1>();           // group ci-2 no longer reads buf[b]
+                    if (elect_one()) tma_store_wait_read<1>();           // group ci-2 no longer reads buf[b]
                 } else {
-                    if (lane == 0) tma_store_wait_read<0>();           // single staging buffer: previous store has read it
+                    if (elect_one()) tma_store_wait_read<0>();           // single staging buffer: previous store has read it
                 }
                 // non-residual epilogues double-buffer the accumulator chunk: tcgen05.ld of chunk ch+1 is in flight while
                 // chunk ch is processed (the residual variant has no registers to spare at 10 warps / 168 registers)
@@ -437,7 +459,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {       // elect.sync is deterministic: the same lane owns every bulk-store group of the warp
                     if (kF32Out) tma_store_2d(&tmX, xs, col0, rowb);
                     if (do_split) {
                         if (OUT16C) tma_store_2d(&tmS, ss, col0 * 2, rowb);
@@ -451,7 +473,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             // slots in fences, profiles/r02a)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+            if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
             if (kResid) {
                 if (row_ok && p.stats_out) {
                     float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;
@@ -463,7 +485,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (lane == 0) tma_store_wait_all();
+        if (elect_one()) tma_store_wait_all();
     }
 
     tc_fence_before();

@@ -242,6 +242,23 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 
 
 // ------------------------------------------------------------ clusters / 2-CTA (cta_group::2) ---------
+// One lane of the (converged) warp, chosen by the hardware.  Unlike `lane == 0`, nvcc treats the surrounding code as
+// warp-uniform: addresses / descriptors of the tcgen05 and TMA instructions stay in uniform registers (no per-instruction
+// ELECT + R2UR "waterfall" in the SASS).  Use together with warp_uniform() for the role dispatch.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// a value nvcc knows to be the same in every lane (warp index for role dispatch)
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
