@@ -80,7 +80,7 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
     uint64_t* o_empty = bars + 14;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);          // role dispatch on a value nvcc knows is warp-uniform
     const int lane = threadIdx.x & 31;
     const int num_groups = (p.nseq + ATS_FRAMES - 1) / ATS_FRAMES;
     const int num_prob = num_groups * p.H;
@@ -109,7 +109,8 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        // (every lane walks the warp-uniform loop, one elected lane issues: operands stay in uniform registers)
+        {
             for (int i = 0; i < n_mine; ++i) {
                 const int prob = blockIdx.x + i * gridDim.x;
                 const int h = prob % p.H, g = prob / p.H;
@@ -133,12 +134,17 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
                 };
                 const int col16 = (h * HD / 32) * 64;
                 mbar_wait(&qk_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&qk_full[s], 2 * Cfg::TILE_BYTES);
-                load_tile(set, &qk_full[s], col16);                                   // Q
-                load_tile(set + Cfg::TILE_BYTES, &qk_full[s], 2 * p.C + col16);       // K
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&qk_full[s], 2 * Cfg::TILE_BYTES);
+                    load_tile(set, &qk_full[s], col16);                                   // Q
+                    load_tile(set + Cfg::TILE_BYTES, &qk_full[s], 2 * p.C + col16);       // K
+                }
                 mbar_wait(&v_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&v_full[s], Cfg::TILE_BYTES);
-                load_tile(set + 2 * Cfg::TILE_BYTES, &v_full[s], 4 * p.C + col16);    // V
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&v_full[s], Cfg::TILE_BYTES);
+                    load_tile(set + 2 * Cfg::TILE_BYTES, &v_full[s], 4 * p.C + col16);    // V
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -151,7 +157,7 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
             const int s = i & 1;
             mbar_wait(&qk_full[s], (i >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t sQ = smem_u32(smem + s * Cfg::SET_BYTES);
                 const uint32_t sK = sQ + Cfg::TILE_BYTES;
                 const uint32_t tS = tmem_base + s * Cfg::TMEM_SET;
@@ -178,7 +184,7 @@ attn_s16_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 3-D (6
             mbar_wait(&v_full[s], ph);
             mbar_wait(&o_empty[s], ph ^ 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t sV = smem_u32(smem + s * Cfg::SET_BYTES + 2 * Cfg::TILE_BYTES);
                 const uint32_t tS = tmem_base + s * Cfg::TMEM_SET;
                 const uint32_t tO = tS + 128;

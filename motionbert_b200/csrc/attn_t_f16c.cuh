@@ -63,7 +63,7 @@ attn_t16_kernel(const __grid_constant__ CUtensorMap tmQ,    // 4-D (6C x 16-bit,
     uint64_t* o_empty = bars + 13;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);          // role dispatch on a value nvcc knows is warp-uniform
     const int lane = threadIdx.x & 31;
     const int num_prob = p.B * p.J * p.H;
     const int num_qt = (p.F + ATT_BM - 1) / ATT_BM;
@@ -105,32 +105,38 @@ attn_t16_kernel(const __grid_constant__ CUtensorMap tmQ,    // 4-D (6C x 16-bit,
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
-            for (int t = 0; t < T; ++t) {
-                int h, j, b;
-                prob_of(t, h, j, b);
-                const int i = t / num_qt, qt = t % num_qt;
-                const uint32_t kv_ph = i & 1;
-                const int col16 = (h * HD / 32) * 64;                 // 16-bit-unit column of the head's first block (q part)
-                if (qt == 0) {
-                    mbar_wait(k_empty, kv_ph ^ 1);
+        // (every lane walks the warp-uniform loop, one elected lane issues: operands stay in uniform registers)
+        for (int t = 0; t < T; ++t) {
+            int h, j, b;
+            prob_of(t, h, j, b);
+            const int i = t / num_qt, qt = t % num_qt;
+            const uint32_t kv_ph = i & 1;
+            const int col16 = (h * HD / 32) * 64;                 // 16-bit-unit column of the head's first block (q part)
+            if (qt == 0) {
+                mbar_wait(k_empty, kv_ph ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(k_full, kv_bytes);
                     for (int blk = 0; blk < Cfg::NBLK; ++blk)
                         tma_load_4d(smem + Cfg::OFF_K + blk * kv_blk, &tmKV, k_full, 2 * p.C + col16 + blk * 64, j, 0, b);
                 }
-                const int qs = t & 1;
-                mbar_wait(&q_empty[qs], ((t >> 1) & 1) ^ 1);
+            }
+            const int qs = t & 1;
+            mbar_wait(&q_empty[qs], ((t >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&q_full[qs], Cfg::Q_BYTES);
                 for (int blk = 0; blk < Cfg::NBLK; ++blk)
                     tma_load_4d(smem + Cfg::OFF_Q + qs * Cfg::Q_BYTES + blk * Cfg::Q_BLK, &tmQ, &q_full[qs],
                                 col16 + blk * 64, j, qt * ATT_BM, b);
-                if (qt == 0) {
-                    mbar_wait(v_empty, kv_ph ^ 1);
+            }
+            if (qt == 0) {
+                mbar_wait(v_empty, kv_ph ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(v_full, kv_bytes);
                     for (int blk = 0; blk < Cfg::NBLK; ++blk)
                         tma_load_4d(smem + Cfg::OFF_V + blk * kv_blk, &tmKV, v_full, 4 * p.C + col16 + blk * 64, j, 0, b);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
@@ -146,7 +152,7 @@ attn_t16_kernel(const __grid_constant__ CUtensorMap tmQ,    // 4-D (6C x 16-bit,
             const int qs = t & 1;
             mbar_wait(&q_full[qs], (t >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t sQ = smem_u32(smem + Cfg::OFF_Q + qs * Cfg::Q_BYTES);
                 for (int hf = 0; hf < nh; ++hf) {
                     const int n = hf == 0 ? nk_a : nk_b;
@@ -171,7 +177,7 @@ attn_t16_kernel(const __grid_constant__ CUtensorMap tmQ,    // 4-D (6C x 16-bit,
         };
         // O(t) (+)= P V over key half hf of q-tile t
         auto issue_PV = [&](int t, int hf) {
-            if (lane == 0) {
+            if (elect_one()) {
                 const int n = hf == 0 ? nk_a : nk_b;
                 const uint32_t tP = tmem_base + Cfg::TM_X + 128u * static_cast<uint32_t>((t * nh + hf) % 3);
                 const uint32_t tO = tmem_base + Cfg::TM_O + static_cast<uint32_t>((t & 1) * HD);
@@ -207,7 +213,7 @@ attn_t16_kernel(const __grid_constant__ CUtensorMap tmQ,    // 4-D (6C x 16-bit,
                 tc_fence_after();
                 issue_PV(t, 1);
             }
-            if (lane == 0) {
+            if (elect_one()) {
                 tc_commit(&o_full[t & 1]);
                 if (qt == num_qt - 1) tc_commit(v_empty);
             }
