@@ -79,7 +79,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     float* red = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);   // [2][128] max, then [2][128] sum
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);      // uniform role dispatch (see ptx.cuh elect_one)
     const int lane = threadIdx.x & 31;
     const int nseq = p.B * p.J;
     const int num_prob = PACK ? ((nseq + 3) / 4) * p.H : nseq * p.H;
@@ -105,7 +105,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
     const uint32_t tmem_dP = tmem_base + 256;      // [256,512): dP, then dQ accumulator in its first HD columns
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t t_it = 0;
             int ip = 0;
             for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++ip) {
@@ -158,7 +158,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                 mbar_wait(t_full, ph);
                 mbar_wait(dq_empty, ph ^ 1);          // previous tile's dQ (aliases dP) has been read out
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint64_t dq_ = umma_smem_desc(sQ, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                     const uint64_t ddo = umma_smem_desc(sDO, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                     const uint64_t dk = umma_smem_desc(sK, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
@@ -179,7 +179,7 @@ attn_bwd_q_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, box
                 __syncwarp();
                 mbar_wait(ds_full, ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const int nks = NKe / 16;
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t a = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);      // packed bf16 dS
@@ -375,7 +375,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
     float* v_lse = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);   // [256]
     float* v_delta = v_lse + 256;                                   // [256]
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);      // uniform role dispatch (see ptx.cuh elect_one)
     const int lane = threadIdx.x & 31;
     const int nseq = p.B * p.J;
     const int num_prob = PACK ? ((nseq + 3) / 4) * p.H : nseq * p.H;
@@ -401,7 +401,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
     const uint32_t tmem_dP = tmem_base + 256;      // [256,512): dP^T, then dV at [256,256+HD), dK at [256+HD,256+2HD)
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t t_it = 0;
             int ip = 0;
             for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x, ++ip) {
@@ -450,7 +450,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
                 mbar_wait(t_full, ph);
                 mbar_wait(g_empty, ph ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint64_t dk = umma_smem_desc(sK, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                     const uint64_t dv = umma_smem_desc(sV, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                     const uint64_t dq_ = umma_smem_desc(sQ, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
@@ -471,7 +471,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tmQKV_t,   // qkv 5-D, bo
                 __syncwarp();
                 mbar_wait(ps_full, ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const int nks = NKe / 16;
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t a_p = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);     // P^T  : first 16 columns of the chunk

@@ -71,7 +71,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 4-D (
     uint64_t* o_empty = bars + 14;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);      // uniform role dispatch (see ptx.cuh elect_one)
     const int lane = threadIdx.x & 31;
     const int num_groups = (p.nseq + ATS_FRAMES - 1) / ATS_FRAMES;
     const int num_prob = num_groups * p.H;
@@ -100,7 +100,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 4-D (
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             for (int i = 0; i < n_mine; ++i) {
                 const int prob = blockIdx.x + i * gridDim.x;
                 const int h = prob % p.H, g = prob / p.H;
@@ -139,7 +139,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 4-D (
             const int s = i & 1;
             mbar_wait(&qk_full[s], (i >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t sQ = smem_u32(smem + s * Cfg::SET_BYTES);
                 const uint32_t sK = sQ + Cfg::TILE_BYTES;
                 const uint32_t tS = tmem_base + s * Cfg::TMEM_SET;
@@ -172,7 +172,7 @@ attn_s_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,   // spatial : 4-D (
             mbar_wait(&v_full[s], ph);
             mbar_wait(&o_empty[s], ph ^ 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t sV = smem_u32(smem + s * Cfg::SET_BYTES + 2 * Cfg::TILE_BYTES);
                 const uint32_t tS = tmem_base + s * Cfg::TMEM_SET;
                 const uint32_t tO = tS + 128;

@@ -94,7 +94,7 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
     uint64_t* o_empty = bars + 11;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);      // uniform role dispatch (see ptx.cuh elect_one)
     const int lane = threadIdx.x & 31;
     const int num_prob = p.B * p.J * p.H;
     const int num_qt = (p.F + ATT_BM - 1) / ATT_BM;
@@ -124,7 +124,7 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t kv_it = 0, q_it = 0;
             for (int prob = blockIdx.x; prob < num_prob; prob += gridDim.x) {
                 const int h = prob % p.H, j = (prob / p.H) % p.J, b = prob / (p.H * p.J);
@@ -164,7 +164,7 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                 const uint32_t t_ph = t_it & 1;
                 mbar_wait(&q_full[qs], q_ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sQ = smem_u32(smem + Cfg::OFF_Q + qs * Cfg::Q_BYTES);
                     const uint64_t q_hi = umma_smem_desc(sQ, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
                     const uint64_t q_lo = umma_smem_desc(sQ + Cfg::Q_PLANE, 16, 8 * Cfg::SWZ, Cfg::LAYOUT);
@@ -192,7 +192,7 @@ attn_t_tc_kernel(const __grid_constant__ CUtensorMap tmQ,    // box (HD, 1, 128,
                 if (qt == 0) mbar_wait(v_full, kv_ph);
                 mbar_wait(o_empty, t_ph ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const int nks = p.NK / 16;
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t a_hi = tmem_S + 32 * (ks >> 1) + 8 * (ks & 1);

@@ -56,7 +56,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG,   // bf16 3D (N, M, plane)
     uint64_t* done_bar = bars + 2 * WG_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_uniform(threadIdx.x >> 5);      // uniform role dispatch (see ptx.cuh elect_one)
     const int lane = threadIdx.x & 31;
     const int tiles_k = p.K / 256;
     const int tiles = (p.N / 128) * tiles_k;
@@ -86,7 +86,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG,   // bf16 3D (N, M, plane)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nblk; ++kb) {
@@ -111,7 +111,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG,   // bf16 3D (N, M, plane)
         for (int kb = 0; kb < nblk; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
