@@ -182,7 +182,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = pair; tile < num_tiles; tile += npairs) {
-                mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // no memory is handed over: TMEM reads are ordered by the tcgen05 fences
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -279,7 +279,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             if (Cfg::F16C && !kResid) {
                 tc_fence_before();
                 __syncwarp();
-                if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                if (elect_one()) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 continue;
             }
@@ -325,7 +325,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 bb = __ldg(b4 + i);
-                        const float4 x = *reinterpret_cast<const float4*>(buf[b] + lane * 128 + ((i ^ sw128) << 4));
+                        const float4 x = lds_v4f(smem_u32(buf[b]) + lane * 128 + ((i ^ sw128) << 4));
                         v[4 * i + 0] = x.x + rscale * (__uint_as_float(r[4 * i + 0]) + bb.x);
                         v[4 * i + 1] = x.y + rscale * (__uint_as_float(r[4 * i + 1]) + bb.y);
                         v[4 * i + 2] = x.z + rscale * (__uint_as_float(r[4 * i + 2]) + bb.z);
@@ -408,11 +408,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 __syncwarp();
                 uint8_t* xs = buf[b];                                   // fp32 staging (aliases the residual tile)
                 uint8_t* ss = kResid ? bufS : buf[b];                   // split staging
+                const uint32_t xs_row = smem_u32(xs) + lane * 128;     // this lane's 128-byte staging rows
+                const uint32_t ss_row = smem_u32(ss) + lane * 128;
+                const uint32_t ss_row64 = smem_u32(ss) + lane * 64;
                 if (kF32Out) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4*>(xs + lane * 128 + ((i ^ sw128) << 4)) =
-                            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        sts_v4f(xs_row + ((i ^ sw128) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
                 const bool do_split = kSplitOut && (!kResid || p.out_hi != nullptr);   // block-final residuals feed
                 if (do_split && OUT16C) {
@@ -424,16 +426,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                                              v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]};
                         uint32_t h4[4], l2[2], g2[2];
                         split8_f16c(xv, h4, l2, g2);
-                        *reinterpret_cast<uint4*>(ss + lane * 128 + ((g ^ sw128) << 4)) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                        sts_v4(ss_row + ((g ^ sw128) << 4), h4[0], h4[1], h4[2], h4[3]);
                         l8[2 * g] = l2[0]; l8[2 * g + 1] = l2[1];
                         g8[2 * g] = g2[0]; g8[2 * g + 1] = g2[1];
                     }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        *reinterpret_cast<uint4*>(ss + lane * 128 + (((4 + u) ^ sw128) << 4)) =
-                            make_uint4(l8[4 * u], l8[4 * u + 1], l8[4 * u + 2], l8[4 * u + 3]);
-                        *reinterpret_cast<uint4*>(ss + lane * 128 + (((6 + u) ^ sw128) << 4)) =
-                            make_uint4(g8[4 * u], g8[4 * u + 1], g8[4 * u + 2], g8[4 * u + 3]);
+                        sts_v4(ss_row + (((4 + u) ^ sw128) << 4), l8[4 * u], l8[4 * u + 1], l8[4 * u + 2], l8[4 * u + 3]);
+                        sts_v4(ss_row + (((6 + u) ^ sw128) << 4), g8[4 * u], g8[4 * u + 1], g8[4 * u + 2], g8[4 * u + 3]);
                     }
                 } else if (do_split) {                                                 // only the fp32 fusion kernel
                     uint32_t hi[16], lo[16];
@@ -450,11 +450,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        *reinterpret_cast<uint4*>(ss + lane * 64 + ((i ^ sw64) << 4)) =
-                            make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                        sts_v4(ss_row64 + ((i ^ sw64) << 4), hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
                         if (kTwoPlanes)
-                            *reinterpret_cast<uint4*>(ss + 2048 + lane * 64 + ((i ^ sw64) << 4)) =
-                                make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                            sts_v4(ss_row64 + 2048 + ((i ^ sw64) << 4), lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
                     }
                 }
                 fence_proxy_async_smem();
@@ -473,7 +471,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             // slots in fences, profiles/r02a)
             tc_fence_before();
             __syncwarp();
-            if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+            if (elect_one()) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
             if (kResid) {
                 if (row_ok && p.stats_out) {
                     float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;

@@ -277,6 +277,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrive on a barrier of another CTA of the cluster WITHOUT a cluster-scope release.  For hand-overs that publish no
+// generic-proxy memory -- e.g. "this warp's tcgen05.ld's of the accumulator are complete" (ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync): the cluster-scope release compiles to MEMBAR.ALL.CTA + ERRBAR +
+// MEMBAR.ALL.GPU + CCTL.IVALL (an L1 invalidate) in front of the arrive -- 24 % of the stall samples of the F16C qkv GEMM
+// (profiles/r02f), once per warp and tile.  Same form as CUTLASS's ClusterBarrier::arrive(cta_id).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -455,6 +463,19 @@ __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, MUFU.EX2 (rel e
 }
 // explicit shared-window accesses (pointers derived from the aligned dynamic-smem base lose their address space and
 // compile to generic LD / ST)
+// 16-byte shared-memory accesses through 32-bit shared-window addresses (STS.128 / LDS.128 instead of generic ST.E.128 /
+// LD.E.128 with 64-bit address arithmetic when nvcc cannot prove the address space of a staging pointer)
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_v4f(uint32_t saddr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4f(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
