@@ -319,6 +319,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     tmem_ld_wait();
                     if (ch + 1 < NCH) tmem_ld32(t_row + (ch + 1) * 32, racc[(ch + 1) & 1]);
                 }
+                if (ch == NCH - 1) {
+                    // every TMEM read of this accumulator is complete (the last chunk sits in registers) -> hand it back to
+                    // the leader's MMA warp BEFORE the last chunk is processed and stored: each lane fences its
+                    // tcgen05.ld's, the warp converges, ONE lane arrives (a 32-way release-arrive cost 11 % of the
+                    // epilogue's issue slots in fences, profiles/r02a)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                }
                 float v[32];
                 if (kResid) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
@@ -466,12 +475,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     tma_store_commit();
                 }
             }
-            // every TMEM read of this accumulator is complete -> release it to the leader's MMA warp: each lane fences its
-            // tcgen05.ld's, the warp converges, ONE lane arrives (a 32-way release-arrive cost 11 % of the epilogue's issue
-            // slots in fences, profiles/r02a)
-            tc_fence_before();
-            __syncwarp();
-            if (elect_one()) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
             if (kResid) {
                 if (row_ok && p.stats_out) {
                     float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;
