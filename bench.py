@@ -533,7 +533,7 @@ def main():
         "class_share": {n: (cls_ms[n] / prof_total if prof_total else 0.0) for n in names},
     }
 
-    launches = _lib.check(lib.mb_forward_launch_count(st.handle, 1, 0)) * args.steps
+    launches = _lib.check(lib.mb_forward_launch_count(st.handle, 1, args.kernel_flags)) * args.steps
 
     line = {
         "metric": f"sequences/sec DSTformer-{args.model} fwd (Bx{T}x17)",

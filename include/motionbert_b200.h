@@ -80,6 +80,8 @@ typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 #define MB_FLAG_GEMM_1CTA  0x4u   /* TEST ONLY: first-generation 1-CTA tcgen05 GEMM (LSU epilogue)    */
 #define MB_FLAG_ATTN_T_UNPACKED 0x20u /* one-sequence-per-tile temporal kernel even when F <= 32 (both libraries)  */
 #define MB_FLAG_ATTN_BF16X3 0x40u /* F16C mode A/B: qkv as bf16 hi/lo planes + the BF16x3 attention kernels (both)  */
+#define MB_FLAG_MLP_SPLIT   0x100u /* F16C mode: the MLP sublayer as two GEMM launches (fc1, fc2) instead of the fused kernel */
+#define MB_FLAG_MLP_NO_RING 0x200u /* fused MLP kernel: hidden rows indexed by token block (full buffer) instead of the L2 ring */
 
 int mb_version(void);
 const char* mb_last_error(void);

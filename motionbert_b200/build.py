@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmotionbert_b200.so")
 TEST_LIB = os.path.join(HERE, "libmotionbert_b200_test.so")
 SOURCES = ["mb_api.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "attn_t_tc.cuh", "attn_s_tc.cuh", "attn_s_f16c.cuh", "attn_t_f16c.cuh", "attn_bwd_tc.cuh", "backward_kernels.cuh", "loss_kernels.cuh", "optim_kernels.cuh", "simt_kernels.cuh", "wgrad_tc.cuh",
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "mlp_fused.cuh", "attn_t_tc.cuh", "attn_s_tc.cuh", "attn_s_f16c.cuh", "attn_t_f16c.cuh", "attn_bwd_tc.cuh", "backward_kernels.cuh", "loss_kernels.cuh", "optim_kernels.cuh", "simt_kernels.cuh", "wgrad_tc.cuh",
            os.path.join("..", "..", "include", "motionbert_b200.h"), os.path.join("..", "..", "include", "motionbert_b200_test.h")]
 
 

@@ -22,6 +22,7 @@
 #include "backward_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "mlp_fused.cuh"
 #include "loss_kernels.cuh"
 #include "optim_kernels.cuh"
 #include "simt_kernels.cuh"
@@ -201,6 +202,7 @@ static int device_init(int* dev_out, DevInfo* info_out) {
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_SPLIT, false, 8, false>, Gemm2Cfg<2, EPI_LN_SPLIT>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_GELU_SPLIT>, Gemm2Cfg<2, EPI_LN_GELU_SPLIT>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_RESID>, Gemm2Cfg<2, EPI_RESID>::SMEM_BYTES));
+        CUDA_TRY(set_smem(mlp_fused_kernel, MlpFusedCfg::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_LN_TANH_F32>, Gemm2Cfg<2, EPI_LN_TANH_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<2, EPI_BIAS_F32>, Gemm2Cfg<2, EPI_BIAS_F32>::SMEM_BYTES));
         CUDA_TRY(set_smem(gemm2_kernel<1, EPI_LN_TANH_POOL>, Gemm2Cfg<1, EPI_LN_TANH_POOL>::SMEM_BYTES));
@@ -759,6 +761,13 @@ static int build_plan(MbEncoder* e, Plan* P, void* ws, int B, int F) {
 }
 
 // ------------------------------------------------------------------------------------ launches
+// The residual MLP sublayer runs as ONE kernel (mlp_fused.cuh) in the F16C inference arithmetic unless the caller asks
+// for the two-GEMM form (MB_FLAG_MLP_SPLIT: A/B measurements and the bit-exactness test of the fusion).
+static bool mlp_is_fused(const MbDesc& d, uint32_t flags) {
+    return d.math == MB_MATH_F16C && !(flags & MB_FLAG_MLP_SPLIT) && d.hidden / 256 <= MLPF_MAX_NT1 &&
+           !(flags & (MB_FLAG_REF_GEMM | MB_FLAG_GEMM_1CTA));
+}
+
 // Epilogue tensor maps of the 2-CTA kernel (unused ones may be null).
 struct EpiMaps {
     const CUtensorMap* resid = nullptr;   // fp32 residual tile source       (EPI_RESID)
@@ -955,10 +964,10 @@ static int launch_attn(const MbEncoder* e, uint32_t flags, bool temporal, const 
 
 extern "C" int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags) {
     if (!enc) return fail(MB_ERR_NULL, "enc is NULL");
-    (void)flags;
-    // embed + depth * (2 blocks * 4 sublayers * {attn: 3 kernels, mlp: 2 kernels}/2 ... ) + fuse + tail
-    // per block: 2 attention sublayers (qkv gemm, attention, proj gemm) + 2 mlp sublayers (fc1, fc2) = 10
-    return 1 + enc->d.depth * (2 * 10 + 1) + 1 + (want_out ? 1 : 0);
+    // embed + depth * (2 blocks * (2 attention sublayers * 3 kernels [qkv gemm, attention, proj gemm]
+    //                              + 2 MLP sublayers * {1 fused kernel | fc1 gemm + fc2 gemm})  + fuse) + tail (+ head)
+    const int mlp = mlp_is_fused(enc->d, flags) ? 1 : 2;
+    return 1 + enc->d.depth * (2 * (2 * 3 + 2 * mlp) + 1) + 1 + (want_out ? 1 : 0);
 }
 
 // Saved-for-backward region of a training forward: one slot per residual-stream tensor (fp32 x + LN partial statistics).
@@ -1137,6 +1146,29 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
     // one residual MLP sublayer: dst = src + fc2(gelu(fc1(LN(src))))             (DSTformer.py:242,244,247,249)
     auto mlp_sublayer = [&](const LinearPack* L, bool temporal, const ActBuf& src, const ActBuf& dst,
                             bool block_final) -> int {
+        if (mlp_is_fused(d, flags)) {
+            const LinearPack& L1 = L[temporal ? L_FC1_T : L_FC1_S];
+            const LinearPack& L2 = L[temporal ? L_FC2_T : L_FC2_S];
+            MlpParams mp;
+            memset(&mp, 0, sizeof(mp));
+            mp.M = M; mp.C = C; mp.H = d.hidden;
+            mp.c1 = reinterpret_cast<const float*>(pk + L1.off_c);
+            mp.s1 = reinterpret_cast<const float*>(pk + L1.off_s);
+            mp.b2 = reinterpret_cast<const float*>(pk + L2.off_c);
+            mp.stats_in = src.stats; mp.nh_in = ng; mp.ln_dim = static_cast<float>(C); mp.eps = d.eps;
+            mp.row_scale = dp(sub++); mp.J = J;
+            mp.stats_out = block_final ? nullptr : dst.stats;
+            mp.split_out = block_final ? 0 : 1;
+            mp.ring = (flags & MB_FLAG_MLP_NO_RING) ? 0 : 1;
+            const int num_mp = (M + 255) / 256;
+            const int max_pairs = enc->dev.sms / 2;
+            const int grid = 2 * (num_mp < max_pairs ? num_mp : max_pairs);
+            prof_mark(enc, st, PC_GEMM_FC1);
+            mlp_fused_kernel<<<grid, MLPF_THREADS, MlpFusedCfg::SMEM_BYTES, st>>>(
+                src.tmap, L1.tmap2, P.tm_hid, L2.tmap2, P.tm_hid_st, src.tm_x, dst.tm_x, dst.tm_st, mp);
+            LAUNCH_CHECK("mlp_fused_kernel");
+            return MB_OK;
+        }
         GemmParams p = base;
         p.stats_in = src.stats;
         p.out_hi = P.hid;
