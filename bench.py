@@ -490,7 +490,10 @@ def main():
     n_cls = (ctypes.c_int * 9)()
     _lib.check(lib.mb_profile_read(st.handle, ms_cls, n_cls))
     _lib.check(lib.mb_profile_enable(st.handle, 0))
-    names = ["gemm_qkv", "gemm_fc1", "gemm_resid", "gemm_tail", "attn_t", "attn_s", "embed", "fuse", "head"]
+    # class 1 holds the MLP sublayer's first launch: the fused fc1+GELU+fc2+residual kernel (F16C default: then
+    # "gemm_resid" is the 20 output projections only), or the fc1 GEMM of the two-GEMM form (bf16 modes / --kernel-flags 0x100)
+    mlp_fused = args.math == "f16c" and not (args.kernel_flags & _lib.MB_FLAG_MLP_SPLIT)
+    names = ["gemm_qkv", "mlp_fused" if mlp_fused else "gemm_fc1", "gemm_resid", "gemm_tail", "attn_t", "attn_s", "embed", "fuse", "head"]
     cls_ms = {n: float(ms_cls[i]) / args.steps for i, n in enumerate(names)}
     cls_n = {n: int(n_cls[i]) // args.steps for i, n in enumerate(names)}
     gemm_ms = sum(cls_ms[n] for n in names[:4])
@@ -517,10 +520,14 @@ def main():
             except Exception:
                 pass
     roofline = {
-        "bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05, all 4 epilogue variants)",
+        "bound": "tensor", "kernel": ("gemm2_kernel (qkv / proj / tail) + mlp_fused_kernel (fc1+GELU+fc2+residual), 2-CTA tcgen05"
+                                      if mlp_fused else "gemm2_kernel (2-CTA tcgen05, all 4 epilogue variants)"),
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         "traffic": traffic, "traffic_source": traffic_src,
-        "algorithmic_dram_bytes_per_launch": (8.66e9 + 8.66e9 + 6.50e9 + 10.83e9) / 4 * (B / 256.0) if args.model == "base" and T == 243 else None,
+        # per launch at B=256: qkv 8.66 GB, proj 8.66 GB; MLP: fused 8.66 GB (x rows + fp32 residual in, fp32 + rows out; the
+        # hidden activation stays in L2) | two-GEMM form fc1 6.50 GB + fc2 10.83 GB
+        "algorithmic_dram_bytes_per_launch": ((8.66e9 if mlp_fused else (8.66e9 + 8.66e9 + 6.50e9 + 10.83e9) / 4) * (B / 256.0)
+                                              if args.model == "base" and T == 243 else None),
         "peak_source": peaks["_source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "mma_passes": passes,
         "note": f"achieved = algorithmic GEMM FLOPs per launch ({gemm_flop / max(gemm_launches, 1) / 1e9:.1f} GFLOP avg over "

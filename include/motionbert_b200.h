@@ -82,6 +82,7 @@ typedef struct MbEncoder MbEncoder;   /* opaque host-side handle */
 #define MB_FLAG_ATTN_BF16X3 0x40u /* F16C mode A/B: qkv as bf16 hi/lo planes + the BF16x3 attention kernels (both)  */
 #define MB_FLAG_MLP_SPLIT   0x100u /* F16C mode: the MLP sublayer as two GEMM launches (fc1, fc2) instead of the fused kernel */
 #define MB_FLAG_MLP_NO_RING 0x200u /* fused MLP kernel: hidden rows indexed by token block (full buffer) instead of the L2 ring */
+#define MB_FLAG_MLP_NO_HINT 0x800u /* fused MLP kernel: no L2::evict_last on the hidden stores / loads */
 
 int mb_version(void);
 const char* mb_last_error(void);

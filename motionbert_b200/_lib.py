@@ -22,6 +22,7 @@ MB_FLAG_REF_ATTN_S = 0x8
 MB_FLAG_ATTN_T_UNPACKED = 0x20
 MB_FLAG_ATTN_BF16X3 = 0x40
 MB_FLAG_MLP_SPLIT = 0x100      # F16C: the MLP sublayer as two GEMM launches instead of the fused kernel (A/B, tests)
+MB_FLAG_MLP_NO_HINT = 0x800    # fused MLP: no L2::evict_last on the hidden stores / loads
 MB_FLAG_MLP_NO_RING = 0x200    # fused MLP: hidden rows indexed by token block instead of the per-pair L2 ring
 
 # every symbol include/motionbert_b200.h declares (TEST_EXPORTS: include/motionbert_b200_test.h, test library only)

@@ -1160,6 +1160,7 @@ static int forward_impl(MbEncoder* enc, const void* packed, const float* x, floa
             mp.stats_out = block_final ? nullptr : dst.stats;
             mp.split_out = block_final ? 0 : 1;
             mp.ring = (flags & MB_FLAG_MLP_NO_RING) ? 0 : 1;
+            mp.l2_hint = (flags & MB_FLAG_MLP_NO_HINT) ? 0 : 1;
             const int num_mp = (M + 255) / 256;
             const int max_pairs = enc->dev.sms / 2;
             const int grid = 2 * (num_mp < max_pairs ? num_mp : max_pairs);

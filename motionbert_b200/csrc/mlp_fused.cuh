@@ -7,23 +7,24 @@
 // launches move.  A single 128-row tile cannot hold the fc2 accumulator (C fp32 columns) AND a hidden accumulator in
 // the 512 TMEM columns at C = 512, so the fusion here is a PANEL schedule inside one persistent launch instead:
 //
-//   * a CTA pair owns one 256-row token block at a time and walks   fc1 tile 0 .. NT1-1   (256 hidden columns each,
-//     K = C)   then   fc2 tile 0 .. NT2-1   (256 output columns each, K = hidden)   through the SAME TMA ring / UMMA
-//     issue path / two TMEM accumulators as gemm2_kernel: the mainloop never drains between the two linears;
-//   * the fc1 epilogue (LayerNorm fold, GELU, F16C encode) stores its hidden chunk by TMA into a per-pair slot of a small
-//     ring (pairs x 256 rows x hidden x 4 B = 77 MB for 74 pairs): the slot is rewritten every token block, stays in the
-//     126 MB L2 and never has to reach HBM as a 4.33 GB stream;
-//   * the producer warp of each CTA reloads ITS OWN 128 hidden rows as the fc2 A operand; the only dependency is
-//     intra-CTA: hready[n] (an mbarrier, one arrival per epilogue warp) is signalled once every store of fc1 tile n has
-//     completed (cp.async.bulk.wait_group, then a proxy fence), and gates the 8 K blocks of fc2 that read those 256
-//     hidden columns.  fc2 tile 0 therefore starts on hidden columns 0..767 while the epilogue of the last fc1 tile is
-//     still running; only its last quarter waits for it;
-//   * WAR on the ring slot is excluded by the pipeline itself: the first hidden store of token block k+1 follows the
-//     tfull commit of its fc1 tile 0, which follows (in-order tensor pipe) every MMA -- hence every operand load -- of
-//     token block k's fc2 tiles.
+//   * a CTA pair owns 256-row token blocks and walks their   fc1 tiles 0 .. NT1-1   (256 hidden columns each, K = C)
+//     and   fc2 tiles 0 .. NT2-1   (256 output columns each, K = hidden)   through the SAME TMA ring / UMMA issue path /
+//     two TMEM accumulators as gemm2_kernel: the mainloop never drains between the two linears;
+//   * the fc1 epilogue (LayerNorm fold, GELU, F16C encode) stores its hidden chunk by TMA; the producer warp of each CTA
+//     reloads ITS OWN 128 hidden rows as the fc2 A operand.  The only dependency is intra-CTA: hready[set][n] (an
+//     mbarrier, one arrival per epilogue warp) is signalled once every store of fc1 tile n has completed
+//     (cp.async.bulk.wait_group: both sides of the hand-over are async-proxy accesses of L2) and gates the 8 K blocks of
+//     fc2 that read those 256 hidden columns;
+//   * tile order: block by block, fc1 0..NT1-1 then fc2 0..NT2-1.  The hidden rows live in a per-pair slot of a small
+//     ring (pairs x 256 rows x hidden x 4 B = 77 MB for 74 pairs, L2::evict_last) that is rewritten every token block.
+//     fc2 tile 0 starts on hidden columns 0..767 while the epilogue of the last fc1 tile still runs; only its last
+//     quarter waits for it.  (Measured and dropped, profiles/README.md round 2: interleaving the fc2 tiles of block k-1
+//     with the fc1 tiles of block k -- better MMA/epilogue overlap on paper, 5 % slower at the board's power cap.)
+//     WAR on a ring slot is excluded by the pipeline itself: the first hidden store of token block k+1 follows the tfull
+//     commit of its fc1 tile 0, which follows (in-order tensor pipe) every MMA -- hence every operand load -- of token
+//     block k's fc2 tiles.
 //
-// The fc2 epilogue is gemm2_kernel's EPI_RESID (residual tile in by TMA, fp32 + F16C rows + LN statistics out); its
-// first residual chunk -- the MLP input itself -- is prefetched at the start of the token block.
+// The fc2 epilogue is gemm2_kernel's EPI_RESID (residual tile in by TMA, fp32 + F16C rows + LN statistics out).
 // Arithmetic is identical to the split form instruction for instruction (same MMA order per K block, same epilogue
 // math), so the two forms agree BIT FOR BIT: tests/test_gpu_mlp_fused.py.
 #pragma once
@@ -44,6 +45,7 @@ struct MlpParams {
     float* stats_out;          // LN partial statistics of x' [M][C/128][3], or null (block-final sublayer)
     int split_out;             // also emit x' as F16C rows (tmS)
     int ring;                  // hidden rows indexed by CTA pair (L2-resident ring) instead of by token block
+    int l2_hint;               // hidden stores / loads carry L2::evict_last
 };
 
 constexpr int MLPF_STAGES = 4;
@@ -58,10 +60,27 @@ struct MlpFusedCfg {
     static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 };
 
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;      // createpolicy.fractional.L2::evict_last, fraction 1.0
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_done() {     // <= N groups may still be in flight (writes included)
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* smem_src, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta_hint(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr,
+                                                      int c0, int c1, int c2, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+        : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLPF_THREADS, 1)
@@ -95,6 +114,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
     const int num_mp = (p.M + 255) / 256;
     const int NT1 = p.H / 256, NT2 = p.C / 256;
     const int KB1 = p.C / 32, KB2 = p.H / 32;
+    const int rounds = pair < num_mp ? (num_mp - pair + npairs - 1) / npairs : 0;   // token blocks of this pair
+    const uint64_t hpol = p.l2_hint ? L2_EVICT_LAST : L2_EVICT_NORMAL;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2);
@@ -117,42 +138,43 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // hidden rows of this pair's k-th token block (global block index mblk)
+    auto hidden_row0 = [&](int mblk) { return (p.ring ? pair : mblk) * 256 + static_cast<int>(rank) * 128; };
+
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
-        uint32_t phase = 0, hphase = 0;
-        auto load_stage = [&](const CUtensorMap* ma, const CUtensorMap* mb_, int kb, int a_row, int b_row) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
-                uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-                uint8_t* sB = sA + Cfg::A_BYTES;
-                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                tma_load_3d_2cta(sA, ma, full_leader, kb * 64, a_row, 0);
-                tma_load_3d_2cta(sB, mb_, full_leader, kb * 64, b_row, 0);
-            }
-            __syncwarp();
-            if (++stage == MLPF_STAGES) { stage = 0; phase ^= 1; }
-        };
-        for (int mblk = pair; mblk < num_mp; mblk += npairs) {
-            const int a_row = mblk * 256 + static_cast<int>(rank) * 128;
-            const int h_row = (p.ring ? pair : mblk) * 256 + static_cast<int>(rank) * 128;
-            for (int n = 0; n < NT1; ++n) {
+        uint32_t phase = 0;
+        for (int k = 0; k < rounds; ++k) {                         // k: which of this pair's token blocks
+            for (int e = 0; e < NT1 + NT2; ++e) {
+                const bool is_fc2 = e >= NT1;
+                const int n = is_fc2 ? e - NT1 : e;
+                const int mblk = pair + k * npairs;
+                const int a_row = is_fc2 ? hidden_row0(mblk) : mblk * 256 + static_cast<int>(rank) * 128;
                 const int b_row = n * 256 + static_cast<int>(rank) * 128;
-                for (int kb = 0; kb < KB1; ++kb) load_stage(&tmA1, &tmB1, kb, a_row, b_row);
-            }
-            for (int n = 0; n < NT2; ++n) {
-                const int b_row = n * 256 + static_cast<int>(rank) * 128;
-                for (int kb = 0; kb < KB2; ++kb) {
-                    if (n == 0 && (kb & 7) == 0) {
+                const CUtensorMap* ma = is_fc2 ? &tmA2 : &tmA1;
+                const CUtensorMap* mw = is_fc2 ? &tmB2 : &tmB1;
+                const int nkb = is_fc2 ? KB2 : KB1;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (is_fc2 && n == 0 && (kb & 7) == 0) {
                         // hidden columns [32 kb, 32 kb + 256) = fc1 tile kb/8 of my own 128 rows: stores complete?
-                        mbar_wait(&hready[kb >> 3], hphase);
-                        fence_proxy_async_all();
+                        mbar_wait(&hready[kb >> 3], k & 1);
+                        fence_proxy_async_global();
                     }
-                    load_stage(&tmA2, &tmB2, kb, h_row, b_row);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one()) {
+                        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                        uint8_t* sB = sA + Cfg::A_BYTES;
+                        const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        if (is_fc2) tma_load_3d_2cta_hint(sA, ma, full_leader, kb * 64, a_row, 0, hpol);
+                        else tma_load_3d_2cta(sA, ma, full_leader, kb * 64, a_row, 0);
+                        tma_load_3d_2cta(sB, mw, full_leader, kb * 64, b_row, 0);
+                    }
+                    __syncwarp();
+                    if (++stage == MLPF_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-            hphase ^= 1;
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -163,9 +185,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int mblk = pair; mblk < num_mp; mblk += npairs) {
-                for (int t = 0; t < NT1 + NT2; ++t) {
-                    const int nkb = t < NT1 ? KB1 : KB2;
+            for (int k = 0; k < rounds; ++k) {
+                for (int e = 0; e < NT1 + NT2; ++e) {
+                    const int nkb = e >= NT1 ? KB2 : KB1;
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * 256;
@@ -204,10 +226,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
         uint64_t* my_rbar = rbar + 2 * ew;
         const int ngrp_out = p.C / STATS_GROUP;
         const uint32_t sw128 = static_cast<uint32_t>(lane & 7);          // SWIZZLE_128B: chunk16 ^= row % 8
-        uint32_t rc = 0;    // residual chunks consumed: buffer parity / rbar phase (4 NT2 per token block: rc & 1 == 0 at its start)
+        uint32_t rc = 0;    // residual chunks consumed: buffer parity / rbar phase (4 per fc2 tile: rc & 1 == 0 at every tile start)
         uint32_t hc = 0;    // hidden chunks stored: staging parity (buf[1] / bufS)
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint64_t* pend = nullptr;    // hready barrier of the last fc1 tile, not yet signalled (its stores may be in flight)
+        int k_stats = -1;            // token block whose LN statistics (mean, rstd) are loaded
+        float mean = 0.f, rstd = 1.f;
 
         // one F16C block per row into a SWIZZLE_128B staging tile: 16-byte units 0..3 = 32 f16, 4..5 = 32 lo8, 6..7 = 32 hi8
         auto stage_f16c = [&](const float (&v)[32], uint32_t ss_row) {
@@ -229,163 +254,168 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
             }
         };
 
-        for (int mblk = pair; mblk < num_mp; mblk += npairs) {
-            const int rowb = mblk * 256 + static_cast<int>(rank) * 128 + quad * 32;
-            const int hrowb = (p.ring ? pair : mblk) * 256 + static_cast<int>(rank) * 128 + quad * 32;
-            const int row = rowb + lane;
-            const bool row_ok = row < p.M;
-            float mean = 0.f, rstd = 1.f, rscale = 1.f;
-            if (row_ok) {
-                ln_row_stats(p.stats_in + static_cast<size_t>(row) * p.nh_in * 3, p.nh_in, p.ln_dim, p.eps, mean, rstd);
-                if (p.row_scale) rscale = p.row_scale[row / p.J];
-            }
-            // first residual chunk of this token block (the MLP input itself: available now) -> buf[rc & 1]; the fc1
-            // epilogues below stage in the other buffer and in bufS
-            if (elect_one()) {
-                tma_store_wait_read<0>();                                  // the previous token block's stores have read all staging
-                mbar_arrive_expect_tx(&my_rbar[rc & 1], 4096);
-                tma_load_2d(buf[rc & 1], &tmR, &my_rbar[rc & 1], half * 128, rowb);
-            }
-            __syncwarp();
-
-            // ---------------- fc1 tiles: h = gelu(rstd (acc - mean s) + c) -> F16C rows of the hidden ring
-            for (int n = 0; n < NT1; ++n) {
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
+        for (int k = 0; k < rounds; ++k) {
+            for (int e = 0; e < NT1 + NT2; ++e) {
+                const bool is_fc2 = e >= NT1;
+                const int n = is_fc2 ? e - NT1 : e;
+                const int mblk = pair + k * npairs;
+                const int rowb = mblk * 256 + static_cast<int>(rank) * 128 + quad * 32;
+                const int row = rowb + lane;
+                const bool row_ok = row < p.M;
                 const uint32_t t_row = tmem_base + acc * 256 + half * 128 + (static_cast<uint32_t>(quad * 32) << 16);
-                uint32_t racc[2][32];
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch, ++hc) {
-                    const int col0 = n * 256 + half * 128 + ch * 32;
-                    if (elect_one()) {
-                        if (ch == 1 && n > 0) {
-                            // every store group of fc1 tile n-1 has COMPLETED (only this tile's chunk 0 may be in flight):
-                            // its 32 rows x 128 hidden columns are in L2 for the producer's reload
-                            tma_store_wait_done<1>();
-                            fence_proxy_async_all();
-                            mbar_arrive(&hready[n - 1]);
-                        } else {
-                            tma_store_wait_read<1>();                      // group hc-2 no longer reads this staging buffer
-                        }
+
+                if (!is_fc2) {
+                    // ---------------- fc1 tile: h = gelu(rstd (acc - mean s) + c) -> F16C rows of the hidden buffer
+                    if (k != k_stats) {
+                        mean = 0.f; rstd = 1.f;
+                        if (row_ok) ln_row_stats(p.stats_in + static_cast<size_t>(row) * p.nh_in * 3, p.nh_in, p.ln_dim, p.eps, mean, rstd);
+                        k_stats = k;
                     }
-                    uint32_t (&r)[32] = racc[ch & 1];
-                    if (ch == 0) tmem_ld32(t_row, racc[0]);
-                    tmem_ld_wait();
-                    if (ch + 1 < 4) tmem_ld32(t_row + (ch + 1) * 32, racc[(ch + 1) & 1]);
-                    if (ch == 3) {
-                        tc_fence_before();
+                    const int hrowb = hidden_row0(mblk) + quad * 32;
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    uint32_t racc[2][32];
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch, ++hc) {
+                        const int col0 = n * 256 + half * 128 + ch * 32;
+                        if (elect_one()) {
+                            if (ch == 1 && pend) {
+                                // every store group of the previous fc1 tile has COMPLETED (only this tile's chunk 0 may be
+                                // in flight): its 32 rows x 128 hidden columns are in L2 for the producer's reload
+                                tma_store_wait_done<1>();
+                                mbar_arrive(pend);
+                            } else if (ch == 0) {
+                                tma_store_wait_read<0>();                  // the previous tile (possibly an fc2 tile, whose groups
+                                                                           // read buf AND bufS) has released all staging
+                            } else {
+                                tma_store_wait_read<1>();                  // group hc-2 no longer reads this staging buffer
+                            }
+                        }
+                        if (ch == 1) pend = nullptr;
+                        uint32_t (&r)[32] = racc[ch & 1];
+                        if (ch == 0) tmem_ld32(t_row, racc[0]);
+                        tmem_ld_wait();
+                        if (ch + 1 < 4) tmem_ld32(t_row + (ch + 1) * 32, racc[(ch + 1) & 1]);
+                        if (ch == 3) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (elect_one()) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                        }
+                        float v[32];
+                        {
+                            const float4* c4 = reinterpret_cast<const float4*>(p.c1 + col0);
+                            const float4* s4 = reinterpret_cast<const float4*>(p.s1 + col0);
+                            const float ms = -mean * rstd;
+                            const float2 ms2 = make_float2(ms, ms), rstd2 = make_float2(rstd, rstd);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 c = __ldg(c4 + i);
+                                const float4 s = __ldg(s4 + i);
+                                float2 a = __ffma2_rn(rstd2, make_float2(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1])),
+                                                      __ffma2_rn(ms2, make_float2(s.x, s.y), make_float2(c.x, c.y)));
+                                float2 b = __ffma2_rn(rstd2, make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
+                                                      __ffma2_rn(ms2, make_float2(s.z, s.w), make_float2(c.z, c.w)));
+                                a = gelu_erf2(a);
+                                b = gelu_erf2(b);
+                                v[4 * i + 0] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+                            }
+                        }
+                        __syncwarp();                                      // the elected lane has seen the older store group retire
+                        uint8_t* ss = (hc & 1) ? bufS : buf[(rc & 1) ^ 1];
+                        stage_f16c(v, smem_u32(ss) + lane * 128);
+                        fence_proxy_async_smem();
                         __syncwarp();
-                        if (elect_one()) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-                    }
-                    float v[32];
-                    {
-                        const float4* c4 = reinterpret_cast<const float4*>(p.c1 + col0);
-                        const float4* s4 = reinterpret_cast<const float4*>(p.s1 + col0);
-                        const float ms = -mean * rstd;
-                        const float2 ms2 = make_float2(ms, ms), rstd2 = make_float2(rstd, rstd);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 c = __ldg(c4 + i);
-                            const float4 s = __ldg(s4 + i);
-                            float2 a = __ffma2_rn(rstd2, make_float2(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1])),
-                                                  __ffma2_rn(ms2, make_float2(s.x, s.y), make_float2(c.x, c.y)));
-                            float2 b = __ffma2_rn(rstd2, make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])),
-                                                  __ffma2_rn(ms2, make_float2(s.z, s.w), make_float2(c.z, c.w)));
-                            a = gelu_erf2(a);
-                            b = gelu_erf2(b);
-                            v[4 * i + 0] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+                        if (elect_one()) {
+                            tma_store_2d_hint(&tmH, ss, col0 * 2, hrowb, hpol);
+                            tma_store_commit();
                         }
                     }
-                    __syncwarp();                                          // the elected lane has seen the older store group retire
-                    uint8_t* ss = (hc & 1) ? bufS : buf[(rc & 1) ^ 1];
-                    stage_f16c(v, smem_u32(ss) + lane * 128);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        tma_store_2d(&tmH, ss, col0 * 2, hrowb);
-                        tma_store_commit();
+                    pend = &hready[n];
+                    if (n == NT1 - 1) {
+                        // the last hidden columns gate the tail of fc2 tile 0, whose epilogue is the next thing this warp
+                        // does: signal now
+                        if (elect_one()) {
+                            tma_store_wait_done<0>();
+                            mbar_arrive(pend);
+                        }
+                        __syncwarp();
+                        pend = nullptr;
                     }
-                }
-                if (n == NT1 - 1) {
-                    // the last hidden columns gate the tail of fc2 tile 0, whose epilogue comes after this point: signal now
+                } else {
+                    // ---------------- fc2 tile: x' = x + rowscale (acc + b2); fp32 + F16C rows + LN statistics
+                    float rscale = 1.f;
+                    if (row_ok && p.row_scale) rscale = p.row_scale[row / p.J];
+                    // first residual chunk of this tile -> buf[rc & 1] (lands while this warp waits for the accumulator)
                     if (elect_one()) {
-                        tma_store_wait_done<0>();
-                        fence_proxy_async_all();
-                        mbar_arrive(&hready[n]);
+                        tma_store_wait_read<0>();                          // older store groups have read all staging
+                        mbar_arrive_expect_tx(&my_rbar[rc & 1], 4096);
+                        tma_load_2d(buf[rc & 1], &tmR, &my_rbar[rc & 1], n * 256 + half * 128, rowb);
                     }
                     __syncwarp();
-                }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-            }
-
-            // ---------------- fc2 tiles: x' = x + rowscale (acc + b2); fp32 + F16C rows + LN statistics
-            for (int n = 0; n < NT2; ++n) {
-                float st_shift = 0.f, st_sum = 0.f, st_sq = 0.f;
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
-                const uint32_t t_row = tmem_base + acc * 256 + half * 128 + (static_cast<uint32_t>(quad * 32) << 16);
-                uint32_t r[32];
+                    float st_shift = 0.f, st_sum = 0.f, st_sq = 0.f;
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    uint32_t r[32];
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch, ++rc) {
-                    const int b = rc & 1;
-                    const int col0 = n * 256 + half * 128 + ch * 32;
-                    mbar_wait(&my_rbar[b], (rc >> 1) & 1);               // residual chunk landed in buf[b]
-                    if (elect_one()) {
-                        tma_store_wait_read<0>();                          // older groups no longer read buf[b^1] / bufS
-                        int nn = n, nc = ch + 1;
-                        if (nc == 4) { nc = 0; nn = n + 1; }
-                        if (nn < NT2) {
+                    for (int ch = 0; ch < 4; ++ch, ++rc) {
+                        const int b = rc & 1;
+                        const int col0 = n * 256 + half * 128 + ch * 32;
+                        mbar_wait(&my_rbar[b], (rc >> 1) & 1);           // residual chunk landed in buf[b]
+                        if (ch < 3 && elect_one()) {
+                            tma_store_wait_read<0>();                      // older groups no longer read buf[b^1] / bufS
                             mbar_arrive_expect_tx(&my_rbar[b ^ 1], 4096);
-                            tma_load_2d(buf[b ^ 1], &tmR, &my_rbar[b ^ 1], nn * 256 + half * 128 + nc * 32, rowb);
+                            tma_load_2d(buf[b ^ 1], &tmR, &my_rbar[b ^ 1], col0 + 32, rowb);
                         }
-                    }
-                    tmem_ld32(t_row + ch * 32, r);
-                    tmem_ld_wait();
-                    if (ch == 3) {
-                        tc_fence_before();
+                        tmem_ld32(t_row + ch * 32, r);
+                        tmem_ld_wait();
+                        if (ch == 3) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (elect_one()) {
+                                mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                                tma_store_wait_read<0>();                  // (no prefetch this chunk) bufS is free again
+                            }
+                        }
+                        float v[32];
+                        {
+                            const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 bb = __ldg(b4 + i);
+                                const float4 x = lds_v4f(smem_u32(buf[b]) + lane * 128 + ((i ^ sw128) << 4));
+                                v[4 * i + 0] = x.x + rscale * (__uint_as_float(r[4 * i + 0]) + bb.x);
+                                v[4 * i + 1] = x.y + rscale * (__uint_as_float(r[4 * i + 1]) + bb.y);
+                                v[4 * i + 2] = x.z + rscale * (__uint_as_float(r[4 * i + 2]) + bb.z);
+                                v[4 * i + 3] = x.w + rscale * (__uint_as_float(r[4 * i + 3]) + bb.w);
+                            }
+                            if (ch == 0) st_shift = v[0];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float d = v[i] - st_shift;
+                                st_sum += d;
+                                st_sq = fmaf(d, d, st_sq);
+                            }
+                        }
+                        __syncwarp();                                      // all lanes have consumed buf[b]; older stores retired
+                        const uint32_t xs_row = smem_u32(buf[b]) + lane * 128;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            sts_v4f(xs_row + ((i ^ sw128) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        if (p.split_out) stage_f16c(v, smem_u32(bufS) + lane * 128);
+                        fence_proxy_async_smem();
                         __syncwarp();
-                        if (elect_one()) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-                    }
-                    float v[32];
-                    {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col0);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 bb = __ldg(b4 + i);
-                            const float4 x = lds_v4f(smem_u32(buf[b]) + lane * 128 + ((i ^ sw128) << 4));
-                            v[4 * i + 0] = x.x + rscale * (__uint_as_float(r[4 * i + 0]) + bb.x);
-                            v[4 * i + 1] = x.y + rscale * (__uint_as_float(r[4 * i + 1]) + bb.y);
-                            v[4 * i + 2] = x.z + rscale * (__uint_as_float(r[4 * i + 2]) + bb.z);
-                            v[4 * i + 3] = x.w + rscale * (__uint_as_float(r[4 * i + 3]) + bb.w);
-                        }
-                        if (ch == 0) st_shift = v[0];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float d = v[i] - st_shift;
-                            st_sum += d;
-                            st_sq = fmaf(d, d, st_sq);
+                        if (elect_one()) {
+                            tma_store_2d(&tmX, buf[b], col0, rowb);
+                            if (p.split_out) tma_store_2d(&tmS, bufS, col0 * 2, rowb);
+                            tma_store_commit();
                         }
                     }
-                    __syncwarp();                                          // all lanes have consumed buf[b]; older stores retired
-                    const uint32_t xs_row = smem_u32(buf[b]) + lane * 128;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        sts_v4f(xs_row + ((i ^ sw128) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    if (p.split_out) stage_f16c(v, smem_u32(bufS) + lane * 128);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        tma_store_2d(&tmX, buf[b], col0, rowb);
-                        if (p.split_out) tma_store_2d(&tmS, bufS, col0 * 2, rowb);
-                        tma_store_commit();
+                    if (row_ok && p.stats_out) {
+                        float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n * 2 + half) * 3;
+                        so[0] = st_shift;
+                        so[1] = st_sum;
+                        so[2] = st_sq;
                     }
-                }
-                if (row_ok && p.stats_out) {
-                    float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n * 2 + half) * 3;
-                    so[0] = st_shift;
-                    so[1] = st_sum;
-                    so[2] = st_sq;
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;

@@ -18,6 +18,8 @@ import os
 import math
 from collections import OrderedDict
 
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -82,6 +84,7 @@ class _DeviceState:
         self.pinned = set()          # workspace keys baked into a captured CUDA graph (make_graphed)
         self.zeros = {}
         self.side_stream = None
+        self.graphs = {}             # (B, F, return_rep, kernel_flags) -> auto-captured inference graph (DSTformer._auto_graph)
 
     def __del__(self):
         try:
@@ -150,6 +153,8 @@ class DSTformer(nn.Module):
         self.math_mode = _lib.MB_MATH_F16C
         self.train_math_mode = _lib.MB_MATH_BF16X3
         self._kernel_flags = 0
+        # forwards of at most this many tokens (B*F*J) are CUDA-graphed automatically in inference (0 / MB_AUTO_GRAPH=0: never)
+        self.auto_graph_max_tokens = 0 if os.environ.get("MB_AUTO_GRAPH", "1") == "0" else 16384
         self._lib_loader = _lib.load               # tests may switch to the test twin (use_test_library)
         # shared (by reference) between nn.DataParallel replicas: keyed by device index
         self._dev_state = {}
@@ -563,5 +568,52 @@ class DSTformer(nn.Module):
         if needs_grad:
             params = [p for p in self._ordered_params() if p is not None]
             return DSTformerFunction.apply(self, x, bool(return_rep), dp_scale, *params)
+        if dp_scale is None and self.auto_graph_max_tokens > 0 and B * F * J <= self.auto_graph_max_tokens:
+            res = self._auto_graph(x, bool(return_rep))
+            if res is not None:
+                return res
         out, rep = self._launch(x, not return_rep, bool(return_rep), dp_scale)
         return rep if return_rep else out
+
+    # ------------------------------------------------------------------ launch-bound shapes: automatic CUDA-graph replay
+    AUTO_GRAPH_AFTER = 2         # eager calls of one (B, F, output kind) before its forward is captured
+    AUTO_GRAPH_MAX = 8           # captured shapes per device
+
+    def _auto_graph(self, x, return_rep):
+        """Inference forwards of small clips (B*F*J <= auto_graph_max_tokens, e.g. infer_wild's B=1 windows) are bound by
+        the ~90 kernel launches, not by the kernels: from the third call of a shape on, the forward is captured into a CUDA
+        graph and replayed (one launch).  Returns None when this call has to run eagerly.  The graph bakes in the pointers
+        of the workspace and of the packed weights: both are pinned by the cache entry, and an entry dies as soon as the
+        parameters change (`pack_key`).  The result is a fresh tensor (a copy of the graph's static output)."""
+        if torch.cuda.is_current_stream_capturing() or threading.current_thread() is not threading.main_thread():
+            return None
+        device = x.device
+        B, F = int(x.shape[0]), int(x.shape[1])
+        with torch.cuda.device(device):
+            st = self._state_for(device)
+            self._ensure_packed(st, device, torch.cuda.current_stream(device).cuda_stream)
+            key = (B, F, return_rep, self._kernel_flags)
+            ent = st.graphs.get(key)
+            if ent is not None and ent.get("graph") is not None and ent["pack_key"] != st.pack_key:
+                st.pinned.discard((B, F))
+                ent = None                                     # parameters changed: capture again after the warm-up calls
+            if ent is None:
+                if len(st.graphs) >= self.AUTO_GRAPH_MAX and key not in st.graphs:
+                    return None
+                st.graphs[key] = {"hits": 1, "graph": None}
+                return None
+            if ent["graph"] is None:
+                ent["hits"] += 1
+                if ent["hits"] <= self.AUTO_GRAPH_AFTER or (B, F) not in st.workspaces:
+                    return None                                # (workspace evicted meanwhile: one more eager call)
+                static_x = torch.empty_like(x)
+                static_x.copy_(x)
+                st.pinned.add((B, F))
+                graph = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out, rep = self._launch(static_x, not return_rep, return_rep, None)
+                ent.update(graph=graph, x=static_x, y=rep if return_rep else out, pack_key=st.pack_key,
+                           keep=(st.workspaces[(B, F)], st.packed))
+            ent["x"].copy_(x, non_blocking=True)
+            ent["graph"].replay()
+            return ent["y"].clone()

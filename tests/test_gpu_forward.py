@@ -330,3 +330,35 @@ def test_two_streams_and_odd_batch_tail(cuda_device):
     with torch.no_grad():
         o5 = m(torch.cat([xt, xt[:2]], 0))                      # B = 5
     assert np.array_equal(o5[:3].cpu().numpy(), ref) and np.array_equal(o5[3:].cpu().numpy(), ref[:2])
+
+
+def test_small_shapes_are_graphed_automatically_and_track_parameter_updates(cuda_device):
+    """Launch-bound inference shapes: from the third call on the forward is a CUDA-graph replay (one launch instead of
+    ~90) with bit-identical results; a parameter update drops the captured graph (no stale weights)."""
+    cfg, P, x, g = load_case("lite_b2_f27")
+    m = build_module(cfg, P, cuda_device)
+    xt = torch.from_numpy(x).to(cuda_device)
+    m.auto_graph_max_tokens = 0
+    with torch.no_grad():
+        ref = m(xt).clone()
+        m.auto_graph_max_tokens = 16384
+        outs = [m(xt) for _ in range(5)]
+        st = m._state_for(cuda_device)
+        ent = st.graphs[(2, 27, False, 0)]
+        assert ent["graph"] is not None and (2, 27) in st.pinned
+        assert all(torch.equal(o, ref) for o in outs) and outs[3].data_ptr() != outs[4].data_ptr()
+        x2 = torch.from_numpy(O.make_input(2, 27, cfg.num_joints, 77)).to(cuda_device)
+        m.auto_graph_max_tokens = 0
+        ref2 = m(x2).clone()
+        m.auto_graph_max_tokens = 16384
+        assert torch.equal(m(x2), ref2)                                   # replay on new input data
+        m.head.bias.add_(0.25)                                            # in-place update: _version changes
+        o_new = m(xt)
+        assert torch.allclose(o_new, ref + 0.25, atol=1e-6) and not torch.equal(o_new, ref)
+        for _ in range(3):
+            o_new2 = m(xt)                                                # re-captured with the new weights
+        assert torch.equal(o_new2, o_new) and st.graphs[(2, 27, False, 0)]["graph"] is not None
+        big = torch.from_numpy(O.make_input(8, 243, cfg.num_joints, 5)).to(cuda_device)   # 33048 tokens: never graphed
+        for _ in range(4):
+            m(big)
+        assert st.graphs.get((8, 243, False, 0)) is None
