@@ -269,7 +269,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
             if (kResid) {
                 if (row_ok && p.row_scale) rscale = p.row_scale[row / p.J];
             }
-            float st_shift = 0.f, st_sum = 0.f, st_sq = 0.f;
+            float st_shift = 0.f;
+            float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -341,11 +342,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                         v[4 * i + 3] = x.w + rscale * (__uint_as_float(r[4 * i + 3]) + bb.w);
                     }
                     if (ch == 0) st_shift = v[0];
+                    {
+                        // packed fp32x2 accumulation (two independent chains; combined after the last chunk)
+                        const float2 nsh = make_float2(-st_shift, -st_shift);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float d = v[i] - st_shift;
-                        st_sum += d;
-                        st_sq = fmaf(d, d, st_sq);
+                        for (int i = 0; i < 16; ++i) {
+                            const float2 d = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), nsh);
+                            st_sum2 = __fadd2_rn(st_sum2, d);
+                            st_sq2 = __ffma2_rn(d, d, st_sq2);
+                        }
                     }
                 } else if (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_SPLIT || EPI == EPI_BIAS_GELU_PAIR) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.vec0 + col0);
@@ -479,8 +484,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                 if (row_ok && p.stats_out) {
                     float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n_idx * 2 + half) * 3;
                     so[0] = st_shift;
-                    so[1] = st_sum;
-                    so[2] = st_sq;
+                    so[1] = st_sum2.x + st_sum2.y;
+                    so[2] = st_sq2.x + st_sq2.y;
                 }
             }
             acc ^= 1;

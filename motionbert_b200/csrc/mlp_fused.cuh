@@ -352,7 +352,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
                         tma_load_2d(buf[rc & 1], &tmR, &my_rbar[rc & 1], n * 256 + half * 128, rowb);
                     }
                     __syncwarp();
-                    float st_shift = 0.f, st_sum = 0.f, st_sq = 0.f;
+                    float st_shift = 0.f;
+                    float2 st_sum2 = make_float2(0.f, 0.f), st_sq2 = make_float2(0.f, 0.f);
                     mbar_wait(&tfull_bar[acc], acc_phase);
                     tc_fence_after();
                     uint32_t r[32];
@@ -389,11 +390,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
                                 v[4 * i + 3] = x.w + rscale * (__uint_as_float(r[4 * i + 3]) + bb.w);
                             }
                             if (ch == 0) st_shift = v[0];
+                            {
+                                // packed fp32x2 accumulation (two independent chains; combined after the last chunk)
+                                const float2 nsh = make_float2(-st_shift, -st_shift);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float d = v[i] - st_shift;
-                                st_sum += d;
-                                st_sq = fmaf(d, d, st_sq);
+                                for (int i = 0; i < 16; ++i) {
+                                    const float2 d = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), nsh);
+                                    st_sum2 = __fadd2_rn(st_sum2, d);
+                                    st_sq2 = __ffma2_rn(d, d, st_sq2);
+                                }
                             }
                         }
                         __syncwarp();                                      // all lanes have consumed buf[b]; older stores retired
@@ -413,8 +418,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
                     if (row_ok && p.stats_out) {
                         float* so = p.stats_out + (static_cast<size_t>(row) * ngrp_out + n * 2 + half) * 3;
                         so[0] = st_shift;
-                        so[1] = st_sum;
-                        so[2] = st_sq;
+                        so[1] = st_sum2.x + st_sum2.y;
+                        so[2] = st_sq2.x + st_sq2.y;
                     }
                 }
                 acc ^= 1;
