@@ -455,7 +455,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA,   // bf16 3D (K, M, plane)
                     for (int i = 0; i < 16; ++i) {
                         if (EPI == EPI_BIAS_GELU_PAIR) {
                             const __nv_bfloat162 y2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                            const __nv_bfloat162 g2 = __floats2bfloat162_rn(gelu_erf(v[2 * i]), gelu_erf(v[2 * i + 1]));
+                            const float2 gl = gelu_erf2(make_float2(v[2 * i], v[2 * i + 1]));
+                            const __nv_bfloat162 g2 = __floats2bfloat162_rn(gl.x, gl.y);
                             hi[i] = *reinterpret_cast<const uint32_t*>(&y2);
                             lo[i] = *reinterpret_cast<const uint32_t*>(&g2);
                         } else {

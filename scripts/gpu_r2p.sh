@@ -14,7 +14,7 @@ cap() {  # name, kernel regex, count
   ncu -i /tmp/${TAG}_$1.ncu-rep --page source --csv > gpurun_out/${TAG}_$1_source.csv 2>/dev/null
   ls -la /tmp/${TAG}_$1.ncu-rep gpurun_out/${TAG}_$1_raw.csv gpurun_out/${TAG}_$1_source.csv
 }
-cap gemm gemm2_kernel 4
+cap gemm "gemm2_kernel|mlp_fused" 4
 cap attn attn_ 2
 cap fuse fuse_kernel 1
 du -sh gpurun_out; tail -n 3 gpurun_out/${TAG}_gemm.log gpurun_out/${TAG}_attn.log

@@ -65,11 +65,11 @@ for part in ("gemm", "attn", "fuse"):
         out["kernels"].append(k)
 math = sys.argv[2] if len(sys.argv) > 2 else "f16c"
 out["math"] = math
-gem = [k for k in out["kernels"] if "gemm2_kernel<" in k["kernel"]]
+gem = [k for k in out["kernels"] if "gemm2_kernel<" in k["kernel"] or "mlp_fused_kernel" in k["kernel"]]
 if gem:
     out["gemm_avg_dram_bytes_per_launch"] = sum(k["dram_bytes"] for k in gem) / len(gem)
     out["gemm_traffic_note"] = ("mean of dram__bytes_read.sum + dram__bytes_write.sum over one captured launch of each "
-                                "GEMM flavour (qkv, proj, fc1, fc2: 20 launches each per forward), ncu --set full")
+                                "GEMM-class launch of a forward's first four (qkv, proj, fused MLP, ...: 20 launches each per forward), ncu --set full")
 json.dump(out, open(f"profiles/{tag}_ncu_summary.json", "w"), indent=1)
 print(f"launch list ({out['launch_list_total_ms']:.2f} ms under ncu, serialised):")
 for e in out["launch_list"]:
