@@ -14,9 +14,11 @@ ap.add_argument("--model", default="base")
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--frames", type=int, default=243)
 ap.add_argument("--math", default="f16c")
+ap.add_argument("--kernel-flags", type=lambda v: int(v, 0), default=0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 m = build_model(a.model, dev, a.math)
+m._kernel_flags = a.kernel_flags
 x = synthetic_clips(a.batch, a.frames, 1).to(dev)
 with torch.no_grad():
     for _ in range(2):
