@@ -38,6 +38,8 @@ class DSTformerFunction(torch.autograd.Function):
                                "operation' here)")
         x, rep, saved = ctx.saved_tensors
         g = grad.contiguous().float()
+        if g.data_ptr() & 15:                       # a contiguous slice of a gathered gradient (nn.DataParallel): 16-byte reads
+            g = g.clone()
         grads, d_x = mod._launch_backward(x, rep, saved, None if ctx.return_rep else g,
                                           g if ctx.return_rep else None, ctx.dp_scale, ctx.needs_input_grad[1])
         skip = mod._head_param_slots() if ctx.return_rep else ()      # the head is not part of get_representation()

@@ -106,6 +106,17 @@ static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle_bytes, int elem_bytes = 2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  A fresh host thread
+    // (nn.DataParallel's replica threads, train.py:256) whose only runtime calls so far were cudaGetDevice / cached
+    // allocations has none bound yet (CUDA_ERROR_INVALID_CONTEXT): bind the device's primary context once per thread.
+    {
+        static thread_local int bound_dev = -1;
+        int dev = -1;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_dev) {
+            cudaFree(nullptr);
+            bound_dev = dev;
+        }
+    }
     if (reinterpret_cast<uintptr_t>(base) & 15) return fail(MB_ERR_ALIGN, "tensor map base not 16-byte aligned");
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bdim[5], estr[5];

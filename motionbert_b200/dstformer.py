@@ -300,6 +300,12 @@ class DSTformer(nn.Module):
                 if t.dtype != torch.float32 or not t.is_contiguous():
                     t = t.float().contiguous()
                     keep.append(t)
+                if t.data_ptr() & 15:
+                    # nn.DataParallel replicas hold their parameters as slices of ONE coalesced broadcast buffer
+                    # (comm.broadcast_coalesced): everything after the 3-element head.bias sits at 4-byte alignment.
+                    # The kernels read parameters with 16-byte accesses: hand them an aligned copy.
+                    t = t.clone()
+                    keep.append(t)
                 if t.numel() != st.numels[i]:
                     raise RuntimeError(f"parameter {i} has {t.numel()} elements, library expects {st.numels[i]}")
             ptrs[i] = t.data_ptr()
@@ -471,6 +477,8 @@ class DSTformer(nn.Module):
                 bounds[phases[i] + 1] = off
             flat = torch.zeros(off, dtype=torch.float32, device=device)
             grads = [flat[offs[i]:offs[i] + p.numel()].view(p.shape) for i, p in enumerate(params)]
+            # (16-byte aligned parameter storage: see _ensure_packed -- replicas of nn.DataParallel are not)
+            params = [p if not (p.data_ptr() & 15) else p.detach().clone() for p in params]
             pp = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
             gp = (ctypes.c_void_p * len(params))(*[g.data_ptr() for g in grads])
             d_x = torch.empty_like(x) if want_dx else None
