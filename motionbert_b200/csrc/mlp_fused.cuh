@@ -16,10 +16,16 @@
 //     (cp.async.bulk.wait_group: both sides of the hand-over are async-proxy accesses of L2) and gates the 8 K blocks of
 //     fc2 that read those 256 hidden columns;
 //   * tile order: block by block, fc1 0..NT1-1 then fc2 0..NT2-1.  The hidden rows live in a per-pair slot of a small
-//     ring (pairs x 256 rows x hidden x 4 B = 77 MB for 74 pairs, L2::evict_last) that is rewritten every token block.
-//     fc2 tile 0 starts on hidden columns 0..767 while the epilogue of the last fc1 tile still runs; only its last
-//     quarter waits for it.  (Measured and dropped, profiles/README.md round 2: interleaving the fc2 tiles of block k-1
-//     with the fc1 tiles of block k -- better MMA/epilogue overlap on paper, 5 % slower at the board's power cap.)
+//     ring (pairs x 256 rows x hidden x 4 B = 77 MB for 74 pairs) that is rewritten every token block, with an L2 policy
+//     per access class: ring stores / reloads L2::evict_last, everything touched once (fp32 residual in, both outputs,
+//     the last pass over the x rows) L2::evict_first.  Measured at BASELINE config 2 (ncu, profiles/r02l_mlp_dram_*.csv):
+//     15.9 GB of DRAM traffic per launch against 17.4 GB without the policies and 18.0 GB for the two GEMM launches
+//     -- the reloads hit L2 more often (read hit rate 69 -> 72-75 %), but ~300 MB of streaming traffic pass through
+//     the 126 MB L2 per token-block period and the ring's WRITES still miss (write hit rate < 5 %): the ring is a
+//     partial win, not an HBM-free hand-over.  fc2 tile 0 starts on hidden columns 0..767 while the epilogue of the
+//     last fc1 tile still runs; only its last quarter waits for it.  (Measured and dropped, profiles/README.md round 2:
+//     interleaving the fc2 tiles of block k-1 with the fc1 tiles of block k -- the same number of SM cycles, 5 % slower
+//     at the board's power cap.)
 //     WAR on a ring slot is excluded by the pipeline itself: the first hidden store of token block k+1 follows the tfull
 //     commit of its fc1 tile 0, which follows (in-order tensor pipe) every MMA -- hence every operand load -- of token
 //     block k's fc2 tiles.
@@ -122,8 +128,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1,   // x as F16C rows  
     const int NT1 = p.H / 256, NT2 = p.C / 256;
     const int KB1 = p.C / 32, KB2 = p.H / 32;
     const int rounds = pair < num_mp ? (num_mp - pair + npairs - 1) / npairs : 0;   // token blocks of this pair
-    // L2 policy: the hidden ring must survive ~300 MB of streaming traffic per token-block period in a 126 MB L2 -> ring lines
-    // evict_last, everything that is touched once (fp32 residual in, both outputs, the last pass over the x rows) evict_first
+    // L2 policy per access class (see the header): ring lines evict_last, touched-once traffic evict_first
     const uint64_t hpol = p.l2_hint ? L2_EVICT_LAST : L2_EVICT_NORMAL;
     const uint64_t spol = p.l2_hint ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 

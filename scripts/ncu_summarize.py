@@ -67,9 +67,39 @@ math = sys.argv[2] if len(sys.argv) > 2 else "f16c"
 out["math"] = math
 gem = [k for k in out["kernels"] if "gemm2_kernel<" in k["kernel"] or "mlp_fused_kernel" in k["kernel"]]
 if gem:
-    out["gemm_avg_dram_bytes_per_launch"] = sum(k["dram_bytes"] for k in gem) / len(gem)
-    out["gemm_traffic_note"] = ("mean of dram__bytes_read.sum + dram__bytes_write.sum over one captured launch of each "
-                                "GEMM-class launch of a forward's first four (qkv, proj, fused MLP, ...: 20 launches each per forward), ncu --set full")
+    # launch-weighted mean over the distinct GEMM-class kernels captured (first capture of each), weights = launches per
+    # forward from the launch list
+    seen, num, den = set(), 0.0, 0.0
+    for k in gem:
+        name = k["kernel"].replace("void ", "").strip()
+        if name in seen:
+            continue
+        seen.add(name)
+        w = next((e["launches"] for e in out["launch_list"] if e["kernel"].replace("void ", "").strip().startswith(name[:28])), 1)
+        num += w * k["dram_bytes"]
+        den += w
+    out["gemm_avg_dram_bytes_per_launch"] = num / den
+    out["gemm_traffic_note"] = ("launch-weighted mean of dram__bytes_read.sum + dram__bytes_write.sum over one captured launch of each "
+                                "GEMM-class kernel (qkv, proj, fused MLP: 20 launches each per forward), ncu --set full")
+# DRAM bytes of the fused MLP kernel with the final build's L2 policies (metrics-only ncu pass, optional third argument)
+if len(sys.argv) > 3 and os.path.exists(sys.argv[3]):
+    rr = [r for r in csv.reader(open(sys.argv[3])) if len(r) > 10]
+    h = rr[0]
+    n, v, idc = h.index("Metric Name"), h.index("Metric Value"), h.index("ID")
+    per = collections.OrderedDict()
+    for r in rr[1:]:
+        if r[n].startswith("dram__bytes"):
+            per[r[idc]] = per.get(r[idc], 0.0) + float(r[v].replace(",", ""))
+    out["mlp_fused_dram_bytes_final_build"] = list(per.values())
+    out["mlp_fused_dram_note"] = ("final build (L2::evict_last ring, evict_first streaming): first launch = a block-interior MLP "
+                                  "(fp32 + rows out), second = a block-final one (fp32 out only); the --set full capture above is "
+                                  "the build before the L2 policies")
+    if gem and per:
+        mlp_w = 20.0
+        old = next((k["dram_bytes"] for k in gem if "mlp_fused" in k["kernel"]), None)
+        if old is not None:
+            new = sum(per.values()) / len(per)
+            out["gemm_avg_dram_bytes_per_launch"] += mlp_w * (new - old) / den
 json.dump(out, open(f"profiles/{tag}_ncu_summary.json", "w"), indent=1)
 print(f"launch list ({out['launch_list_total_ms']:.2f} ms under ncu, serialised):")
 for e in out["launch_list"]:
