@@ -92,3 +92,38 @@ def test_sass_contains_blackwell_instructions():
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTCQMMA" in sass and "UTMALDG" in sass and "LDTM" in sass and "STTM" in sass
     assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_kernel_flag_constants_match_the_header():
+    """MB_FLAG_* / MB_MATH_* of the ctypes binding are the header's values (the flags are A/B switches: a drifted constant
+    would silently select another kernel path)."""
+    src = open(os.path.join(ROOT, "include", "motionbert_b200.h")).read()
+    flags = {k: int(v, 16) for k, v in re.findall(r"#define\s+(MB_FLAG_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+)u", src)}
+    assert len(flags) >= 8 and len(set(flags.values())) == len(flags)          # distinct bits
+    for k, v in flags.items():
+        assert getattr(_lib, k) == v, k
+        assert v & (v - 1) == 0, k                                              # single bit each
+    maths = {k: int(v) for k, v in re.findall(r"(MB_MATH_[A-Z0-9]+)\s*=\s*(\d+)", src)}
+    assert maths == {"MB_MATH_BF16X3": 0, "MB_MATH_BF16": 1, "MB_MATH_F16C": 2}
+    for k, v in maths.items():
+        assert getattr(_lib, k) == v
+
+
+def test_product_library_contains_the_fused_mlp_kernel_with_blackwell_instructions():
+    """mlp_fused_kernel ships in the product library and is a tcgen05 / TMA kernel: UTCHMMA + UTCQMMA (the F16C pass pair),
+    LDTM, UTMALDG and UTMASTG in its SASS, no legacy HMMA."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    build.build()
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    i = sass.find("Function : _ZN2mb16mlp_fused_kernel")
+    assert i >= 0
+    j = sass.find("Function : ", i + 20)
+    body = sass[i:j if j > 0 else len(sass)]
+    for mnem in ("UTCHMMA.2CTA", "UTCQMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR"):
+        assert mnem in body, mnem
+    assert "HMMA.16816" not in body and " HMMA." not in body
+    assert body.count("MUFU.EX2") >= 100 and body.count("MUFU.RCP") < 30       # one-MUFU GELU (RCP only in the LN statistics)
