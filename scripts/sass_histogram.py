@@ -25,7 +25,7 @@ for line in sass.splitlines():
         continue
     if cur is None:
         continue
-    m = re.search(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.search(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m:
         op = m.group(1)
         per[cur]["_total"] += 1
