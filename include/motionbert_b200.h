@@ -198,14 +198,17 @@ int mb_augment2d(const float* x, int cin, int B, int F, int J, int K, int noise,
                  float s, const float* mask_u, const float* maskT_u, float mask_ratio, float mask_T_ratio, float* out,
                  void* stream);
 
-/* Number of kernels one mb_forward call launches for this (B, F) (for bench.py's gpu_launches). */
+/* Number of kernels one mb_forward call launches (for bench.py's gpu_launches): 88 for depth 5 in F16C mode (one kernel
+ * per MLP sublayer), 108 with MB_FLAG_MLP_SPLIT and in the bf16 modes. */
 int mb_forward_launch_count(const MbEncoder* enc, int want_out, uint32_t flags);
 
 /* Per-kernel-class device timing for bench.py's roofline: while enabled, mb_forward brackets every launch
  * with CUDA events on the caller's stream.  mb_profile_read synchronises, returns the accumulated
  * milliseconds and launch counts per class since the last read and resets them.
- * classes: 0 gemm LN->qkv, 1 gemm LN->fc1+GELU, 2 gemm proj/fc2+residual, 3 gemm tail (rep), 4 temporal attention,
- *          5 spatial attention, 6 embed, 7 fusion, 8 head.   Not thread-safe; measurement only. */
+ * classes: 0 gemm LN->qkv, 1 the MLP sublayer's first launch (F16C: the fused fc1+GELU+fc2+residual kernel = the whole
+ *          sublayer; MB_FLAG_MLP_SPLIT / bf16 modes: gemm LN->fc1+GELU), 2 gemm proj+residual (and fc2+residual in the
+ *          two-GEMM form), 3 gemm tail (rep), 4 temporal attention, 5 spatial attention, 6 embed, 7 fusion, 8 head.
+ *          Not thread-safe; measurement only. */
 #define MB_PROFILE_CLASSES 9
 int mb_profile_enable(MbEncoder* enc, int on);
 int mb_profile_read(MbEncoder* enc, float* ms_by_class, int* launches_by_class);
