@@ -87,7 +87,11 @@ class Emu:
     def __init__(self, cfg, P, lin_scheme, att_scheme):
         self.cfg = cfg
         self.P = {k: torch.from_numpy(v).to(D) for k, v in P.items()}
-        self.mm = make_mm(lin_scheme)
+        # lin_scheme: one scheme for every linear, or "default;fc2=scheme;qkv=scheme;..." (per-kind overrides: qkv, proj, fc1,
+        # fc2, pre_logits)
+        base, *over = lin_scheme.split(";")
+        self.mm = make_mm(base)
+        self.mm_by_kind = {kv.split("=")[0]: make_mm(kv.split("=")[1]) for kv in over}
         qk, _, pv = att_scheme.partition("|")
         self.amm = make_mm(qk)
         self.pvmm = make_mm(pv or qk)
@@ -103,11 +107,11 @@ class Emu:
         mu = x.mean(-1, keepdim=True)
         var = ((x - mu) ** 2).mean(-1, keepdim=True)
         rstd = 1.0 / torch.sqrt(var + self.cfg.eps)
-        acc = self.mm(x, Wf)
+        acc = self.mm_by_kind.get(lin.split(".")[-1], self.mm)(x, Wf)
         return rstd * (acc - mu * s) + c
 
     def linear(self, x, lin):
-        return self.mm(x, self.P[lin + ".weight"]) + self.P[lin + ".bias"]
+        return self.mm_by_kind.get(lin.split(".")[-1], self.mm)(x, self.P[lin + ".weight"]) + self.P[lin + ".bias"]
 
     def attention(self, x, ln, p, mode, F):
         cfg = self.cfg
@@ -166,13 +170,17 @@ def main():
               f"{np.linalg.norm(out0, axis=-1).mean():.4f}")
         for lin, att in (("fp32", "fp32"), ("bf16x3", "bf16x3"), ("f16+e5m2", "f16+e5m2"), ("f16+e5m2", "exact"),
                          ("exact", "f16+e5m2"), ("f16", "f16"), ("f16w2", "f16"), ("exact", "f16"),
-                         ("exact", "f16+e5m2|f16c_pv_ph"), ("bf16", "bf16")):
+                         ("exact", "f16+e5m2|f16c_pv_ph"), ("bf16", "bf16"),
+                         # candidates for a cheaper fused MLP: the GELU'd hidden activation as plain fp16 in fc2 (no lo8 plane:
+                         # one e5m2 MMA and the lo8 encode of the epilogue-bound fc1 phase less), weights still compensated
+                         ("f16+e5m2;fc2=f16c_pv_ph", "f16+e5m2"), ("f16+e5m2;fc2=f16", "f16+e5m2"),
+                         ("f16+e5m2;fc2=f16c_pv_ph;proj=f16c_pv_ph", "f16+e5m2")):
             out, rep = Emu(cfg, P, lin, att).forward(x)
             tok = np.linalg.norm((rep - rep0).reshape(-1, rep.shape[-1]), axis=-1) / \
                 np.linalg.norm(rep0.reshape(-1, rep.shape[-1]), axis=-1)
             disp = np.linalg.norm(out - out0, axis=-1).mean()
             rel = disp / np.linalg.norm(out0, axis=-1).mean()
-            print(f"  linears {lin:9s} attention {att:22s}: rep per-token rel {tok.mean():.2e} / {tok.max():.2e}   "
+            print(f"  linears {lin:40s} attention {att:22s}: rep per-token rel {tok.mean():.2e} / {tok.max():.2e}   "
                   f"out displacement {disp:.2e} abs, {rel:.2e} rel")
 
 
