@@ -382,6 +382,62 @@ def gpu_eager_baseline(model, model_name, T, device, batch=32, iters=3):
     return res
 
 
+def gpu_eager_train_baseline(model, model_name, T, device, batch=16, iters=3):
+    """SURVEY.md 8d, config 3's GPU comparator: the reference's op sequence (the torch port of lib/model/DSTformer.py) as a
+    TRAINING step in torch eager on this device -- forward under torch.autocast(bf16) (and, second entry, plain fp32 with
+    TF32 matmuls), an MPJPE-style loss, autograd backward, torch's fused AdamW.  A reported baseline at a batch that fits the
+    eager activations (the reference materialises the (B, 8, 17, T, T) score tensors); nothing of it is on the product path."""
+    from oracle import dstformer_oracle as O
+    from oracle import dstformer_torch_cpu as OT
+    cfg = O.BASE if model_name == "base" else O.LITE
+    P = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in model.state_dict().items()}
+    opt = torch.optim.AdamW(list(P.values()), lr=1e-5, weight_decay=0.01, fused=(device.type == "cuda"))
+    x = synthetic_clips(batch, T, seed=5).to(device)
+    gt = synthetic_clips(batch, T, seed=6).to(device)
+    res = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    fwd = OT.forward.__wrapped__          # the port itself (its public entry is wrapped in torch.no_grad for the CPU baseline)
+
+    def step(autocast):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast(device.type, dtype=torch.bfloat16, enabled=autocast):
+            out, _rep = fwd(P, x, cfg.depth, cfg.num_heads, cfg.eps)
+        loss = (out.float() - gt).norm(dim=-1).mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    try:
+        for name, autocast, tf32 in (("bf16_autocast", True, False), ("tf32", False, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                step(autocast)
+            if device.type == "cuda":
+                torch.cuda.synchronize(device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    step(autocast)
+                e1.record()
+                torch.cuda.synchronize(device)
+                ms = e0.elapsed_time(e1) / iters
+            else:                                                   # (CPU: only used to exercise this function in the tests)
+                t0 = time.perf_counter()
+                for _ in range(iters):
+                    step(autocast)
+                ms = (time.perf_counter() - t0) * 1e3 / iters
+            res[name] = {"value": batch / (ms * 1e-3), "unit": "sequences/sec", "ms_per_step": ms}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    res["what"] = (f"torch eager training step (port of lib/model/DSTformer.py forward, autograd backward, torch.optim.AdamW fused) "
+                   f"on the same device, B={batch}, T={T}, {iters} iterations after 2 warm-ups; torch {torch.__version__}")
+    del P, x, gt, opt
+    if device.type == "cuda":
+        torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -601,6 +657,9 @@ def main():
         if world == 1:
             guarded("gpu_eager_baseline",
                     lambda: gpu_eager_baseline(build_model(args.model, device, args.math), args.model, T, device))
+            # ... and its training step (config 3's comparator: autocast-bf16 / TF32 eager fwd + autograd bwd + AdamW)
+            guarded("gpu_eager_train_baseline",
+                    lambda: gpu_eager_train_baseline(build_model(args.model, device, args.math), args.model, T, device))
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_rate(args.model, T, budget_s=20.0)
