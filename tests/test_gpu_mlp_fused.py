@@ -79,3 +79,26 @@ def test_fused_mlp_many_token_blocks_per_cta_pair(cuda_device, model, B, F):
         o_f2, r_f2 = _run(m, xt)
         assert torch.equal(r_f, r_f2) and torch.equal(o_f, o_f2), label
         assert torch.equal(r_f, r_s) and torch.equal(o_f, o_s), label
+
+
+@pytest.mark.parametrize("dim,ratio,B,F", [(512, 4, 3, 50), (256, 1, 3, 50), (256, 2, 2, 33), (512, 1, 2, 40), (512, 4, 8, 243)])
+def test_fused_mlp_tile_geometries_no_shipped_config_uses(cuda_device, dim, ratio, B, F):
+    """hidden = 2048 (8 fc1 tiles per token block, the kernel's maximum), hidden = C (one fc1 tile), C = hidden = 512 (2 + 2):
+    bit equality with the two-GEMM form, and parity with the float64 oracle (profiles/r02m_mlp_geometry_check.log)."""
+    cfg = O.EncoderConfig(dim_feat=dim, mlp_ratio=ratio, depth=2)
+    P = O.make_params(cfg, 5)
+    xn = O.make_input(B, F, cfg.num_joints, 9)
+    xt = torch.from_numpy(xn).to(cuda_device)
+    m = build_module(cfg, P, cuda_device)
+    with torch.no_grad():
+        m._kernel_flags = _lib.MB_FLAG_MLP_SPLIT
+        r_s = m.get_representation(xt).clone()
+        m._kernel_flags = 0
+        r_f = m.get_representation(xt).clone()
+        m._kernel_flags = _lib.MB_FLAG_MLP_NO_RING
+        r_n = m.get_representation(xt).clone()
+    assert torch.isfinite(r_f).all() and torch.equal(r_f, r_s) and torch.equal(r_n, r_s)
+    if B * F < 400:
+        _o, r_ref = O.forward(P, xn[:1], cfg, np.float64)
+        d = r_f[:1].cpu().numpy().astype(np.float64) - r_ref
+        assert float((np.linalg.norm(d, axis=-1) / np.linalg.norm(r_ref, axis=-1)).max()) < 1e-3
