@@ -98,7 +98,9 @@ int mb_param_info(const MbEncoder* enc, int index, char* name, int name_cap, int
 
 /* Packed weights: bf16 hi/lo planes of every nn.Linear weight with the preceding LayerNorm's affine
  * folded in, plus the small fp32 vectors.  Re-run after every optimizer step / load_state_dict.
- *   params : host array of mb_param_count() device pointers (fp32, contiguous) in state_dict order. */
+ *   params : host array of mb_param_count() device pointers (fp32, contiguous, 16-BYTE ALIGNED: the kernels read
+ *            parameters with 128-bit accesses -- slices of a coalesced buffer such as nn.DataParallel's broadcast replicas
+ *            are not; the Python class hands over aligned copies) in state_dict order. */
 int mb_packed_bytes(const MbEncoder* enc, size_t* bytes);
 int mb_pack_weights(MbEncoder* enc, const float* const* params, void* packed, void* stream);
 
@@ -131,7 +133,8 @@ int mb_forward_host(MbEncoder* enc, const void* packed, const float* x_host, flo
  * mb_backward      : gradients of all mb_param_count() parameters for given d_out (B,F,J,dim_out) and/or d_rep
  *                    (B,F,J,dim_rep) (either may be NULL).  bf16 single-pass tensor-core arithmetic with fp32
  *                    accumulation; qkv / hidden activations / attention probabilities are recomputed, not stored.
- *     params : the same device pointers given to mb_pack_weights (fp32, state_dict order)
+ *     params : the same device pointers given to mb_pack_weights (fp32, state_dict order, 16-byte aligned);
+ *              d_out / d_rep 16-byte aligned as well
  *     grads  : device pointers, same order and sizes, ZERO-FILLED by the caller (the kernels accumulate into them)
  *     x, rep, saved : the input / output / saved region of the matching mb_forward_train call
  *     workspace : mb_backward_workspace_bytes() bytes, 1024-byte aligned (independent of the forward workspace)
